@@ -1,0 +1,285 @@
+// extern "C" surface declared in include/bayesic_b200.h.  Plain pointers and sizes only.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "plan.h"
+
+
+namespace bb {
+int plan_infer(bb_plan*, const bb_tensor_arg*, int32_t, bb_result_info*, int64_t*);
+int plan_execute(bb_plan*, const bb_tensor_arg*, int32_t, void* const*, void*, int64_t, cudaStream_t);
+int plan_validate(const bb_node_desc*, int32_t, const int32_t*, int32_t, int32_t);
+// suffstats_sm100.cu (accumulating variant used by the host-streaming path)
+int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,
+                            int64_t workspace_bytes, bool accumulate, cudaStream_t stream);
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" {
+
+BB_API int bb_abi_version(void) { return BB_ABI_VERSION; }
+
+BB_API const char* bb_last_error(void) { return get_error(); }
+
+BB_API int64_t bb_launch_count(void) { return g_launch_count; }
+
+BB_API int bb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  BB_CUDA_OK(cudaGetDevice(&dev));
+  int sms = 0, major = 0, minor = 0;
+  BB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  BB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  BB_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = major;
+  if (cc_minor) *cc_minor = minor;
+  return BB_OK;
+}
+
+BB_API int bb_plan_create(const bb_node_desc* nodes, int32_t n_nodes, const int32_t* outputs,
+                   int32_t n_outputs, int32_t n_inputs, bb_plan** plan) {
+  if (plan == nullptr) { set_error("null plan out-pointer"); return BB_ERR_INVALID; }
+  *plan = nullptr;
+  BB_TRY(plan_validate(nodes, n_nodes, outputs, n_outputs, n_inputs));
+  bb_plan* p = new (std::nothrow) bb_plan();
+  if (p == nullptr) { set_error("out of host memory"); return BB_ERR_INVALID; }
+  p->nodes.assign(nodes, nodes + n_nodes);
+  p->outputs.assign(outputs, outputs + n_outputs);
+  p->n_inputs = n_inputs;
+  *plan = p;
+  return BB_OK;
+}
+
+BB_API int bb_plan_destroy(bb_plan* plan) {
+  delete plan;
+  return BB_OK;
+}
+
+BB_API int bb_plan_infer(bb_plan* plan, const bb_tensor_arg* inputs, int32_t n_inputs,
+                  bb_result_info* results, int64_t* workspace_bytes) {
+  return plan_infer(plan, inputs, n_inputs, results, workspace_bytes);
+}
+
+BB_API int bb_plan_execute(bb_plan* plan, const bb_tensor_arg* inputs, int32_t n_inputs,
+                    void* const* out_ptrs, void* workspace, int64_t workspace_bytes, void* stream) {
+  return plan_execute(plan, inputs, n_inputs, out_ptrs, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_plan_last_launch_count(bb_plan* plan, int32_t* count) {
+  if (plan == nullptr || count == nullptr) { set_error("null argument"); return BB_ERR_INVALID; }
+  *count = plan->last_launches;
+  return BB_OK;
+}
+
+// ---- fused statistics ------------------------------------------------------------
+
+static int64_t generic_suffstats_workspace(int64_t n, int32_t d) {
+  // float32 S2 + split-K partials + float32 S1 + float64 reduce scratch
+  return align_up(static_cast<int64_t>(d) * d * 4, 256) + gemm_workspace_bytes(d, d, n, 1) +
+         align_up(static_cast<int64_t>(d) * 4, 256) + reduce_sum_scratch_bytes(d) + 1024;
+}
+
+BB_API int64_t bb_suffstats_gaussian_workspace(int64_t n, int32_t d) {
+  int64_t need = generic_suffstats_workspace(n, d);
+  if (d >= 4 && d <= 64 && d % 4 == 0) need = std::max(need, suffstats_tc_workspace(n));
+  return need;
+}
+
+static int suffstats_device(const float* X, int64_t n, int32_t d, double* sum_x, double* sum_xxT,
+                            void* workspace, int64_t workspace_bytes, bool accumulate,
+                            cudaStream_t st) {
+  if (X == nullptr || sum_xxT == nullptr || n < 0 || d < 1) {
+    set_error("suffstats_gaussian: bad arguments (n=%lld d=%d)", static_cast<long long>(n), d);
+    return BB_ERR_INVALID;
+  }
+  if (workspace_bytes < bb_suffstats_gaussian_workspace(n, d)) {
+    set_error("suffstats_gaussian: workspace %lld < %lld bytes", static_cast<long long>(workspace_bytes),
+              static_cast<long long>(bb_suffstats_gaussian_workspace(n, d)));
+    return BB_ERR_WORKSPACE;
+  }
+  if (n == 0) {
+    if (!accumulate) {
+      BB_CUDA_OK(cudaMemsetAsync(sum_xxT, 0, sizeof(double) * d * d, st));
+      if (sum_x) BB_CUDA_OK(cudaMemsetAsync(sum_x, 0, sizeof(double) * d, st));
+    }
+    return BB_OK;
+  }
+  if (suffstats_tc_supported(n, d, X))
+    return launch_suffstats_tc_acc(X, n, d, sum_x, sum_xxT, workspace, workspace_bytes, accumulate, st);
+  if (accumulate) {
+    set_error("suffstats_gaussian: accumulating mode needs d <= 64, d %% 4 == 0");
+    return BB_ERR_UNSUPPORTED;
+  }
+  // generic path: split-K GEMM for X^T X and a column reduction for sum x
+  char* ws = static_cast<char*>(workspace);
+  float* s2f = reinterpret_cast<float*>(ws);
+  ws += align_up(static_cast<int64_t>(d) * d * 4, 256);
+  void* gemm_ws = ws;
+  ws += gemm_workspace_bytes(d, d, n, 1);
+  float* s1f = reinterpret_cast<float*>(ws);
+  ws += align_up(static_cast<int64_t>(d) * 4, 256);
+  void* red_ws = ws;
+  BB_TRY(launch_gemm(X, X, s2f, d, d, n, 1, 0, 1, d, 0, d, 1, gemm_ws, st));
+  BB_TRY(launch_f32_to_f64(s2f, sum_xxT, static_cast<int64_t>(d) * d, st));
+  if (sum_x != nullptr) {
+    View in, out;
+    in.ptr = const_cast<float*>(X);
+    in.ndim = 2; in.shape[0] = n; in.shape[1] = d; in.set_contiguous_strides();
+    out.ptr = s1f; out.ndim = 1; out.shape[0] = d; out.set_contiguous_strides();
+    const bool reduce[kMaxDims] = {true, false};
+    BB_TRY(launch_reduce_sum(in, reduce, out, red_ws, st));
+    BB_TRY(launch_f32_to_f64(s1f, sum_x, d, st));
+  }
+  return BB_OK;
+}
+
+BB_API int bb_suffstats_gaussian(const float* X, int64_t n, int32_t d, double* sum_x, double* sum_xxT,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+  return suffstats_device(X, n, d, sum_x, sum_xxT, workspace, workspace_bytes, false,
+                          static_cast<cudaStream_t>(stream));
+}
+
+// Staging pool of the host-streaming entry point: two device chunk buffers, statistics and
+// kernel workspace; grown on demand, kept for the life of the process.
+namespace {
+struct Staging {
+  float* chunk[2] = {nullptr, nullptr};
+  int64_t chunk_bytes = 0;
+  double* stats = nullptr;      // [d*d + d]
+  int64_t stats_doubles = 0;
+  void* ws = nullptr;
+  int64_t ws_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  cudaEvent_t consumed[2] = {nullptr, nullptr};
+  int device = -1;
+};
+Staging g_staging;
+}  // namespace
+
+BB_API int bb_suffstats_gaussian_host(const float* X_host, int64_t n, int32_t d, double* sum_x_host,
+                               double* sum_xxT_host, int64_t chunk_rows, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (X_host == nullptr || sum_xxT_host == nullptr || n < 0 || d < 1) {
+    set_error("suffstats_gaussian_host: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  if (!(d >= 4 && d <= 64 && d % 4 == 0)) {
+    set_error("suffstats_gaussian_host: needs d <= 64 and d %% 4 == 0 (got %d)", d);
+    return BB_ERR_UNSUPPORTED;
+  }
+  if (chunk_rows <= 0) chunk_rows = int64_t(1) << 20;
+  chunk_rows = std::min<int64_t>(std::max<int64_t>(chunk_rows, 128), std::max<int64_t>(n, 128));
+  chunk_rows = (chunk_rows + 127) / 128 * 128;
+  Staging& s = g_staging;
+  int dev = 0;
+  BB_CUDA_OK(cudaGetDevice(&dev));
+  if (s.device != dev) {
+    if (s.device >= 0) { set_error("suffstats_gaussian_host: staging pool bound to device %d", s.device); return BB_ERR_UNSUPPORTED; }
+    s.device = dev;
+    BB_CUDA_OK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      BB_CUDA_OK(cudaEventCreateWithFlags(&s.copied[i], cudaEventDisableTiming));
+      BB_CUDA_OK(cudaEventCreateWithFlags(&s.consumed[i], cudaEventDisableTiming));
+    }
+  }
+  const int64_t need_chunk = chunk_rows * d * static_cast<int64_t>(sizeof(float));
+  if (s.chunk_bytes < need_chunk) {
+    for (int i = 0; i < 2; ++i) {
+      if (s.chunk[i]) BB_CUDA_OK(cudaFree(s.chunk[i]));
+      s.chunk[i] = nullptr;
+      BB_CUDA_OK(cudaMalloc(&s.chunk[i], need_chunk));
+    }
+    s.chunk_bytes = need_chunk;
+  }
+  const int64_t need_stats = static_cast<int64_t>(d) * d + d;
+  if (s.stats_doubles < need_stats) {
+    if (s.stats) BB_CUDA_OK(cudaFree(s.stats));
+    s.stats = nullptr;
+    BB_CUDA_OK(cudaMalloc(&s.stats, need_stats * sizeof(double)));
+    s.stats_doubles = need_stats;
+  }
+  const int64_t need_ws = bb_suffstats_gaussian_workspace(chunk_rows, d);
+  if (s.ws_bytes < need_ws) {
+    if (s.ws) BB_CUDA_OK(cudaFree(s.ws));
+    s.ws = nullptr;
+    BB_CUDA_OK(cudaMalloc(&s.ws, need_ws));
+    s.ws_bytes = need_ws;
+  }
+  double* s2 = s.stats;
+  double* s1 = s.stats + static_cast<int64_t>(d) * d;
+  BB_CUDA_OK(cudaMemsetAsync(s.stats, 0, need_stats * sizeof(double), st));
+  int64_t done = 0;
+  for (int64_t c = 0; done < n; ++c) {
+    const int b = static_cast<int>(c & 1);
+    const int64_t rows = std::min(chunk_rows, n - done);
+    if (c >= 2) BB_CUDA_OK(cudaStreamWaitEvent(s.copy_stream, s.consumed[b], 0));
+    BB_CUDA_OK(cudaMemcpyAsync(s.chunk[b], X_host + done * d, rows * d * sizeof(float),
+                               cudaMemcpyHostToDevice, s.copy_stream));
+    BB_CUDA_OK(cudaEventRecord(s.copied[b], s.copy_stream));
+    BB_CUDA_OK(cudaStreamWaitEvent(st, s.copied[b], 0));
+    BB_TRY(suffstats_device(s.chunk[b], rows, d, s1, s2, s.ws, s.ws_bytes, true, st));
+    BB_CUDA_OK(cudaEventRecord(s.consumed[b], st));
+    done += rows;
+  }
+  BB_CUDA_OK(cudaMemcpyAsync(sum_xxT_host, s2, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
+  if (sum_x_host)
+    BB_CUDA_OK(cudaMemcpyAsync(sum_x_host, s1, sizeof(double) * d, cudaMemcpyDeviceToHost, st));
+  BB_CUDA_OK(cudaStreamSynchronize(st));
+  return BB_OK;
+}
+
+BB_API int bb_release_staging(void) {
+  Staging& s = g_staging;
+  if (s.device < 0) return BB_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (s.chunk[i]) cudaFree(s.chunk[i]);
+    if (s.copied[i]) cudaEventDestroy(s.copied[i]);
+    if (s.consumed[i]) cudaEventDestroy(s.consumed[i]);
+  }
+  if (s.stats) cudaFree(s.stats);
+  if (s.ws) cudaFree(s.ws);
+  if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+  s = Staging();
+  return BB_OK;
+}
+
+BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xxT, double n,
+                                const double* E_Lambda, const double* E_Lambda_mu, double E_muLmu,
+                                double E_logdet, int32_t d, double* out, void* stream) {
+  if (!sum_x || !sum_xxT || !E_Lambda || !E_Lambda_mu || !out || d < 1) {
+    set_error("gaussian_expected_loglik: null argument");
+    return BB_ERR_INVALID;
+  }
+  return launch_gaussian_expected_loglik(sum_x, sum_xxT, n, E_Lambda, E_Lambda_mu, E_muLmu, E_logdet,
+                                         d, out, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_logsoftmax_rows(const float* logits, int64_t n, int32_t k, float* log_resp, float* lse,
+                       double* sum_lse, void* stream) {
+  if (!logits || !log_resp || n < 0) { set_error("logsoftmax_rows: bad arguments"); return BB_ERR_INVALID; }
+  return launch_logsoftmax_rows(logits, n, k, log_resp, lse, sum_lse, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int64_t bb_suffstats_weighted_workspace(int64_t n, int32_t d, int32_t k) {
+  return weighted_stats_workspace(n, d, k) + 256;
+}
+
+BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int32_t d, int32_t k, double* Nk,
+                          double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
+  if (!X || !R || !sum_rxx || n < 0) { set_error("suffstats_weighted: bad arguments"); return BB_ERR_INVALID; }
+  return launch_weighted_stats(X, R, n, d, k, Nk, sum_rx, sum_rxx, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// Internal launcher declarations (one per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace bb {
+
+// generic_kernels.cu
+int launch_elementwise(int op, const View& out, const View* operands, int n_operands,
+                       cudaStream_t stream);
+int launch_strided_copy(const View& out, const View& in, cudaStream_t stream);
+int launch_fill(float* out, int64_t n, float value, cudaStream_t stream);
+int launch_eye(float* out, int64_t n, cudaStream_t stream);
+int launch_f64_to_f32(const double* in, float* out, int64_t n, cudaStream_t stream);
+int64_t reduce_sum_scratch_bytes(int64_t kept_total);
+int launch_reduce_sum(const View& in, const bool* reduce_axis, const View& out, void* scratch,
+                      cudaStream_t stream);
+int64_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch);
+int launch_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                int64_t batch, int64_t sAb, int64_t sAm, int64_t sAk, int64_t sBb, int64_t sBk,
+                int64_t sBn, void* workspace, cudaStream_t stream);
+
+// suffstats_sm100.cu
+bool suffstats_tc_supported(int64_t n, int d, const void* x);
+int64_t suffstats_tc_workspace(int64_t n);
+int launch_suffstats_tc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t stream);
+
+// mixture_kernels.cu
+int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_resp, float* lse,
+                           double* sum_lse, cudaStream_t stream);
+int64_t weighted_stats_workspace(int64_t n, int d, int k);
+int launch_weighted_stats(const float* x, const float* r, int64_t n, int d, int k, double* nk,
+                          double* sum_rx, double* sum_rxx, void* workspace,
+                          int64_t workspace_bytes, cudaStream_t stream);
+
+// stats_kernels.cu
+int launch_f32_to_f64(const float* in, double* out, int64_t n, cudaStream_t stream);
+int launch_gaussian_expected_loglik(const double* s1, const double* s2, double n,
+                                    const double* e_lambda, const double* e_lambda_mu,
+                                    double e_mu_l_mu, double e_logdet, int d, double* out,
+                                    cudaStream_t stream);
+
+}  // namespace bb

@@ -1,0 +1,346 @@
+// One-pass Gaussian sufficient statistics  S1 = sum_n x_n,  S2 = sum_n x_n x_n^T
+// over X[n, d] (float32, row-major, d <= 64) on sm_100a.
+//
+// What it replaces: the reference evaluates Sigma x x^T as the plan
+//   _tensordot(_dimshuffle(X,1,0), X, [1],[0])        (bayesic/algebra.py:527-551, 1347-1351)
+// i.e. one Theano/BLAS sgemm over the data axis, and Sigma x as _sum(X, 0) -- a second full
+// pass (algebra.py:1290-1291).  These are the iid-summed statistics of
+// ExpFamIndependentObservations (bayesic/distribution/base.py:328-332) for
+// MultivariateNormal's (x, x x^T) (distribution/core.py:41-44).
+//
+// Design (HBM-bound: 256 B/row must stream once at ~6.5 TB/s, but 8 256 flop/row would need
+// ~210 TFLOP/s -- more than the FP32 SIMT pipes have -- so the outer products go to tcgen05):
+//
+//   * persistent kernel, one CTA per SM, each owning a contiguous range of 128-row tiles;
+//   * a TMA producer thread streams tiles (two 128x32 boxes, SWIZZLE_128B) through a
+//     6-stage mbarrier ring: 192 KB of loads in flight per SM;
+//   * error-compensated TF32 ("3xTF32" for the price of one MMA): x = hi + lo with
+//     hi = x truncated to TF32 (exactly what the tensor core reads from a raw FP32 word) and
+//     lo = x - hi.  Four "split" warps write A = [hi ; lo] (M = 128 rows: 64 features of hi
+//     stacked on 64 features of lo, K = data rows) into TMEM with tcgen05.st; the B operand
+//     is the raw FP32 tile itself in shared memory (MN-major, read as hi by the hardware).
+//     One M=128, N=64, K=8 tcgen05.mma per 8 data rows therefore yields
+//         D[0:64]   += hi^T hi         D[64:128] += lo^T hi
+//     and  S2 = hi^T hi + lo^T hi + (lo^T hi)^T  (+ O(2^-20) lo^T lo, dropped);
+//   * FP32 accumulation in TMEM is drained every 512 rows into float64 registers by four
+//     epilogue warps (double-buffered accumulators, so the MMA never waits);
+//   * Sigma x rides along for free in the split warps (they already touch every element);
+//   * per-CTA float64 partials go to a workspace; a tiny finalize kernel adds them up in a
+//     fixed order (deterministic) and applies the symmetrisation above.
+//
+// Algorithmic traffic: 4*d bytes per row, read once.  Nothing else touches HBM except
+// 148 x 65.5 KB of partials.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace bb {
+
+namespace {
+
+constexpr int kFeat = 64;          // padded feature extent (= MMA N, = half of MMA M)
+constexpr int kTileRows = 128;     // data rows per pipeline stage
+constexpr int kStages = 6;
+constexpr int kFlushTiles = 4;     // drain TMEM accumulators every 4 tiles = 512 rows
+constexpr int kBoxCols = 32;       // one TMA box = 128 rows x 32 floats = one 128B-swizzle column block
+constexpr int kHalfBytes = kTileRows * kBoxCols * 4;   // 16 KB
+constexpr int kStageBytes = 2 * kHalfBytes;            // 32 KB
+constexpr int kKBlocks = kTileRows / 8;                // 16 MMAs (K = 8) per tile
+constexpr int kThreads = 320;      // warps 0-3 split, 4-7 epilogue, 8 TMA, 9 MMA
+constexpr int kTmemCols = 512;
+constexpr int kTmemAcc = 0;        // 2 accumulators x 64 columns
+constexpr int kTmemA = 128;        // 2 A buffers x 128 columns
+
+struct __align__(1024) SmemLayout {
+  uint8_t stage[kStages][kStageBytes];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t a_ready[2];
+  uint64_t a_free[2];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+constexpr uint32_t kIdesc = ptx::make_idesc(128, kFeat, /*tf32*/ 2, /*A K-major*/ 0, /*B MN-major*/ 1);
+
+__global__ void __launch_bounds__(kThreads, 1)
+suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
+                    double* __restrict__ partial_s2,   // [grid][128][64]
+                    double* __restrict__ partial_s1) { // [grid][64]
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t tile_begin = n_tiles * blockIdx.x / gridDim.x;
+  const int64_t tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int my_tiles = static_cast<int>(tile_end - tile_begin);
+
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        ptx::mbar_init(&sm.full[s], 1);
+        ptx::mbar_init(&sm.empty[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&sm.a_ready[b], 128);
+        ptx::mbar_init(&sm.a_free[b], 1);
+        ptx::mbar_init(&sm.acc_full[b], 1);
+        ptx::mbar_init(&sm.acc_empty[b], 128);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
+  } else if (warp == 8 && lane == 0) {
+    ptx::prefetch_tensormap(&x_map);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (ptx::elect_one()) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        ptx::mbar_wait(&sm.empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&sm.full[s], kStageBytes);
+        const int32_t row0 = static_cast<int32_t>((tile_begin + i) * kTileRows);
+        ptx::tma_load_2d(sm.stage[s], &x_map, &sm.full[s], 0, row0);
+        ptx::tma_load_2d(sm.stage[s] + kHalfBytes, &x_map, &sm.full[s], kBoxCols, row0);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    if (ptx::elect_one()) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % kStages;
+        const int b = i & 1;
+        const int chunk = i / kFlushTiles;
+        const int ab = chunk & 1;
+        const bool first_in_chunk = (i % kFlushTiles) == 0;
+        if (first_in_chunk) ptx::mbar_wait(&sm.acc_empty[ab], ((chunk >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&sm.full[s], (i / kStages) & 1);
+        ptx::mbar_wait(&sm.a_ready[b], (i >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t stage_addr = ptx::smem_u32(sm.stage[s]);
+        const uint32_t d_tmem = tmem + kTmemAcc + ab * kFeat;
+        const uint32_t a_tmem = tmem + kTmemA + b * kTileRows;
+#pragma unroll
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+          // B = rows [8kb, 8kb+8) of the tile: K = 8 rows, N = 64 features in two 32-wide
+          // swizzle blocks kHalfBytes apart (LBO); 8-row groups are 1024 B apart (SBO).
+          const uint64_t b_desc = ptx::make_smem_desc(stage_addr + kb * 1024, kHalfBytes, 1024,
+                                                      ptx::kLayoutSwizzle128B);
+          ptx::mma_tf32_ts(d_tmem, a_tmem + kb * 8, b_desc, kIdesc,
+                           (first_in_chunk && kb == 0) ? 0u : 1u);
+        }
+        ptx::mma_commit(&sm.empty[s]);
+        ptx::mma_commit(&sm.a_free[b]);
+        if ((i % kFlushTiles) == kFlushTiles - 1 || i == my_tiles - 1)
+          ptx::mma_commit(&sm.acc_full[ab]);
+      }
+    }
+  } else if (warp < 4) {
+    // ---------------- split warps: A = [hi ; lo] into TMEM, and Sigma x ----------------
+    const int q = warp;                 // TMEM lane quadrant
+    const int half = q & 1;             // which 32-feature column block
+    const bool is_lo = q >= 2;
+    uint32_t off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      off[j] = half * kHalfBytes + j * 128 + ((((lane >> 2) ^ j) & 7) << 4) + (lane & 3) * 4;
+    double s1 = 0.0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % kStages;
+      const int b = i & 1;
+      ptx::mbar_wait(&sm.full[s], (i / kStages) & 1);
+      ptx::mbar_wait(&sm.a_free[b], ((i >> 1) & 1) ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint8_t* stage = sm.stage[s];
+      const uint32_t a_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemA + b * kTileRows;
+      float s1_tile = 0.f;
+#pragma unroll 4
+      for (int kb = 0; kb < kKBlocks; ++kb) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x = *reinterpret_cast<const float*>(stage + kb * 1024 + off[j]);
+          const uint32_t hi_bits = __float_as_uint(x) & 0xFFFFE000u;
+          if (is_lo) {
+            const float lo = x - __uint_as_float(hi_bits);
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+            v[j] = r;
+          } else {
+            v[j] = hi_bits;
+            s1_tile += x;
+          }
+        }
+        ptx::tmem_st_32x32b_x8(a_addr + kb * 8, v);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&sm.a_ready[b]);
+      s1 += static_cast<double>(s1_tile);
+    }
+    if (!is_lo) partial_s1[static_cast<int64_t>(blockIdx.x) * kFeat + half * 32 + lane] = s1;
+  } else {
+    // ---------------- epilogue warps: TMEM fp32 chunks -> float64 registers ----------------
+    const int q = warp - 4;
+    double acc[kFeat];
+#pragma unroll
+    for (int c = 0; c < kFeat; ++c) acc[c] = 0.0;
+    const int n_chunks = (my_tiles + kFlushTiles - 1) / kFlushTiles;
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int ab = chunk & 1;
+      ptx::mbar_wait(&sm.acc_full[ab], (chunk >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemAcc + ab * kFeat;
+#pragma unroll
+      for (int part = 0; part < kFeat / 16; ++part) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(d_addr + part * 16, v);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[part * 16 + j] += static_cast<double>(__uint_as_float(v[j]));
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&sm.acc_empty[ab]);
+    }
+    double* out = partial_s2 + (static_cast<int64_t>(blockIdx.x) * 128 + q * 32 + lane) * kFeat;
+#pragma unroll
+    for (int c = 0; c < kFeat; ++c) out[c] = acc[c];
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) ptx::tmem_dealloc(tmem, kTmemCols);
+}
+
+// S2[d,e] = sum_cta ( P[d][e] + P[64+d][e] + P[64+e][d] ),  S1[d] = sum_cta p1[d]
+__global__ void suffstats_finalize_kernel(const double* __restrict__ partial_s2,
+                                          const double* __restrict__ partial_s1, int n_partials,
+                                          int d, int accumulate, double* __restrict__ s2,
+                                          double* __restrict__ s1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < d * d) {
+    const int r = idx / d, c = idx % d;
+    double acc = 0.0;
+    for (int p = 0; p < n_partials; ++p) {
+      const double* P = partial_s2 + static_cast<int64_t>(p) * 128 * kFeat;
+      acc += P[r * kFeat + c] + P[(kFeat + r) * kFeat + c] + P[(kFeat + c) * kFeat + r];
+    }
+    s2[idx] = accumulate ? s2[idx] + acc : acc;
+  }
+  if (s1 != nullptr && idx < d) {
+    double acc = 0.0;
+    for (int p = 0; p < n_partials; ++p) acc += partial_s1[static_cast<int64_t>(p) * kFeat + idx];
+    s1[idx] = accumulate ? s1[idx] + acc : acc;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+bool suffstats_tc_supported(int64_t n, int d, const void* x) {
+  return n > 0 && d >= 4 && d <= kFeat && (d % 4) == 0 &&
+         (reinterpret_cast<uintptr_t>(x) % 16) == 0 && n < (int64_t(1) << 31) - kTileRows;
+}
+
+int64_t suffstats_tc_workspace(int64_t n) {
+  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  int64_t grid = device_sm_count();
+  if (grid <= 0) grid = 148;
+  if (tiles < grid) grid = tiles > 0 ? tiles : 1;
+  return grid * (128 * kFeat + kFeat) * static_cast<int64_t>(sizeof(double)) + 256;
+}
+
+// s1 may be nullptr.  s1/s2 are device float64; with `accumulate` the results are added to them.
+int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double* s2,
+                            void* workspace, int64_t workspace_bytes, bool accumulate,
+                            cudaStream_t stream) {
+  if (!suffstats_tc_supported(n, d, x)) {
+    set_error("suffstats_tc: unsupported shape n=%lld d=%d", static_cast<long long>(n), d);
+    return BB_ERR_UNSUPPORTED;
+  }
+  const int64_t need = suffstats_tc_workspace(n);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("suffstats_tc: workspace %lld < %lld bytes", static_cast<long long>(workspace_bytes),
+              static_cast<long long>(need));
+    return BB_ERR_WORKSPACE;
+  }
+  EncodeTiledFn encode = get_encode_tiled();
+  if (encode == nullptr) {
+    set_error("cuTensorMapEncodeTiled unavailable from the driver");
+    return BB_ERR_CUDA;
+  }
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d) * sizeof(float)};
+  const cuuint32_t box[2] = {kBoxCols, kTileRows};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim,
+                       gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%lld d=%d)", static_cast<int>(cr),
+              static_cast<long long>(n), d);
+    return BB_ERR_CUDA;
+  }
+  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  int grid = device_sm_count();
+  if (tiles < grid) grid = static_cast<int>(tiles);
+  double* partial_s2 = reinterpret_cast<double*>(
+      (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  double* partial_s1 = partial_s2 + static_cast<int64_t>(grid) * 128 * kFeat;
+
+  const int smem_bytes = static_cast<int>(sizeof(SmemLayout)) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BB_CUDA_OK(cudaFuncSetAttribute(suffstats_tc_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial_s2, partial_s1);
+  BB_CHECK_LAUNCH("suffstats_tc_kernel");
+  const int fin_threads = 256;
+  const int fin_blocks = (d * d + fin_threads - 1) / fin_threads;
+  suffstats_finalize_kernel<<<fin_blocks, fin_threads, 0, stream>>>(partial_s2, partial_s1, grid, d,
+                                                                    accumulate ? 1 : 0, s2, s1);
+  BB_CHECK_LAUNCH("suffstats_finalize_kernel");
+  return BB_OK;
+}
+
+int launch_suffstats_tc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t stream) {
+  return launch_suffstats_tc_acc(x, n, d, s1, s2, workspace, workspace_bytes, false, stream);
+}
+
+}  // namespace bb

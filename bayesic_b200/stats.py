@@ -1,0 +1,169 @@
+"""Fused sufficient-statistic / responsibility passes (Python face of the C-ABI).
+
+These are the iid-summed exponential-family statistics the reference's distribution
+sketch asks for -- ``ExpFamIndependentObservations.sufficient_statistics``
+(``bayesic/distribution/base.py:328-332``) of ``MultivariateNormal``'s ``(x, x x^T)``
+(``distribution/core.py:41-44``) -- computed in ONE pass over the data, plus the
+mixture-responsibility pass and the ELBO term assembled from the statistics.
+
+Inputs may be CUDA ``torch.Tensor``s (resident data, results stay on the device as
+float64 tensors) or numpy arrays (streamed host->device in chunks, numpy results) --
+the latter is the reference-facing call (numpy in, numpy out, ``algebra.py:55-56``).
+No CPU fallback: everything here raises without the CUDA library and a GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from .backend import library as L
+
+__all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'log_responsibilities',
+           'weighted_suffstats', 'launch_count']
+
+_scratch = {}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bayesic_b200: no CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def _workspace(nbytes, device):
+    torch = _torch()
+    buf = _scratch.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _scratch[device] = buf
+    return buf
+
+
+def _stream(device):
+    return ctypes.c_void_p(_torch().cuda.current_stream(device).cuda_stream)
+
+
+def launch_count():
+    """Kernels launched by the library on this thread so far."""
+    return int(L.load().bb_launch_count())
+
+
+def _as_device_f32(t, ndim, what):
+    torch = _torch()
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA torch.Tensor" % what)
+    if t.dim() != ndim:
+        raise TypeError("%s: expected ndim %d, got %d" % (what, ndim, t.dim()))
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def gaussian_suffstats(X, out=None, chunk_rows=0):
+    """``(n, sum_x[d], sum_xxT[d, d])`` of the rows of ``X[n, d]`` in float64.
+
+    CUDA tensor in -> float64 CUDA tensors out (no synchronisation).
+    numpy array in -> numpy float64 out through ``bb_suffstats_gaussian_host`` (chunked
+    host->device streaming; pass pinned memory for full PCIe speed)."""
+    torch = _torch()
+    lib = L.load()
+    if isinstance(X, torch.Tensor) and X.is_cuda:
+        X = _as_device_f32(X, 2, 'X')
+        n, d = X.shape
+        with torch.cuda.device(X.device):
+            if out is None:
+                s1 = torch.empty(d, dtype=torch.float64, device=X.device)
+                s2 = torch.empty((d, d), dtype=torch.float64, device=X.device)
+            else:
+                s1, s2 = out
+            need = lib.bb_suffstats_gaussian_workspace(n, d)
+            ws = _workspace(need, X.device)
+            L.check(lib.bb_suffstats_gaussian(X.data_ptr(), n, d, s1.data_ptr(), s2.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _stream(X.device)),
+                    'bb_suffstats_gaussian')
+        return n, s1, s2
+    if isinstance(X, torch.Tensor):          # pinned / pageable host tensor
+        host = X.detach()
+        if host.dtype != torch.float32 or not host.is_contiguous() or host.dim() != 2:
+            raise TypeError("host X must be a contiguous float32 matrix")
+        n, d = host.shape
+        ptr = host.data_ptr()
+    else:
+        host = np.ascontiguousarray(X, dtype=np.float32)
+        if host.ndim != 2:
+            raise TypeError("X: expected ndim 2, got %d" % host.ndim)
+        n, d = host.shape
+        ptr = host.ctypes.data
+    s1 = np.empty(d, dtype=np.float64)
+    s2 = np.empty((d, d), dtype=np.float64)
+    device = torch.device('cuda', torch.cuda.current_device())
+    L.check(lib.bb_suffstats_gaussian_host(ptr, n, d, s1.ctypes.data, s2.ctypes.data,
+                                           int(chunk_rows), _stream(device)),
+            'bb_suffstats_gaussian_host')
+    return n, s1, s2
+
+
+def gaussian_expected_loglik(n, s1, s2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, out=None):
+    """E_q[sum_n log N(x_n | mu, Lambda^-1)] from device float64 statistics and the
+    expectations of the natural parameters; returns a 1-element float64 CUDA tensor."""
+    torch = _torch()
+    lib = L.load()
+    dev = s2.device
+    d = s2.shape[0]
+
+    def f64(t):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t, dtype=np.float64))
+        return t.to(device=dev, dtype=torch.float64).contiguous()
+
+    s1, s2, e_lambda, e_lambda_mu = f64(s1), f64(s2), f64(e_lambda), f64(e_lambda_mu)
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.bb_gaussian_expected_loglik(s1.data_ptr(), s2.data_ptr(), float(n),
+                                                e_lambda.data_ptr(), e_lambda_mu.data_ptr(),
+                                                float(e_mu_l_mu), float(e_logdet), d, out.data_ptr(),
+                                                _stream(dev)), 'bb_gaussian_expected_loglik')
+    return out
+
+
+def log_responsibilities(logits, want_lse=True, want_sum=True, out=None):
+    """``log r = logits - logsumexp(logits, axis=1)`` in one pass.  Returns
+    ``(log_resp[n, k] float32, lse[n] float32 | None, sum_lse float64[1] | None)``."""
+    torch = _torch()
+    lib = L.load()
+    logits = _as_device_f32(logits, 2, 'logits')
+    n, k = logits.shape
+    dev = logits.device
+    with torch.cuda.device(dev):
+        log_resp = out if out is not None else torch.empty_like(logits)
+        lse = torch.empty(n, dtype=torch.float32, device=dev) if want_lse else None
+        total = torch.empty(1, dtype=torch.float64, device=dev) if want_sum else None
+        L.check(lib.bb_logsoftmax_rows(logits.data_ptr(), n, k, log_resp.data_ptr(),
+                                       lse.data_ptr() if want_lse else None,
+                                       total.data_ptr() if want_sum else None, _stream(dev)),
+                'bb_logsoftmax_rows')
+    return log_resp, lse, total
+
+
+def weighted_suffstats(X, R):
+    """``(N_k[k], sum_rx[k, d], sum_rxx[k, d, d])`` float64 CUDA tensors, one pass over (R, X)."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    R = _as_device_f32(R, 2, 'R')
+    if X.shape[0] != R.shape[0]:
+        raise ValueError("X and R disagree on the data axis (%d vs %d)" % (X.shape[0], R.shape[0]))
+    n, d = X.shape
+    k = R.shape[1]
+    dev = X.device
+    with torch.cuda.device(dev):
+        nk = torch.empty(k, dtype=torch.float64, device=dev)
+        rx = torch.empty((k, d), dtype=torch.float64, device=dev)
+        rxx = torch.empty((k, d, d), dtype=torch.float64, device=dev)
+        need = lib.bb_suffstats_weighted_workspace(n, d, k)
+        ws = _workspace(need, dev)
+        L.check(lib.bb_suffstats_weighted(X.data_ptr(), R.data_ptr(), n, d, k, nk.data_ptr(),
+                                          rx.data_ptr(), rxx.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          _stream(dev)), 'bb_suffstats_weighted')
+    return nk, rx, rxx

@@ -1,0 +1,203 @@
+/*
+ * bayesic_b200 -- C-ABI of the B200 (sm_100a) executor for Bayesic's einsum plans.
+ *
+ * This is the drop-in boundary for the one hot path of mjwillson/Bayesic: the
+ * per-minibatch evaluation of a compiled expression.  The reference has no FFI;
+ * its seam is the Python protocol
+ *
+ *     fn = theano.function(inputs, expression)        bayesic/algebra.py:54
+ *     f(**inputs) -> fn(*arrays)                      bayesic/algebra.py:55-56
+ *     node._apply_to_parents(*parent_vars)            bayesic/algebra.py:34-40,
+ *                                                     1290, 1302, 1318, 1347, 1405
+ *
+ * Every entry point below replaces one of those call sites (cited per function).
+ * Conventions:
+ *   - plain C types only; all tensors are raw pointers + int64 extents;
+ *   - device tensors are dense row-major float32 unless stated; statistics that
+ *     are sums over the data axis are returned as float64;
+ *   - the library BORROWS every pointer for the duration of the call; device
+ *     entry points never allocate: scratch comes from a caller-provided workspace
+ *     whose size is queried first.  The one exception is the host-buffer entry
+ *     point bb_suffstats_gaussian_host, which owns a small staging pool
+ *     (released by bb_release_staging);
+ *   - calls are ordered on the caller's `stream` (a cudaStream_t passed as
+ *     void*); nothing synchronises unless documented;
+ *   - every function returns a bb_status (0 = ok); on failure
+ *     bb_last_error() gives a thread-local message.  No exceptions cross the ABI.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with BB_ERR_CUDA.
+ */
+#ifndef BAYESIC_B200_H
+#define BAYESIC_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BB_API __attribute__((visibility("default")))
+#else
+#define BB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+#define BB_MAX_DIMS 8
+#define BB_MAX_PARENTS 8
+#define BB_MAX_IPARAMS 40
+
+typedef enum {
+  BB_OK = 0,
+  BB_ERR_INVALID = 1,      /* malformed descriptor / argument                      */
+  BB_ERR_CUDA = 2,         /* CUDA runtime or driver error (message has details)   */
+  BB_ERR_UNSUPPORTED = 3,  /* valid request this build cannot serve                */
+  BB_ERR_SHAPE = 4,        /* runtime extents inconsistent with the plan           */
+  BB_ERR_WORKSPACE = 5     /* workspace too small                                  */
+} bb_status;
+
+/* ---- library ------------------------------------------------------------ */
+
+BB_API int bb_abi_version(void);
+BB_API const char* bb_last_error(void);
+/* Kernels launched by this library on the calling thread since load (monotonic). */
+BB_API int64_t bb_launch_count(void);
+/* SM count and compute capability of the current device. */
+BB_API int bb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- plan executor -------------------------------------------------------
+ * A plan is the flat, topologically ordered form of the plan-IR tree the
+ * planner emits (bayesic/algebra.py:527-765).  Node kinds map one-to-one onto
+ * the reference's executor vocabulary; iparams carry the integer attributes. */
+
+typedef enum {
+  BB_NODE_INPUT = 0,      /* var            algebra.py:108-126   iparams: [input slot]            */
+  BB_NODE_SCALAR = 1,     /* constant       algebra.py:129-144   fparam: value (host scalar)      */
+  BB_NODE_SHAPE = 2,      /* shape          algebra.py:147-161   parents: [x]  iparams: [axis]    */
+  BB_NODE_EYE = 3,        /* eye            algebra.py:236-258   parents: [n]                     */
+  BB_NODE_SUM = 4,        /* _sum           algebra.py:1284-1294 parents: [x]  iparams: axes      */
+  BB_NODE_MUL = 5,        /* _mul           algebra.py:1297-1309 parents: factors (<= 8)          */
+  BB_NODE_DIMSHUFFLE = 6, /* _dimshuffle    algebra.py:1312-1326 parents: [x]  iparams: axes, -1 = 'x' */
+  BB_NODE_TENSORDOT = 7,  /* _tensordot     algebra.py:1329-1396 parents: [x, y]
+                             iparams: [n_dot, n_batch, x_dot.., y_dot.., x_batch.., y_batch..]
+                             result axes = batch + x_other + y_other (algebra.py:1161-1171)    */
+  BB_NODE_DIAGONAL = 8,   /* _diagonal      algebra.py:1398-1414 parents: [x]  iparams: [a1, a2];
+                             the diagonal axis is appended last                                  */
+  BB_NODE_ELEMWISE = 9,   /* elemwise/add   algebra.py:195-233, 1435-1448
+                             parents: args (<= 8)  iparams: [bb_elemwise_op]                     */
+  /* fused nodes recognised by the host-side lowering */
+  BB_NODE_LOGSOFTMAX = 20,/* x - log(sum(exp(x), axis=-1)) over the last axis, max-subtracted;
+                             the pattern add(Lg, einsum(-1 * log(einsum(sum exp(Lg)))))          */
+  BB_NODE_SYRK = 21,      /* _tensordot(_dimshuffle(X,1,0), X, [1],[0]): X^T X over the data axis */
+  BB_NODE_WEIGHTED_SCATTER = 22 /* sum_n R[n,k] X[n,d] X[n,e] -> [k,d,e] without materialising
+                             the K x D x N intermediate of algebra.py's plan; parents: [R, X]    */
+} bb_node_kind;
+
+typedef enum {
+  BB_OP_ADD = 0, BB_OP_MUL = 1, BB_OP_LOG = 2, BB_OP_EXP = 3, BB_OP_POW = 4, BB_OP_ABS = 5
+} bb_elemwise_op;
+
+typedef struct {
+  int32_t kind;                       /* bb_node_kind */
+  int32_t n_parents;
+  int32_t parents[BB_MAX_PARENTS];    /* indices of earlier nodes */
+  int32_t n_iparams;
+  int32_t iparams[BB_MAX_IPARAMS];
+  double fparam;
+} bb_node_desc;
+
+/* A tensor argument: a dense row-major float32 device array, or a host scalar
+ * (0-dim inputs, e.g. the int32 scalar `a` of eye(a), test_algebra.py:40). */
+typedef struct {
+  const void* data;                   /* device pointer (ignored for host scalars) */
+  int32_t ndim;
+  int32_t is_host_scalar;
+  int64_t shape[BB_MAX_DIMS];
+  double host_value;
+} bb_tensor_arg;
+
+typedef struct {
+  int32_t ndim;
+  int32_t is_host_scalar;             /* value known on the host (shape arithmetic, literals) */
+  int64_t shape[BB_MAX_DIMS];
+  double host_value;
+} bb_result_info;
+
+typedef struct bb_plan bb_plan;
+
+/* Replaces theano.function(inputs, expression), algebra.py:54. */
+BB_API int bb_plan_create(const bb_node_desc* nodes, int32_t n_nodes,
+                   const int32_t* outputs, int32_t n_outputs,
+                   int32_t n_inputs, bb_plan** plan);
+BB_API int bb_plan_destroy(bb_plan* plan);
+
+/* Shape pass: result extents and scratch size for the given input extents
+ * (plans are shape-polymorphic, algebra.py:539-546). */
+BB_API int bb_plan_infer(bb_plan* plan, const bb_tensor_arg* inputs, int32_t n_inputs,
+                  bb_result_info* results, int64_t* workspace_bytes);
+
+/* Replaces fn(*arrays), algebra.py:55-56.  out_ptrs[i] receives result i as a
+ * dense float32 array (untouched for host-scalar results). */
+BB_API int bb_plan_execute(bb_plan* plan, const bb_tensor_arg* inputs, int32_t n_inputs,
+                    void* const* out_ptrs, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* Number of kernels the last bb_plan_execute on this plan launched. */
+BB_API int bb_plan_last_launch_count(bb_plan* plan, int32_t* count);
+
+/* ---- fused sufficient-statistic passes --------------------------------------
+ * The iid-summed exponential-family statistics of
+ * ExpFamIndependentObservations.sufficient_statistics
+ * (bayesic/distribution/base.py:328-332) for MultivariateNormal's (x, x x^T)
+ * (bayesic/distribution/core.py:41-44), in ONE pass over X. */
+
+/* sum_x[d] = sum_n X[n,d];  sum_xxT[d,e] = sum_n X[n,d] X[n,e]   (float64 out).
+ * X is device float32 [n, d] row-major.  d <= 64 and d % 4 == 0 runs the
+ * tcgen05 kernel; other d use the generic contraction kernels. */
+BB_API int64_t bb_suffstats_gaussian_workspace(int64_t n, int32_t d);
+BB_API int bb_suffstats_gaussian(const float* X, int64_t n, int32_t d,
+                          double* sum_x, double* sum_xxT,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Same pass from a HOST buffer (the reference-facing call: numpy in, numpy out,
+ * algebra.py:55-56).  Streams X through pinned staging in chunks so the copy
+ * overlaps the kernel; synchronises before returning.  sum_x / sum_xxT are host
+ * pointers. */
+BB_API int bb_suffstats_gaussian_host(const float* X_host, int64_t n, int32_t d,
+                               double* sum_x_host, double* sum_xxT_host,
+                               int64_t chunk_rows, void* stream);
+
+/* Frees the staging pool of bb_suffstats_gaussian_host (device chunk buffers, stream, events). */
+BB_API int bb_release_staging(void);
+
+/* Expected Gaussian log-likelihood of the batch under q(mu, Lambda), from the
+ * statistics (log_likelihood = data_term + interaction_term - log_normalizer,
+ * bayesic/distribution/base.py:25-100; eta = (Lambda mu, -1/2 Lambda),
+ * core.py:46-47; A = -1/2 D log 2pi ... core.py:49-52):
+ *   out = -n d/2 log(2 pi) + n/2 E_logdet - 1/2 tr(E_Lambda S2)
+ *         + S1 . E_Lambda_mu - n/2 E_muLmu
+ * All pointers are device float64. */
+BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xxT, double n,
+                                const double* E_Lambda, const double* E_Lambda_mu,
+                                double E_muLmu, double E_logdet, int32_t d,
+                                double* out, void* stream);
+
+/* ---- mixture responsibilities ------------------------------------------------
+ * log r[n,k] = logits[n,k] - logsumexp_k logits[n,:]  (max-subtracted; the
+ * reference can only spell the unstabilised form, algebra.py:1435-1448).
+ * lse[n] and sum_lse (float64, device) are optional (may be NULL). */
+BB_API int bb_logsoftmax_rows(const float* logits, int64_t n, int32_t k,
+                       float* log_resp, float* lse, double* sum_lse, void* stream);
+
+/* Responsibility-weighted statistics in one pass over (R, X):
+ *   Nk[k] = sum_n R[n,k];  sum_rx[k,d] = sum_n R[n,k] X[n,d];
+ *   sum_rxx[k,d,e] = sum_n R[n,k] X[n,d] X[n,e]           (float64 out, device) */
+BB_API int64_t bb_suffstats_weighted_workspace(int64_t n, int32_t d, int32_t k);
+BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int32_t d, int32_t k,
+                          double* Nk, double* sum_rx, double* sum_rxx,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYESIC_B200_H */

@@ -1,0 +1,156 @@
+"""GPU parity of the fused statistic / responsibility kernels against the float64 oracle
+(``oracle/closed_forms.py``), through the C-ABI entry points."""
+import numpy as np
+import pytest
+
+import bayesic_b200.stats as S
+from oracle import closed_forms as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _close(got, want, rtol=RTOL, scale_atol=1e-6):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=scale_atol * max(1.0, np.abs(want).max()))
+
+
+@pytest.mark.parametrize('n,d', [(1, 64), (127, 64), (128, 64), (129, 64), (1000, 16), (10000, 16),
+                                 (65536, 64), (100003, 32), (5000, 60), (777, 48), (2048, 4),
+                                 (777, 20), (513, 96), (40, 3), (0, 64)])
+def test_gaussian_suffstats_device(n, d):
+    import torch
+    rng = np.random.RandomState(n * 131 + d)
+    X = (rng.randn(n, d) * 1.5 + 0.7).astype(np.float32)
+    before = S.launch_count()
+    cnt, s1, s2 = S.gaussian_suffstats(torch.from_numpy(X).cuda())
+    rn, r1, r2 = O.gaussian_suffstats(X)
+    assert cnt == rn
+    _close(s1.cpu().numpy(), r1)
+    _close(s2.cpu().numpy(), r2)
+    if n > 0:
+        assert S.launch_count() > before
+
+
+def test_compensated_tf32_is_exact_to_float32_level():
+    # low mantissa bits set so that plain TF32 (or RN-on-B) would be off by ~2e-4
+    import torch
+    rng = np.random.RandomState(3)
+    X = (1.0 + 2.0 ** -11 + 2.0 ** -12 + rng.rand(4096, 64) * 2.0 ** -14).astype(np.float32)
+    _, s1, s2 = S.gaussian_suffstats(torch.from_numpy(X).cuda())
+    _, r1, r2 = O.gaussian_suffstats(X)
+    np.testing.assert_allclose(s2.cpu().numpy(), r2, rtol=5e-6)
+    np.testing.assert_allclose(s1.cpu().numpy(), r1, rtol=1e-6)
+
+
+def test_cfg1_reference_expression_through_stats():
+    # BASELINE cfg1: tr(Lambda . sum x x^T), N = 10 000, D = 16
+    import torch
+    rng = np.random.RandomState(1234)
+    X = rng.randn(10000, 16).astype(np.float32)
+    a = rng.randn(16, 16)
+    Lam = (a @ a.T / 16 + np.eye(16))
+    _, _, s2 = S.gaussian_suffstats(torch.from_numpy(X).cuda())
+    got = float(np.sum(Lam * s2.cpu().numpy()))
+    want = float(np.einsum('de,nd,ne->', Lam, X.astype('f8'), X.astype('f8')))
+    assert abs(got - want) <= RTOL * abs(want)
+
+
+def test_host_streamed_matches_device_and_oracle():
+    import torch
+    rng = np.random.RandomState(5)
+    X = (rng.randn(300001, 64) + 0.25).astype(np.float32)
+    _, h1, h2 = S.gaussian_suffstats(X, chunk_rows=65536)
+    _, r1, r2 = O.gaussian_suffstats(X)
+    _close(h1, r1)
+    _close(h2, r2)
+    _, d1, d2 = S.gaussian_suffstats(torch.from_numpy(X).cuda())
+    _close(d2.cpu().numpy(), h2, rtol=1e-9)
+    pinned = torch.from_numpy(X).pin_memory()
+    _, p1, p2 = S.gaussian_suffstats(pinned)
+    np.testing.assert_array_equal(p2, h2)
+
+
+def test_full_size_cfg2_properties():
+    # N = 16 Mi, D = 64 (BASELINE cfg2): size-independent properties instead of a CPU oracle
+    import torch
+    n, d = 1 << 24, 64
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    X = torch.randn(n, d, device='cuda', dtype=torch.float32, generator=g) * 1.3 + 0.4
+    _, s1, s2 = S.gaussian_suffstats(X)
+    # (1) additivity over a split of the data axis (linearity of the statistics)
+    _, a1, a2 = S.gaussian_suffstats(X[: n // 3])
+    _, b1, b2 = S.gaussian_suffstats(X[n // 3:])
+    np.testing.assert_allclose((a2 + b2).cpu().numpy(), s2.cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose((a1 + b1).cpu().numpy(), s1.cpu().numpy(), rtol=1e-9)
+    # (2) symmetry, (3) checksums: trace = sum of squares, S1 = column sums (float64 on device)
+    np.testing.assert_array_equal(s2.cpu().numpy(), s2.cpu().numpy().T)
+    tr = float((X.double() ** 2).sum())
+    assert abs(float(s2.diagonal().sum()) - tr) <= 1e-6 * tr
+    col = X.double().sum(0)
+    np.testing.assert_allclose(s1.cpu().numpy(), col.cpu().numpy(), rtol=1e-6)
+    # (4) a random projection: u^T S2 v = sum_n (x_n.u)(x_n.v)
+    u = torch.randn(d, device='cuda', dtype=torch.float64, generator=None)
+    v = torch.randn(d, device='cuda', dtype=torch.float64)
+    want = float(((X.double() @ u) * (X.double() @ v)).sum())
+    got = float(u @ s2 @ v)
+    assert abs(got - want) <= 1e-5 * max(abs(want), float(s2.abs().max()))
+
+
+def test_gaussian_expected_loglik():
+    import torch
+    rng = np.random.RandomState(11)
+    n, d = 5000, 16
+    X = rng.randn(n, d).astype(np.float32)
+    m = rng.randn(d) * 0.1
+    a = rng.randn(d, d)
+    W = np.linalg.inv(a @ a.T / d + np.eye(d)) / (d + 4.0)
+    e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet = O.gaussian_wishart_expectations(m, 2.0, W, d + 4.0)
+    cnt, s1, s2 = S.gaussian_suffstats(torch.from_numpy(X).cuda())
+    got = float(S.gaussian_expected_loglik(cnt, s1, s2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet))
+    rn, r1, r2 = O.gaussian_suffstats(X)
+    want = O.gaussian_expected_loglik(rn, r1, r2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet)
+    assert abs(got - want) <= RTOL * abs(want)
+
+
+@pytest.mark.parametrize('n,k', [(4096, 256), (1000, 128), (33, 7), (5, 1000), (64, 1024), (7, 33),
+                                 (1, 1), (3, 384), (0, 256)])
+def test_log_responsibilities(n, k):
+    import torch
+    rng = np.random.RandomState(n + 7 * k)
+    Lg = (rng.randn(n, k) * 3).astype(np.float32)
+    lr, lse, tot = S.log_responsibilities(torch.from_numpy(Lg).cuda())
+    ref_lr, ref_lse = O.log_responsibilities(Lg)
+    np.testing.assert_allclose(lr.cpu().numpy(), ref_lr, rtol=RTOL, atol=2e-6)
+    np.testing.assert_allclose(lse.cpu().numpy(), ref_lse, rtol=RTOL, atol=2e-6)
+    assert abs(float(tot) - ref_lse.sum()) <= RTOL * max(1.0, abs(ref_lse.sum()))
+
+
+def test_log_responsibilities_extremes():
+    import torch
+    Lg = np.zeros((4, 256), dtype=np.float32)
+    Lg[0, 3] = 100.0                 # would overflow the reference's unstabilised spelling
+    Lg[1] = -300.0
+    Lg[2, :] = np.linspace(-50, 50, 256)
+    Lg[3, 7] = 30.0                  # dominant component: log r must keep relative precision
+    lr, lse, _ = S.log_responsibilities(torch.from_numpy(Lg).cuda())
+    ref_lr, ref_lse = O.log_responsibilities(Lg)
+    got = lr.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref_lr, rtol=RTOL, atol=1e-30)
+    np.testing.assert_allclose(lse.cpu().numpy(), ref_lse, rtol=1e-6)
+
+
+@pytest.mark.parametrize('n,d,k', [(1000, 64, 8), (4099, 16, 5), (300, 6, 3), (50000, 64, 16), (1, 4, 1)])
+def test_weighted_suffstats(n, d, k):
+    import torch
+    rng = np.random.RandomState(n + d + k)
+    X = rng.randn(n, d).astype(np.float32)
+    R = rng.dirichlet(np.ones(k), size=n).astype(np.float32)
+    nk, rx, rxx = S.weighted_suffstats(torch.from_numpy(X).cuda(), torch.from_numpy(R).cuda())
+    rnk, rrx, rrxx = O.weighted_suffstats(X, R)
+    _close(nk.cpu().numpy(), rnk)
+    _close(rx.cpu().numpy(), rrx, scale_atol=1e-5)
+    _close(rxx.cpu().numpy(), rrxx, scale_atol=1e-5)
