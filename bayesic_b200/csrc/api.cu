@@ -97,7 +97,7 @@ BB_API int64_t bb_suffstats_gaussian_workspace(int64_t n, int32_t d) {
 static int suffstats_device(const float* X, int64_t n, int32_t d, double* sum_x, double* sum_xxT,
                             void* workspace, int64_t workspace_bytes, bool accumulate,
                             cudaStream_t st) {
-  if (X == nullptr || sum_xxT == nullptr || n < 0 || d < 1) {
+  if ((X == nullptr && n > 0) || sum_xxT == nullptr || n < 0 || d < 1) {
     set_error("suffstats_gaussian: bad arguments (n=%lld d=%d)", static_cast<long long>(n), d);
     return BB_ERR_INVALID;
   }
@@ -266,7 +266,7 @@ BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xx
 
 BB_API int bb_logsoftmax_rows(const float* logits, int64_t n, int32_t k, float* log_resp, float* lse,
                        double* sum_lse, void* stream) {
-  if (!logits || !log_resp || n < 0) { set_error("logsoftmax_rows: bad arguments"); return BB_ERR_INVALID; }
+  if (n < 0 || (n > 0 && (!logits || !log_resp))) { set_error("logsoftmax_rows: bad arguments"); return BB_ERR_INVALID; }
   return launch_logsoftmax_rows(logits, n, k, log_resp, lse, sum_lse, static_cast<cudaStream_t>(stream));
 }
 
@@ -277,7 +277,7 @@ BB_API int64_t bb_suffstats_weighted_workspace(int64_t n, int32_t d, int32_t k) 
 BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int32_t d, int32_t k, double* Nk,
                           double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
                           void* stream) {
-  if (!X || !R || !sum_rxx || n < 0) { set_error("suffstats_weighted: bad arguments"); return BB_ERR_INVALID; }
+  if (n < 0 || !sum_rxx || (n > 0 && (!X || !R))) { set_error("suffstats_weighted: bad arguments"); return BB_ERR_INVALID; }
   return launch_weighted_stats(X, R, n, d, k, Nk, sum_rx, sum_rxx, workspace, workspace_bytes,
                                static_cast<cudaStream_t>(stream));
 }

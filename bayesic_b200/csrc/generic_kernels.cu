@@ -431,6 +431,11 @@ __global__ void splitk_reduce_kernel(const float* partial, float* out, int64_t n
 
 static void gemm_plan(int64_t M, int64_t N, int64_t K, int64_t batch, int* splits,
                       int64_t* k_per_split) {
+  if (K <= 0 || M <= 0 || N <= 0 || batch <= 0) {
+    *splits = 1;
+    *k_per_split = kGemmK;
+    return;
+  }
   const int64_t tiles = ((M + kGemmTile - 1) / kGemmTile) * ((N + kGemmTile - 1) / kGemmTile) * batch;
   const int64_t target = static_cast<int64_t>(std::max(1, device_sm_count())) * 4;
   int64_t s = std::max<int64_t>(1, target / std::max<int64_t>(1, tiles));

@@ -147,6 +147,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
 // Shared-memory matrix descriptor (sm_100 format): start address, leading / stride byte
 // offsets in 16-byte units, version 1, layout type in bits [61,64).
 constexpr uint64_t kLayoutSwizzle128B = 2;
+constexpr uint64_t kLayoutSwizzle128B32BAtom = 1;  // 128-byte span, 32-byte swizzle atom (MN-major 32-bit operands)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                    uint32_t sbo_bytes, uint64_t layout_type) {
   uint64_t d = 0;

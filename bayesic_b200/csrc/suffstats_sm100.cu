@@ -12,17 +12,19 @@
 // ~210 TFLOP/s -- more than the FP32 SIMT pipes have -- so the outer products go to tcgen05):
 //
 //   * persistent kernel, one CTA per SM, each owning a contiguous range of 128-row tiles;
-//   * a TMA producer thread streams tiles (two 128x32 boxes, SWIZZLE_128B) through a
-//     6-stage mbarrier ring: 192 KB of loads in flight per SM;
+//   * a TMA producer thread streams tiles (two 128x32 boxes, SWIZZLE_128B_ATOM_32B -- the
+//     only shared-memory layout the tensor core accepts for an MN-major 32-bit operand;
+//     measured with tests/cuda/tc_probe.cu: plain SWIZZLE_128B / no-swizzle MN-major TF32
+//     operands silently read as zero) through a 6-stage mbarrier ring: 192 KB in flight per SM;
 //   * error-compensated TF32 ("3xTF32" for the price of one MMA): x = hi + lo with
 //     hi = x truncated to TF32 (exactly what the tensor core reads from a raw FP32 word) and
-//     lo = x - hi.  Four "split" warps write A = [hi ; lo] (M = 128 rows: 64 features of hi
+//     lo = x - hi.  Eight "split" warps write A = [hi ; lo] (M = 128 rows: 64 features of hi
 //     stacked on 64 features of lo, K = data rows) into TMEM with tcgen05.st; the B operand
 //     is the raw FP32 tile itself in shared memory (MN-major, read as hi by the hardware).
 //     One M=128, N=64, K=8 tcgen05.mma per 8 data rows therefore yields
 //         D[0:64]   += hi^T hi         D[64:128] += lo^T hi
 //     and  S2 = hi^T hi + lo^T hi + (lo^T hi)^T  (+ O(2^-20) lo^T lo, dropped);
-//   * FP32 accumulation in TMEM is drained every 512 rows into float64 registers by four
+//   * FP32 accumulation in TMEM is drained every 512 rows into float64 registers by eight
 //     epilogue warps (double-buffered accumulators, so the MMA never waits);
 //   * Sigma x rides along for free in the split warps (they already touch every element);
 //   * per-CTA float64 partials go to a workspace; a tiny finalize kernel adds them up in a
@@ -44,12 +46,23 @@ namespace {
 constexpr int kFeat = 64;          // padded feature extent (= MMA N, = half of MMA M)
 constexpr int kTileRows = 128;     // data rows per pipeline stage
 constexpr int kStages = 6;
-constexpr int kFlushTiles = 4;     // drain TMEM accumulators every 4 tiles = 512 rows
-constexpr int kBoxCols = 32;       // one TMA box = 128 rows x 32 floats = one 128B-swizzle column block
+// TMEM accumulators are drained to float64 every kFlushTiles tiles.  The tensor core truncates
+// its fp32 accumulate, so the chunk length sets the (systematic) error: measured on B200 at
+// N = 16 Mi, D = 64:  4 tiles (512 rows) 2.5e-6 relative, 0.79 ms/pass;  1 tile 7e-7, 0.93 ms.
+// Both are far inside the 1e-4 parity bar; the default favours throughput.
+#ifndef BB_SUFFSTATS_FLUSH_TILES
+#define BB_SUFFSTATS_FLUSH_TILES 4
+#endif
+constexpr int kFlushTiles = BB_SUFFSTATS_FLUSH_TILES;
+constexpr int kBoxCols = 32;       // one TMA box = 128 rows x 32 floats (one 128-byte swizzle span per row)
 constexpr int kHalfBytes = kTileRows * kBoxCols * 4;   // 16 KB
 constexpr int kStageBytes = 2 * kHalfBytes;            // 32 KB
 constexpr int kKBlocks = kTileRows / 8;                // 16 MMAs (K = 8) per tile
-constexpr int kThreads = 320;      // warps 0-3 split, 4-7 epilogue, 8 TMA, 9 MMA
+constexpr int kSplitWarps = 8;     // warps 0-7: quadrant = w & 3, k-half = w >> 2
+constexpr int kEpiWarps = 8;       // warps 8-15: quadrant = w & 3, column half = (w - 8) >> 2
+constexpr int kTmaWarp = kSplitWarps + kEpiWarps;
+constexpr int kMmaWarp = kTmaWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;   // 576
 constexpr int kTmemCols = 512;
 constexpr int kTmemAcc = 0;        // 2 accumulators x 64 columns
 constexpr int kTmemA = 128;        // 2 A buffers x 128 columns
@@ -67,10 +80,71 @@ struct __align__(1024) SmemLayout {
 
 constexpr uint32_t kIdesc = ptx::make_idesc(128, kFeat, /*tf32*/ 2, /*A K-major*/ 0, /*B MN-major*/ 1);
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// One split warp: for every tile, read its 64 rows x 32 features from the swizzled stage
+// (lane = feature, conflict-free: the 32 lanes of a load cover one 128-byte row), split, and
+// store 8 data rows at a time as 8 TMEM columns.
+template <bool kIsLo>
+__device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, int q, int khalf,
+                                                int lane, int my_tiles,
+                                                double* __restrict__ partial_s1) {
+  const int half = q & 1;             // which 32-feature column block
+  // byte offset of (row j of an 8-row group, feature = lane) inside a stage: rows are 128 B,
+  // 32-byte chunks XOR-swizzled with (row & 3)  (TMA SWIZZLE_128B_ATOM_32B)
+  uint32_t off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    off[j] = half * kHalfBytes + khalf * (kKBlocks / 2) * 1024 + j * 128 +
+             ((((lane >> 3) ^ j) & 3) << 5) + (lane & 7) * 4;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemA +
+                             khalf * (kKBlocks / 2) * 8;
+  double s1 = 0.0;
+  for (int i = 0; i < my_tiles; ++i) {
+    const int s = i % kStages;
+    const int b = i & 1;
+    ptx::mbar_wait(&sm.full[s], (i / kStages) & 1);
+    ptx::mbar_wait(&sm.a_free[b], ((i >> 1) & 1) ^ 1);
+    ptx::tc_fence_after_sync();
+    const uint32_t stage_addr = ptx::smem_u32(sm.stage[s]);
+    const uint32_t a_addr = lane_addr + b * kTileRows;
+    float s1_tile = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < kKBlocks / 2; ++kb) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = lds_f32(stage_addr + off[j] + kb * 1024);
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t hi_bits = __float_as_uint(x[j]) & 0xFFFFE000u;
+        if (kIsLo) {
+          const float lo = x[j] - __uint_as_float(hi_bits);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[j]) : "f"(lo));
+        } else {
+          v[j] = hi_bits;
+          s1_tile += x[j];
+        }
+      }
+      ptx::tmem_st_32x32b_x8(a_addr + kb * 8, v);
+    }
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before_sync();
+    ptx::mbar_arrive(&sm.a_ready[b]);
+    if (!kIsLo) s1 += static_cast<double>(s1_tile);
+  }
+  if (!kIsLo)
+    partial_s1[(static_cast<int64_t>(blockIdx.x) * 2 + khalf) * kFeat + half * 32 + lane] = s1;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
                     double* __restrict__ partial_s2,   // [grid][128][64]
-                    double* __restrict__ partial_s1) { // [grid][64]
+                    double* __restrict__ partial_s1) { // [grid][2][64]
   extern __shared__ uint8_t smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -81,23 +155,23 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
   const int64_t tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
   const int my_tiles = static_cast<int>(tile_end - tile_begin);
 
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         ptx::mbar_init(&sm.full[s], 1);
         ptx::mbar_init(&sm.empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
-        ptx::mbar_init(&sm.a_ready[b], 128);
+        ptx::mbar_init(&sm.a_ready[b], kSplitWarps * 32);
         ptx::mbar_init(&sm.a_free[b], 1);
         ptx::mbar_init(&sm.acc_full[b], 1);
-        ptx::mbar_init(&sm.acc_empty[b], 128);
+        ptx::mbar_init(&sm.acc_empty[b], kEpiWarps * 32);
       }
       ptx::fence_mbar_init();
     }
     __syncwarp();
     ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
-  } else if (warp == 8 && lane == 0) {
+  } else if (warp == kTmaWarp && lane == 0) {
     ptx::prefetch_tensormap(&x_map);
   }
   ptx::tc_fence_before_sync();
@@ -105,7 +179,7 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
   ptx::tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // ---------------- TMA producer ----------------
     if (ptx::elect_one()) {
       for (int i = 0; i < my_tiles; ++i) {
@@ -118,7 +192,7 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
         ptx::tma_load_2d(sm.stage[s] + kHalfBytes, &x_map, &sm.full[s], kBoxCols, row0);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ---------------- MMA issuer ----------------
     if (ptx::elect_one()) {
       for (int i = 0; i < my_tiles; ++i) {
@@ -136,10 +210,11 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
         const uint32_t a_tmem = tmem + kTmemA + b * kTileRows;
 #pragma unroll
         for (int kb = 0; kb < kKBlocks; ++kb) {
-          // B = rows [8kb, 8kb+8) of the tile: K = 8 rows, N = 64 features in two 32-wide
-          // swizzle blocks kHalfBytes apart (LBO); 8-row groups are 1024 B apart (SBO).
-          const uint64_t b_desc = ptx::make_smem_desc(stage_addr + kb * 1024, kHalfBytes, 1024,
-                                                      ptx::kLayoutSwizzle128B);
+          // B = rows [8kb, 8kb+8) of the tile: K = 8 rows of 128 B, N = 64 features in two
+          // 32-wide blocks kHalfBytes apart (LBO); the 32-byte-atom swizzle repeats every 4 rows,
+          // so the two 4-row groups of one MMA are 512 B apart (SBO).
+          const uint64_t b_desc = ptx::make_smem_desc(stage_addr + kb * 1024, kHalfBytes, 512,
+                                                      ptx::kLayoutSwizzle128B32BAtom);
           ptx::mma_tf32_ts(d_tmem, a_tmem + kb * 8, b_desc, kIdesc,
                            (first_in_chunk && kb == 0) ? 0u : 1u);
         }
@@ -149,81 +224,49 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
           ptx::mma_commit(&sm.acc_full[ab]);
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < kSplitWarps) {
     // ---------------- split warps: A = [hi ; lo] into TMEM, and Sigma x ----------------
-    const int q = warp;                 // TMEM lane quadrant
-    const int half = q & 1;             // which 32-feature column block
-    const bool is_lo = q >= 2;
-    uint32_t off[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      off[j] = half * kHalfBytes + j * 128 + ((((lane >> 2) ^ j) & 7) << 4) + (lane & 3) * 4;
-    double s1 = 0.0;
-    for (int i = 0; i < my_tiles; ++i) {
-      const int s = i % kStages;
-      const int b = i & 1;
-      ptx::mbar_wait(&sm.full[s], (i / kStages) & 1);
-      ptx::mbar_wait(&sm.a_free[b], ((i >> 1) & 1) ^ 1);
-      ptx::tc_fence_after_sync();
-      const uint8_t* stage = sm.stage[s];
-      const uint32_t a_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemA + b * kTileRows;
-      float s1_tile = 0.f;
-#pragma unroll 4
-      for (int kb = 0; kb < kKBlocks; ++kb) {
-        uint32_t v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x = *reinterpret_cast<const float*>(stage + kb * 1024 + off[j]);
-          const uint32_t hi_bits = __float_as_uint(x) & 0xFFFFE000u;
-          if (is_lo) {
-            const float lo = x - __uint_as_float(hi_bits);
-            uint32_t r;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
-            v[j] = r;
-          } else {
-            v[j] = hi_bits;
-            s1_tile += x;
-          }
-        }
-        ptx::tmem_st_32x32b_x8(a_addr + kb * 8, v);
-      }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&sm.a_ready[b]);
-      s1 += static_cast<double>(s1_tile);
-    }
-    if (!is_lo) partial_s1[static_cast<int64_t>(blockIdx.x) * kFeat + half * 32 + lane] = s1;
+    // Warp w owns TMEM lanes [32 (w&3), +32): quadrants 0,1 hold hi of features 0-31 / 32-63,
+    // quadrants 2,3 hold lo.  The two warps sharing a quadrant take rows 0-63 / 64-127 of a tile.
+    const int q = warp & 3;
+    if (q < 2) split_warp_loop<false>(sm, tmem, q, warp >> 2, lane, my_tiles, partial_s1);
+    else split_warp_loop<true>(sm, tmem, q, warp >> 2, lane, my_tiles, partial_s1);
   } else {
     // ---------------- epilogue warps: TMEM fp32 chunks -> float64 registers ----------------
-    const int q = warp - 4;
-    double acc[kFeat];
+    const int q = warp & 3;
+    const int chalf = (warp - kSplitWarps) >> 2;       // columns [32 chalf, +32)
+    constexpr int kCols = kFeat / 2;
+    double acc[kCols];
 #pragma unroll
-    for (int c = 0; c < kFeat; ++c) acc[c] = 0.0;
+    for (int c = 0; c < kCols; ++c) acc[c] = 0.0;
     const int n_chunks = (my_tiles + kFlushTiles - 1) / kFlushTiles;
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int ab = chunk & 1;
       ptx::mbar_wait(&sm.acc_full[ab], (chunk >> 1) & 1);
       ptx::tc_fence_after_sync();
-      const uint32_t d_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemAcc + ab * kFeat;
-#pragma unroll
-      for (int part = 0; part < kFeat / 16; ++part) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(d_addr + part * 16, v);
-        ptx::tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[part * 16 + j] += static_cast<double>(__uint_as_float(v[j]));
-      }
+      const uint32_t d_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemAcc + ab * kFeat +
+                              chalf * kCols;
+      uint32_t v0[16], v1[16];
+      ptx::tmem_ld_32x32b_x16(d_addr, v0);
+      ptx::tmem_ld_32x32b_x16(d_addr + 16, v1);
+      ptx::tmem_wait_ld();
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&sm.acc_empty[ab]);
-    }
-    double* out = partial_s2 + (static_cast<int64_t>(blockIdx.x) * 128 + q * 32 + lane) * kFeat;
 #pragma unroll
-    for (int c = 0; c < kFeat; ++c) out[c] = acc[c];
+      for (int j = 0; j < 16; ++j) {
+        acc[j] += static_cast<double>(__uint_as_float(v0[j]));
+        acc[16 + j] += static_cast<double>(__uint_as_float(v1[j]));
+      }
+    }
+    double* out = partial_s2 + (static_cast<int64_t>(blockIdx.x) * 128 + q * 32 + lane) * kFeat +
+                  chalf * kCols;
+#pragma unroll
+    for (int c = 0; c < kCols; ++c) out[c] = acc[c];
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
 // S2[d,e] = sum_cta ( P[d][e] + P[64+d][e] + P[64+e][d] ),  S1[d] = sum_cta p1[d]
@@ -243,7 +286,7 @@ __global__ void suffstats_finalize_kernel(const double* __restrict__ partial_s2,
   }
   if (s1 != nullptr && idx < d) {
     double acc = 0.0;
-    for (int p = 0; p < n_partials; ++p) acc += partial_s1[static_cast<int64_t>(p) * kFeat + idx];
+    for (int p = 0; p < 2 * n_partials; ++p) acc += partial_s1[static_cast<int64_t>(p) * kFeat + idx];
     s1[idx] = accumulate ? s1[idx] + acc : acc;
   }
 }
@@ -278,7 +321,7 @@ int64_t suffstats_tc_workspace(int64_t n) {
   int64_t grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (tiles < grid) grid = tiles > 0 ? tiles : 1;
-  return grid * (128 * kFeat + kFeat) * static_cast<int64_t>(sizeof(double)) + 256;
+  return grid * (128 * kFeat + 2 * kFeat) * static_cast<int64_t>(sizeof(double)) + 256;
 }
 
 // s1 may be nullptr.  s1/s2 are device float64; with `accumulate` the results are added to them.
@@ -307,7 +350,7 @@ int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double
   const cuuint32_t estride[2] = {1, 1};
   CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim,
                        gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%lld d=%d)", static_cast<int>(cr),
