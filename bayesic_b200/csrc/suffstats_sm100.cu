@@ -123,8 +123,10 @@ __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, i
       for (int j = 0; j < 8; ++j) {
         const uint32_t hi_bits = __float_as_uint(x[j]) & 0xFFFFE000u;
         if (kIsLo) {
+          // lo = x - hi exactly; round it to TF32 (nearest, on the magnitude bits) so the
+          // tensor core's own truncation of A changes nothing
           const float lo = x[j] - __uint_as_float(hi_bits);
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[j]) : "f"(lo));
+          v[j] = (__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u;
         } else {
           v[j] = hi_bits;
           s1_tile += x[j];
@@ -269,25 +271,47 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
   if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
-// S2[d,e] = sum_cta ( P[d][e] + P[64+d][e] + P[64+e][d] ),  S1[d] = sum_cta p1[d]
-__global__ void suffstats_finalize_kernel(const double* __restrict__ partial_s2,
-                                          const double* __restrict__ partial_s1, int n_partials,
-                                          int d, int accumulate, double* __restrict__ s2,
-                                          double* __restrict__ s1) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < d * d) {
-    const int r = idx / d, c = idx % d;
+// S2[r,c] = sum_cta ( P[r][c] + P[64+r][c] + P[64+c][r] ),  S1[d] = sum_cta p1[d].
+// Blocks 0..nb-1: 32 consecutive outputs x 8 groups of partials each (fixed summation order:
+// deterministic); the last block reduces S1 (64 features x 4 groups).
+constexpr int kFinThreads = 256;
+__global__ void __launch_bounds__(kFinThreads)
+suffstats_finalize_kernel(const double* __restrict__ partial_s2,
+                          const double* __restrict__ partial_s1, int n_partials, int d,
+                          int accumulate, double* __restrict__ s2, double* __restrict__ s1) {
+  __shared__ double red[kFinThreads];
+  const int t = threadIdx.x;
+  if (blockIdx.x + 1 < gridDim.x) {
+    const int lane_c = t & 31, g = t >> 5;
+    const int idx = blockIdx.x * 32 + lane_c;
     double acc = 0.0;
-    for (int p = 0; p < n_partials; ++p) {
-      const double* P = partial_s2 + static_cast<int64_t>(p) * 128 * kFeat;
-      acc += P[r * kFeat + c] + P[(kFeat + r) * kFeat + c] + P[(kFeat + c) * kFeat + r];
+    if (idx < d * d) {
+      const int r = idx / d, c = idx % d;
+#pragma unroll 4
+      for (int p = g; p < n_partials; p += 8) {
+        const double* P = partial_s2 + static_cast<int64_t>(p) * 128 * kFeat;
+        acc += P[r * kFeat + c] + P[(kFeat + r) * kFeat + c] + P[(kFeat + c) * kFeat + r];
+      }
     }
-    s2[idx] = accumulate ? s2[idx] + acc : acc;
-  }
-  if (s1 != nullptr && idx < d) {
+    red[t] = acc;
+    __syncthreads();
+    if (g == 0 && idx < d * d) {
+      double total = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) total += red[j * 32 + lane_c];
+      s2[idx] = accumulate ? s2[idx] + total : total;
+    }
+  } else if (s1 != nullptr) {
+    const int f = t & 63, g = t >> 6;
     double acc = 0.0;
-    for (int p = 0; p < 2 * n_partials; ++p) acc += partial_s1[static_cast<int64_t>(p) * kFeat + idx];
-    s1[idx] = accumulate ? s1[idx] + acc : acc;
+#pragma unroll 4
+    for (int p = g; p < 2 * n_partials; p += 4) acc += partial_s1[static_cast<int64_t>(p) * kFeat + f];
+    red[t] = acc;
+    __syncthreads();
+    if (g == 0 && f < d) {
+      const double total = red[f] + red[64 + f] + red[128 + f] + red[192 + f];
+      s1[f] = accumulate ? s1[f] + total : total;
+    }
   }
 }
 
@@ -373,9 +397,8 @@ int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double
   }
   suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial_s2, partial_s1);
   BB_CHECK_LAUNCH("suffstats_tc_kernel");
-  const int fin_threads = 256;
-  const int fin_blocks = (d * d + fin_threads - 1) / fin_threads;
-  suffstats_finalize_kernel<<<fin_blocks, fin_threads, 0, stream>>>(partial_s2, partial_s1, grid, d,
+  const int fin_blocks = (d * d + 31) / 32 + 1;
+  suffstats_finalize_kernel<<<fin_blocks, kFinThreads, 0, stream>>>(partial_s2, partial_s1, grid, d,
                                                                     accumulate ? 1 : 0, s2, s1);
   BB_CHECK_LAUNCH("suffstats_finalize_kernel");
   return BB_OK;

@@ -1,0 +1,83 @@
+"""Data-parallel plumbing: shard the data axis N over one process per GPU and combine the
+per-GPU partial statistics with ONE all-reduce per minibatch.
+
+The reference has no distributed code at all; what shards is the operation its distribution
+sketch defines -- ``ExpFamIndependentObservations.sufficient_statistics`` sums the per-point
+statistics over the iid axes (``bayesic/distribution/base.py:328-332``) -- so every output of
+the pass is a sum over N and partial sums combine exactly.  Global
+parameters are replicated and updated identically on every rank from the reduced statistics;
+per-point outputs (log-responsibilities) stay sharded.
+
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the transport; the payload is one
+packed float64 buffer so the collective is a single latency-bound call.
+"""
+import numpy as np
+
+__all__ = ['shard_bounds', 'PackedStats', 'allreduce_packed', 'gaussian_suffstats_sharded']
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous, balanced shard ``[start, stop)`` of ``range(n)`` for ``rank``."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank %d of %d" % (rank, world_size))
+    base, extra = divmod(int(n), int(world_size))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+class PackedStats(object):
+    """Layout of the per-minibatch all-reduce payload.  Fields are float64 and contiguous:
+    ``PackedStats([('s2', (d, d)), ('s1', (d,)), ('count', (1,))])``."""
+
+    def __init__(self, fields):
+        self.fields = []
+        offset = 0
+        for name, shape in fields:
+            size = int(np.prod(shape)) if len(shape) else 1
+            self.fields.append((name, tuple(shape), offset, size))
+            offset += size
+        self.numel = offset
+
+    @classmethod
+    def gaussian(cls, d):
+        return cls([('s2', (d, d)), ('s1', (d,)), ('count', (1,))])
+
+    @classmethod
+    def mixture(cls, k, d):
+        return cls([('rxx', (k, d, d)), ('rx', (k, d)), ('nk', (k,)), ('sum_lse', (1,)), ('count', (1,))])
+
+    def allocate(self, device=None):
+        import torch
+        return torch.zeros(self.numel, dtype=torch.float64, device=device)
+
+    def views(self, buffer):
+        """``{name: view}`` into a packed buffer (torch tensor or numpy array); no copies."""
+        if buffer.shape[0] != self.numel:
+            raise ValueError("packed buffer has %d elements, layout needs %d" % (buffer.shape[0], self.numel))
+        return {name: buffer[offset:offset + size].reshape(shape)
+                for name, shape, offset, size in self.fields}
+
+
+def allreduce_packed(buffer, group=None):
+    """Sum the packed statistics over all ranks, in place.  A no-op without an initialised
+    process group (single GPU)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buffer, op=dist.ReduceOp.SUM, group=group)
+    return buffer
+
+
+def gaussian_suffstats_sharded(X_local, layout=None, buffer=None, group=None):
+    """``{count, s1, s2}`` of the WHOLE data set given this rank's shard ``X_local[n_local, d]``
+    (CUDA float32): local one-pass kernel, then one all-reduce.  Returns the dict of views into
+    the packed float64 buffer."""
+    from . import stats
+    n_local, d = X_local.shape
+    layout = layout or PackedStats.gaussian(d)
+    if buffer is None:
+        buffer = layout.allocate(X_local.device)
+    views = layout.views(buffer)
+    stats.gaussian_suffstats(X_local, out=(views['s1'], views['s2']))
+    views['count'].fill_(float(n_local))
+    allreduce_packed(buffer, group)
+    return views

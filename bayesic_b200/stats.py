@@ -108,8 +108,14 @@ def gaussian_expected_loglik(n, s1, s2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logd
     expectations of the natural parameters; returns a 1-element float64 CUDA tensor."""
     torch = _torch()
     lib = L.load()
-    dev = s2.device
-    d = s2.shape[0]
+    dev = None
+    for t in (s2, s1, e_lambda, e_lambda_mu):
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            dev = t.device
+            break
+    if dev is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    d = int(s2.shape[0])
 
     def f64(t):
         if not isinstance(t, torch.Tensor):

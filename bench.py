@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's metric:
+
+    data points / second per sufficient-statistic + ELBO pass
+
+Workload (N=1 and weak scaling): BASELINE config[1] -- multivariate Gaussian-Wishart
+mean-field pass, X[16 Mi, 64] float32 per GPU resident in HBM.  One step =
+  {Sigma x, Sigma x x^T} in one tcgen05 pass over X  (+ NCCL all-reduce of the packed
+  float64 statistics when N > 1)  + the expected log-likelihood (ELBO term) from them.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference ...                   # reference CPU path (numpy/BLAS port)
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value / ms_per_step are
+device-timed (CUDA events, max over ranks, barrier + synchronize on both sides); `e2e` is the
+same metric through the host-buffer API (pinned numpy in, numpy out: H2D copy of every step's
+X inside the timed region); `roofline` is the dominant kernel against the measured HBM peak;
+`cpu_baseline` is the oracle's numpy port timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "data points/sec per suff-stat+ELBO pass"
+UNIT = "points/s"
+D = 64
+N_PER_GPU = 1 << 24            # BASELINE cfg2: N = 16 Mi rows, D = 64, float32
+ALGO_BYTES_PER_POINT = 4 * D   # X read once, outputs negligible
+FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum of suffstats_tc_kernel at this workload, from
+# profiles/r01_suffstats_ncu_full.txt (one `ncu --set full` capture)
+NCU_TRAFFIC_BYTES = 4295027000 + 4994816
+
+
+def gw_hyperparameters(d, seed=1234):
+    """Fixed Gaussian-Wishart variational parameters (m, beta, W, nu) -> expectations."""
+    from oracle.closed_forms import gaussian_wishart_expectations
+    rng = np.random.RandomState(seed)
+    m = rng.randn(d) * 0.1
+    a = rng.randn(d, d)
+    W = np.linalg.inv(a @ a.T / d + np.eye(d)) / (d + 4.0)
+    return gaussian_wishart_expectations(m, 2.0, W, d + 4.0)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured'
+    except Exception:
+        return FALLBACK_HBM_GBS, 'fallback'
+
+
+class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~2 ms)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+               0x4: 'sw_power_cap'}
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.samples, self.reason_bits = [], 0
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.sm_max = None
+        self.error = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            index = self.gpu_index
+            if visible:
+                entry = visible.split(',')[self.gpu_index].strip()
+                index = int(entry) if entry.isdigit() else None
+                handle = (pynvml.nvmlDeviceGetHandleByIndex(index) if index is not None
+                          else pynvml.nvmlDeviceGetHandleByUUID(entry))
+            else:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                        self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                    except Exception as exc:      # keep sampling clocks even if reasons fail
+                        self.error = str(exc)
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as exc:
+            self.error = str(exc)
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+               "sm_max_mhz": self.sm_max, "samples": len(self.samples), "reasons": reasons}
+        if self.error and not self.samples:
+            out["error"] = self.error
+        return out
+
+
+def cpu_pass(X, expectations):
+    """The reference's CPU evaluation of the pass, as a numpy port (oracle): the plans
+    _tensordot(_dimshuffle(X,1,0), X, [1],[0]) and _sum(X, 0) (bayesic/algebra.py:527-551)
+    lowered to numpy/BLAS exactly as Theano's tensordot / sum would be
+    (algebra.py:1290-1291, 1347-1351), then the ELBO term from the statistics."""
+    from oracle.closed_forms import gaussian_expected_loglik
+    s2 = np.tensordot(X.T, X, ([1], [0]))
+    s1 = X.sum(axis=0)
+    e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet = expectations
+    return gaussian_expected_loglik(X.shape[0], s1.astype(np.float64), s2.astype(np.float64),
+                                    e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet)
+
+
+def time_cpu_baseline(sample_rows, reps, expectations):
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((sample_rows, D), dtype=np.float32)
+    cpu_pass(X[: 1 << 16], expectations)           # warm BLAS threads
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_pass(X, expectations)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return sample_rows / best, best, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    expectations = gw_hyperparameters(D)
+    sample_rows = 1 << 22          # 4 Mi rows (1 GiB) per step: bounded sample of the 16 Mi workload
+    cpu_pass(np.zeros((1 << 16, D), dtype=np.float32), expectations)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((sample_rows, D), dtype=np.float32)
+    for _ in range(max(args.warmup, 1)):
+        cpu_pass(X, expectations)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_pass(X, expectations)
+    elapsed = time.perf_counter() - t0
+    value = sample_rows * args.steps / elapsed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2 Gaussian-Wishart suff-stats + ELBO, D=64; bounded sample of "
+                               "%d rows per step of the 16 Mi-row workload" % sample_rows,
+                   "d": D, "rows_per_step": sample_rows},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d rows x %d steps, numpy/BLAS port of the reference plan "
+                                   "(reference is Python+Theano; Theano is not installable here)"
+                                   % (sample_rows, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import bayesic_b200.stats as S
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    n = args.rows
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    X = torch.randn(n, D, device=dev, dtype=torch.float32, generator=gen)
+    X.mul_(1.3).add_(0.4)
+    e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet = gw_hyperparameters(D)
+    e_lambda_d = torch.as_tensor(e_lambda, dtype=torch.float64, device=dev)
+    e_lambda_mu_d = torch.as_tensor(e_lambda_mu, dtype=torch.float64, device=dev)
+    # packed per-GPU partial statistics: [S2 (d*d) | S1 (d) | count] float64 -> one all-reduce
+    from bayesic_b200.parallel import PackedStats, allreduce_packed
+    layout = PackedStats.gaussian(D)
+    packed = layout.allocate(dev)
+    views = layout.views(packed)
+    s2, s1, count = views['s2'], views['s1'], views['count']
+    elbo = torch.zeros(1, dtype=torch.float64, device=dev)
+    total_rows = float(n * world)
+
+    def step(kernel_events=None):
+        if kernel_events is not None:
+            kernel_events[0].record()
+        S.gaussian_suffstats(X, out=(s1, s2))
+        if kernel_events is not None:
+            kernel_events[1].record()
+        if distributed:
+            count.fill_(float(n))
+            allreduce_packed(packed)
+        S.gaussian_expected_loglik(total_rows, s1, s2, e_lambda_d, e_lambda_mu_d, e_mu_l_mu,
+                                   e_logdet, out=elbo)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches_before = S.launch_count()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(kev[i])
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = S.launch_count() - launches_before
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop() if rank == 0 else None
+    if distributed:
+        t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = elapsed_ms / args.steps
+    value = total_rows / (ms_per_step * 1e-3)
+    elbo_value = float(elbo)
+
+    # ---- end to end: host buffers through the public API, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
+        host.copy_(X)
+        e_steps = max(1, min(args.steps, args.e2e_steps))
+
+        def e2e_step():
+            cnt, h1, h2 = S.gaussian_suffstats(host)          # numpy float64 out (D2H inside)
+            if distributed:
+                buf = torch.from_numpy(np.concatenate([h2.ravel(), h1, [float(cnt)]])).to(dev)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                h2 = buf[: D * D].view(D, D)
+                h1 = buf[D * D: D * D + D]
+                cnt = float(buf[-1])
+            out = S.gaussian_expected_loglik(cnt, h1, h2, e_lambda_d, e_lambda_mu_d, e_mu_l_mu,
+                                             e_logdet)
+            return float(out)                                   # D2H read of the step's result
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_value = e2e_step()
+        barrier()
+        e_elapsed = time.perf_counter() - t0
+        if distributed:
+            t = torch.tensor([e_elapsed], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_elapsed = float(t[0])
+        e2e = {"value": total_rows * e_steps / e_elapsed, "unit": UNIT,
+               "h2d_bytes_per_step": int(n * D * 4),
+               "d2h_bytes_per_step": int((D * D + D) * 8 + 8), "steps": e_steps,
+               "ms_per_step": 1e3 * e_elapsed / e_steps,
+               "elbo_matches_device_path": bool(abs(e2e_value - elbo_value) <= 1e-6 * abs(elbo_value))}
+        del host
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        achieved = ALGO_BYTES_PER_POINT * n / (kernel_ms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu_value, cpu_best, cpu_times = time_cpu_baseline(1 << 22, 5, (e_lambda, e_lambda_mu,
+                                                                             e_mu_l_mu, e_logdet))
+            cpu = {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": "4 Mi rows x 5 reps (best), numpy/BLAS port of the reference plan "
+                             "_tensordot(X^T, X) + _sum(X, 0) + ELBO from statistics"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2 Gaussian-Wishart suff-stats + ELBO: X[%d, %d] f32 per GPU, "
+                                   "sharded over N" % (n, D),
+                       "rows_per_gpu": n, "d": D, "arithmetic": "error-compensated TF32 (hi/lo split) on "
+                       "tcgen05, fp32 TMEM accumulate drained to f64",
+                       "l2": "inputs (%.1f GiB per GPU) larger than the 126 MB L2" % (n * D * 4 / 2 ** 30),
+                       "collective": "one NCCL all-reduce of %d float64 per step" % packed.numel()
+                       if distributed else "none (1 GPU)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if n == N_PER_GPU else None,
+                         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured'
+                         else "fallback (B200_PROFILING.md)",
+                         "kernel": "suffstats_tc_kernel + finalize", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "elbo": elbo_value,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--rows', type=int, default=N_PER_GPU, help='rows per GPU (default: cfg2, 16 Mi)')
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,92 @@
+"""World-size-2 gloo test (CPU) of the multi-GPU host logic: shard bounds, packed layout and the
+single all-reduce.  Local statistics come from the oracle here (no GPU in this container); the
+CUDA kernel itself is covered by the -m gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from bayesic_b200.parallel import shard_bounds, PackedStats, allreduce_packed
+
+
+def test_shard_bounds_partition_the_axis():
+    for n in (0, 1, 7, 16, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_packed_layout_views_alias_the_buffer():
+    layout = PackedStats.gaussian(3)
+    assert layout.numel == 9 + 3 + 1
+    buf = np.zeros(layout.numel)
+    v = layout.views(buf)
+    v['s2'][1, 2] = 5.0
+    v['count'][0] = 7.0
+    assert buf[5] == 5.0 and buf[-1] == 7.0
+    mix = PackedStats.mixture(4, 3)
+    assert mix.numel == 4 * 9 + 12 + 4 + 2
+    with pytest.raises(ValueError):
+        layout.views(np.zeros(5))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, d, queue):
+    import torch
+    import torch.distributed as dist
+    from oracle.closed_forms import gaussian_suffstats
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(42)                 # every rank regenerates the same data
+        X = (rng.randn(n, d) + 0.3).astype(np.float32)
+        lo, hi = shard_bounds(n, world, rank)
+        cnt, s1, s2 = gaussian_suffstats(X[lo:hi])      # local partial statistics (oracle)
+        layout = PackedStats.gaussian(d)
+        buf = layout.allocate()
+        views = layout.views(buf)
+        views['s2'].copy_(torch.from_numpy(s2))
+        views['s1'].copy_(torch.from_numpy(s1))
+        views['count'].fill_(float(cnt))
+        allreduce_packed(buf)                           # ONE collective
+        queue.put((rank, buf.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_reproduces_the_full_statistics():
+    import torch.multiprocessing as mp
+    from oracle.closed_forms import gaussian_suffstats
+    world, n, d = 2, 1001, 6
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, d, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.RandomState(42)
+    X = (rng.randn(n, d) + 0.3).astype(np.float32)
+    cnt, s1, s2 = gaussian_suffstats(X)
+    layout = PackedStats.gaussian(d)
+    for rank in range(world):
+        v = layout.views(results[rank])
+        np.testing.assert_allclose(v['s2'], s2, rtol=1e-12)
+        np.testing.assert_allclose(v['s1'], s1, rtol=1e-12)
+        assert v['count'][0] == cnt
+    np.testing.assert_array_equal(results[0], results[1])    # replicas agree bit for bit
