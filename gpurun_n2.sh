@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 50 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "exit $?"; cat gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
+timeout 600 python bench.py --steps 100 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "exit $?"; cat gpurun_out/bench_n1.json

@@ -1,0 +1,65 @@
+"""Pins the float64 closed-form oracle (oracle/closed_forms.py) against scipy.stats / scipy.special,
+since no reference output can exist for bayesic/distribution/ (it does not parse)."""
+import numpy as np
+from scipy.special import logsumexp
+from scipy.stats import multivariate_normal, wishart
+
+from oracle import closed_forms as O
+
+
+def _spd(rng, d):
+    a = rng.randn(d, d)
+    return a @ a.T / d + np.eye(d)
+
+
+def test_mvn_log_likelihood_matches_scipy():
+    rng = np.random.RandomState(0)
+    X, mean, prec = rng.randn(200, 5), rng.randn(5), _spd(rng, 5)
+    want = multivariate_normal(mean, np.linalg.inv(prec)).logpdf(X).sum()
+    np.testing.assert_allclose(O.mvn_log_likelihood(X, mean, prec), want, rtol=1e-12)
+
+
+def test_suffstats_are_the_iid_sums():
+    rng = np.random.RandomState(1)
+    X = rng.randn(37, 4).astype(np.float32)
+    n, s1, s2 = O.gaussian_suffstats(X)
+    assert n == 37
+    np.testing.assert_allclose(s1, sum(x.astype('f8') for x in X), rtol=1e-13)
+    np.testing.assert_allclose(s2, sum(np.outer(x, x).astype('f8') for x in X.astype('f8')), rtol=1e-13)
+
+
+def test_gaussian_wishart_expectations_by_monte_carlo_and_identities():
+    rng = np.random.RandomState(2)
+    d, beta, nu = 3, 2.5, 9.0
+    m, W = rng.randn(d), np.linalg.inv(_spd(rng, d)) / nu
+    e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet = O.gaussian_wishart_expectations(m, beta, W, nu)
+    np.testing.assert_allclose(e_lambda, nu * W, rtol=1e-13)
+    np.testing.assert_allclose(e_lambda_mu, nu * W @ m, rtol=1e-13)
+    samples = wishart(df=nu, scale=W).rvs(size=40000, random_state=3)
+    logdets = np.linalg.slogdet(samples)[1]
+    assert abs(logdets.mean() - e_logdet) < 4 * logdets.std() / np.sqrt(len(logdets))
+    # E[mu^T Lambda mu] with mu | Lambda ~ N(m, (beta Lambda)^-1): d/beta + m^T E[Lambda] m
+    np.testing.assert_allclose(e_mu_l_mu, d / beta + m @ e_lambda @ m, rtol=1e-13)
+
+
+def test_expected_loglik_reduces_to_loglik_for_a_point_posterior():
+    # with E[Lambda]=Lambda, E[Lambda mu]=Lambda mu, E[mu' Lambda mu]=mu' Lambda mu, E[log|L|]=log|L|
+    rng = np.random.RandomState(4)
+    X, mean, prec = rng.randn(100, 4), rng.randn(4), _spd(rng, 4)
+    n, s1, s2 = O.gaussian_suffstats(X)
+    got = O.gaussian_expected_loglik(n, s1, s2, prec, prec @ mean, mean @ prec @ mean,
+                                     np.linalg.slogdet(prec)[1])
+    np.testing.assert_allclose(got, O.mvn_log_likelihood(X, mean, prec), rtol=1e-12)
+
+
+def test_log_responsibilities_and_weighted_stats():
+    rng = np.random.RandomState(5)
+    Lg = rng.randn(50, 7) * 4
+    lr, lse = O.log_responsibilities(Lg)
+    np.testing.assert_allclose(lse, logsumexp(Lg, axis=1), rtol=1e-13)
+    np.testing.assert_allclose(np.exp(lr).sum(1), 1.0, rtol=1e-12)
+    X, R = rng.randn(50, 3), np.exp(lr)
+    nk, rx, rxx = O.weighted_suffstats(X, R)
+    np.testing.assert_allclose(nk.sum(), 50.0, rtol=1e-12)
+    np.testing.assert_allclose(rx.sum(0), X.sum(0), rtol=1e-12)
+    np.testing.assert_allclose(rxx.sum(0), X.T @ X, rtol=1e-12)
