@@ -271,15 +271,15 @@ BB_API int bb_logsoftmax_rows(const float* logits, int64_t n, int32_t k, float* 
 }
 
 BB_API int64_t bb_suffstats_weighted_workspace(int64_t n, int32_t d, int32_t k) {
-  return weighted_stats_workspace(n, d, k) + 256;
+  return weighted_stats_auto_workspace(n, d, k) + 256;
 }
 
 BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int32_t d, int32_t k, double* Nk,
                           double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
                           void* stream) {
   if (n < 0 || !sum_rxx || (n > 0 && (!X || !R))) { set_error("suffstats_weighted: bad arguments"); return BB_ERR_INVALID; }
-  return launch_weighted_stats(X, R, n, d, k, Nk, sum_rx, sum_rxx, workspace, workspace_bytes,
-                               static_cast<cudaStream_t>(stream));
+  return launch_weighted_stats_auto(X, R, n, d, k, Nk, sum_rx, sum_rxx, workspace, workspace_bytes,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -469,10 +469,13 @@ int run_node(Exec& ex, int idx) {
         BB_TRY(ex.materialize(X, &X));
         BB_TRY(ex.alloc_floats(idx, out.numel(), &out.ptr));
         void* acc = nullptr;
+        void* wws = nullptr;
         BB_TRY(ex.alloc_scratch(out.numel() * 8, &acc));
+        const int64_t wws_bytes = weighted_stats_auto_workspace(n, static_cast<int>(d), static_cast<int>(k));
+        BB_TRY(ex.alloc_scratch(wws_bytes, &wws));
         if (!ex.dry()) {
-          BB_TRY(launch_weighted_stats(X.ptr, R.ptr, n, static_cast<int>(d), static_cast<int>(k), nullptr,
-                                       nullptr, static_cast<double*>(acc), nullptr, 0, ex.stream));
+          BB_TRY(launch_weighted_stats_auto(X.ptr, R.ptr, n, static_cast<int>(d), static_cast<int>(k), nullptr,
+                                            nullptr, static_cast<double*>(acc), wws, wws_bytes, ex.stream));
           BB_TRY(launch_f64_to_f32(static_cast<const double*>(acc), out.ptr, out.numel(), ex.stream));
         }
       }

@@ -36,6 +36,18 @@ int launch_weighted_stats(const float* x, const float* r, int64_t n, int d, int 
                           double* sum_rx, double* sum_rxx, void* workspace,
                           int64_t workspace_bytes, cudaStream_t stream);
 
+// weighted_sm100.cu
+bool weighted_tc_supported(int64_t n, int d, int k, const void* x, const void* r);
+int64_t weighted_tc_workspace(int64_t n, int k);
+int launch_weighted_stats_tc(const float* x, const float* r, int64_t n, int d, int k, double* nk,
+                             double* sum_rx, double* sum_rxx, void* workspace,
+                             int64_t workspace_bytes, cudaStream_t stream);
+// tcgen05 kernel when the shape allows it (and BB_WEIGHTED_SIMT is unset), SIMT kernel otherwise
+int64_t weighted_stats_auto_workspace(int64_t n, int d, int k);
+int launch_weighted_stats_auto(const float* x, const float* r, int64_t n, int d, int k, double* nk,
+                               double* sum_rx, double* sum_rxx, void* workspace,
+                               int64_t workspace_bytes, cudaStream_t stream);
+
 // stats_kernels.cu
 int launch_f32_to_f64(const float* in, double* out, int64_t n, cudaStream_t stream);
 int launch_gaussian_expected_loglik(const double* s1, const double* s2, double n,

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -324,6 +325,24 @@ int launch_weighted_stats(const float* x, const float* r, int64_t n, int d, int 
                                                        sum_rxx);
   BB_CHECK_LAUNCH("weighted_stats_simt_kernel");
   return BB_OK;
+}
+
+
+int64_t weighted_stats_auto_workspace(int64_t n, int d, int k) {
+  int64_t need = 256;
+  if (d >= 4 && d <= 64 && d % 4 == 0 && k % 4 == 0 && n > 0) need = std::max(need, weighted_tc_workspace(n, k));
+  return need;
+}
+
+int launch_weighted_stats_auto(const float* x, const float* r, int64_t n, int d, int k, double* nk,
+                               double* sum_rx, double* sum_rxx, void* workspace,
+                               int64_t workspace_bytes, cudaStream_t stream) {
+  static const bool force_simt = getenv("BB_WEIGHTED_SIMT") != nullptr;
+  // the tensor-core kernel pays off once there are enough rows to amortise its per-CTA setup
+  if (!force_simt && n >= 1024 && weighted_tc_supported(n, d, k, x, r) && workspace != nullptr &&
+      workspace_bytes >= weighted_tc_workspace(n, k))
+    return launch_weighted_stats_tc(x, r, n, d, k, nk, sum_rx, sum_rxx, workspace, workspace_bytes, stream);
+  return launch_weighted_stats(x, r, n, d, k, nk, sum_rx, sum_rxx, workspace, workspace_bytes, stream);
 }
 
 }  // namespace bb

@@ -123,8 +123,9 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
-      "r"(v[7])
-      : "memory");
+      "r"(v[7]));   // no "memory" clobber: it moves registers to TMEM only, and leaving it out
+                    // lets the compiler software-pipeline the shared-memory loads around it;
+                    // tcgen05.wait::st / the fences keep theirs
 }
 __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

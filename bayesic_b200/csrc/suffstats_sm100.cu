@@ -136,7 +136,8 @@ __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, i
     }
     ptx::tmem_wait_st();
     ptx::tc_fence_before_sync();
-    ptx::mbar_arrive(&sm.a_ready[b]);
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&sm.a_ready[b]);
     if (!kIsLo) s1 += static_cast<double>(s1_tile);
   }
   if (!kIsLo)
@@ -164,10 +165,10 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
         ptx::mbar_init(&sm.empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
-        ptx::mbar_init(&sm.a_ready[b], kSplitWarps * 32);
+        ptx::mbar_init(&sm.a_ready[b], kSplitWarps);     // one elected arrival per split warp
         ptx::mbar_init(&sm.a_free[b], 1);
         ptx::mbar_init(&sm.acc_full[b], 1);
-        ptx::mbar_init(&sm.acc_empty[b], kEpiWarps * 32);
+        ptx::mbar_init(&sm.acc_empty[b], kEpiWarps);
       }
       ptx::fence_mbar_init();
     }
@@ -253,7 +254,8 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
       ptx::tmem_ld_32x32b_x16(d_addr + 16, v1);
       ptx::tmem_wait_ld();
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&sm.acc_empty[ab]);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.acc_empty[ab]);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         acc[j] += static_cast<double>(__uint_as_float(v0[j]));

@@ -147,7 +147,9 @@ def test_log_responsibilities_extremes():
     np.testing.assert_allclose(lse.cpu().numpy(), ref_lse, rtol=1e-6)
 
 
-@pytest.mark.parametrize('n,d,k', [(1000, 64, 8), (4099, 16, 5), (300, 6, 3), (50000, 64, 16), (1, 4, 1)])
+@pytest.mark.parametrize('n,d,k', [(1000, 64, 8), (4099, 16, 5), (300, 6, 3), (50000, 64, 16), (1, 4, 1),
+                                   (2048, 64, 4), (5000, 32, 8), (40000, 64, 256), (1025, 16, 12),
+                                   (300000, 64, 8)])
 def test_weighted_suffstats(n, d, k):
     import torch
     rng = np.random.RandomState(n + d + k)
@@ -158,3 +160,23 @@ def test_weighted_suffstats(n, d, k):
     _close(nk.cpu().numpy(), rnk)
     _close(rx.cpu().numpy(), rrx, scale_atol=1e-5)
     _close(rxx.cpu().numpy(), rrxx, scale_atol=1e-5)
+    got = rxx.cpu().numpy()
+    np.testing.assert_allclose(got, np.swapaxes(got, 1, 2), rtol=1e-5,
+                               atol=1e-6 * np.abs(got).max())               # symmetric
+
+
+def test_weighted_suffstats_sum_over_components_is_the_plain_statistic():
+    # responsibilities sum to one per row => sum_k Srxx[k] = S2, sum_k Srx[k] = S1, sum_k Nk = n
+    import torch
+    rng = np.random.RandomState(9)
+    n, d, k = 200000, 64, 16
+    X = torch.from_numpy((rng.randn(n, d) + 0.3).astype(np.float32)).cuda()
+    R = torch.from_numpy(rng.dirichlet(np.ones(k) * 0.3, size=n).astype(np.float32)).cuda()
+    nk, rx, rxx = S.weighted_suffstats(X, R)
+    _, s1, s2 = S.gaussian_suffstats(X)
+    rowsum = R.double().sum(1, keepdim=True)           # float32 rows do not sum to exactly 1
+    Xw = X.double() * rowsum
+    np.testing.assert_allclose(rxx.sum(0).cpu().numpy(), (Xw.T @ X.double()).cpu().numpy(), rtol=2e-5,
+                               atol=1e-6 * float(s2.abs().max()))
+    np.testing.assert_allclose(rx.sum(0).cpu().numpy(), Xw.sum(0).cpu().numpy(), rtol=1e-5)
+    assert abs(float(nk.sum()) - float(rowsum.sum())) <= 1e-6 * n
