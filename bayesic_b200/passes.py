@@ -1,0 +1,125 @@
+"""The per-minibatch passes of the five BASELINE configurations, assembled from compiled einsum
+plans (``bayesic_b200.algebra`` -> C-ABI executor) and the fused kernels in ``stats``.
+
+The reference names these algorithms only in prose (VMP ``README.md:30-37``, reparameterised
+gradients ``:47-51``, minibatch SVI ``:69-80``); what it has as code is the expression layer
+they would be written in.  Each pass here is therefore written the way a user of the reference
+would write it -- tensor expressions compiled once, called per minibatch -- and every
+data-axis contraction lands on a device kernel:
+
+  cfg1/2  Gaussian(-Wishart) statistics + expected log-likelihood   ``gaussian_pass``
+  cfg3    GMM VMP local step: logits -> responsibilities -> weighted stats ``GmmStep``
+  cfg4    conjugate natural-gradient SVI step for linear regression  ``LinRegSviStep``
+  cfg5    reparameterised ELBO gradient, logistic regression          ``LogisticReparamGrad``
+
+Global parameters are tiny and replicated; data stays sharded/resident (CUDA tensors in, CUDA
+tensors out).  Parameter-space linear algebra (D x D, K x D x D) uses torch float64 on the
+device -- plumbing around the hot path, not part of it.
+"""
+import math
+
+import numpy as np
+
+from . import algebra as A
+from . import stats
+from .backend.compiled import compile_many
+
+__all__ = ['gaussian_pass', 'GmmStep', 'LinRegSviStep', 'LogisticReparamGrad']
+
+_LOG_2PI = math.log(2.0 * math.pi)
+
+
+def gaussian_pass(X, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet):
+    """cfg1/cfg2: ``{n, sum x, sum x x^T}`` in one pass and the expected log-likelihood under
+    q(mu, Lambda).  Returns ``(n, s1, s2, elbo_term)`` (float64 CUDA tensors)."""
+    n, s1, s2 = stats.gaussian_suffstats(X)
+    ell = stats.gaussian_expected_loglik(n, s1, s2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet)
+    return n, s1, s2, ell
+
+
+class GmmStep(object):
+    """cfg3: local VMP step of a Gaussian mixture with Gaussian-Wishart factors.
+
+    logits[n,k] = c_k - nu_k/2 (x_n - m_k)^T W_k (x_n - m_k) is written as one einsum plan
+    ``c_k + x.b_k - 1/2 x^T A_k x`` with A_k = nu_k W_k, b_k = A_k m_k; then the fused
+    log-softmax kernel gives log r and sum_n lse, and the tcgen05 weighted-statistics kernel
+    gives {N_k, sum r x, sum r x x^T} without materialising K x D x N."""
+
+    def __init__(self):
+        X, Ak, bk, ck = A.var('X', 2), A.var('Ak', 3), A.var('bk', 2), A.var('ck', 1)
+        quad = A.einsum([(X, [('out', 0), ('sum', 0)]), (Ak, [('out', 1), ('sum', 0), ('sum', 1)]),
+                         (X, [('out', 0), ('sum', 1)])], 2)
+        lin = A.dot(X, bk.T)
+        self.logits_fn = (lin + (-0.5) * quad + ck.dimshuffle('x', 0)).compile()
+
+    @staticmethod
+    def expectations(log_pi, m, beta, W, nu):
+        """Per-component (A_k, b_k, c_k) from the variational parameters (float64 numpy in)."""
+        from scipy.special import digamma
+        k, d = m.shape
+        Ak = nu[:, None, None] * W
+        bk = np.einsum('kde,ke->kd', Ak, m)
+        logdet_w = np.linalg.slogdet(W)[1]
+        e_logdet = digamma(0.5 * (nu[:, None] - np.arange(d)[None, :])).sum(1) + d * math.log(2.0) + logdet_w
+        ck = (log_pi + 0.5 * e_logdet - 0.5 * d * _LOG_2PI - 0.5 * d / beta
+              - 0.5 * np.einsum('kd,kd->k', bk, m))
+        return Ak.astype(np.float32), bk.astype(np.float32), ck.astype(np.float32)
+
+    def __call__(self, X, Ak, bk, ck):
+        import torch
+        logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
+        log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place
+        resp = torch.exp(log_resp)
+        nk, rx, rxx = stats.weighted_suffstats(X, resp)
+        return {'log_resp': log_resp, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
+
+
+class LinRegSviStep(object):
+    """cfg4: conjugate natural-gradient SVI for Bayesian linear regression (noise precision tau).
+    The minibatch statistics {X^T X, X^T y, y^T y} come from ONE compiled plan; the natural
+    parameter blend and the expected log-likelihood are float64 parameter-space arithmetic."""
+
+    def __init__(self):
+        X, y = A.var('X', 2), A.var('y', 1)
+        self.stats_fn = compile_many([A.dot(X.T, X), A.dot(X.T, y), A.dot(y, y)])
+
+    def __call__(self, X, y, eta1, eta2, tau, n_total, rho, eta1_prior, eta2_prior):
+        import torch
+        xtx, xty, yty = self.stats_fn(X=X, y=y)
+        b = X.shape[0]
+        xtx, xty, yty = xtx.double(), xty.double(), yty.double()
+        scale = float(n_total) / float(b)
+        new1 = (1 - rho) * eta1 + rho * (eta1_prior + scale * tau * xty)
+        new2 = (1 - rho) * eta2 + rho * (eta2_prior - 0.5 * scale * tau * xtx)
+        cov = torch.linalg.inv(-2.0 * new2)
+        mean = cov @ new1
+        e_wwT = cov + torch.outer(mean, mean)
+        ell = 0.5 * b * (math.log(tau) - _LOG_2PI) - 0.5 * tau * (yty - 2 * mean @ xty + (e_wwT * xtx).sum())
+        return {'xtx': xtx, 'xty': xty, 'yty': yty, 'eta1': new1, 'eta2': new2, 'ell': ell}
+
+
+class LogisticReparamGrad(object):
+    """cfg5: reparameterised ELBO gradient for Bayesian logistic regression, S fixed draws.
+    Written in the reference's vocabulary: softplus(z) = log(1 + exp(z)),
+    sigmoid(z) = (1 + exp(-z))**-1 (``algebra.py:1435-1448`` has log/exp/pow only)."""
+
+    def __init__(self):
+        X, y, Wm = A.var('X', 2), A.var('y', 1), A.var('Wm', 2)        # Wm[S, D]
+        Z = A.dot(X, Wm.T)                                            # [B, S]
+        ycol = y.dimshuffle(0, 'x')
+        loglik = A.sum(ycol * Z - A.log(1 + A.exp(Z)), axis=0)        # [S]
+        resid = ycol - (1 + A.exp(-1 * Z)) ** -1                      # [B, S]
+        G = A.dot(X.T, resid)                                         # [D, S]
+        self.fn = compile_many([loglik, G])
+
+    def __call__(self, X, y, mu, log_sigma, eps):
+        import torch
+        sigma = torch.exp(log_sigma)
+        Wm = (mu[None, :] + sigma[None, :] * eps).to(torch.float32)
+        loglik, G = self.fn(X=X, y=y, Wm=Wm)
+        G = G.double()
+        kl = 0.5 * torch.sum(sigma ** 2 + mu ** 2 - 1.0 - 2.0 * log_sigma)
+        grad_mu = G.mean(dim=1) - mu
+        grad_ls = (G * eps.T).mean(dim=1) * sigma - sigma ** 2 + 1.0
+        return {'elbo': loglik.double().mean() - kl, 'G': G, 'grad_mu': grad_mu,
+                'grad_log_sigma': grad_ls}

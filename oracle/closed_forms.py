@@ -76,3 +76,74 @@ def weighted_suffstats(X, R):
     X = np.asarray(X, dtype=np.float64)
     R = np.asarray(R, dtype=np.float64)
     return R.sum(axis=0), R.T @ X, np.einsum('nk,nd,ne->kde', R, X, X)
+
+
+# ---- BASELINE configs 3-5: float64 restatements of the passes (north-star text; README.md:30-37,
+# 47-51, 69-80 describe the algorithms, the reference has no code for them) -----------------------
+
+def gmm_expected_logits(X, log_pi, m, beta, W, nu):
+    """E_q[log pi_k] + E_q[log N(x_n | mu_k, Lambda_k^-1)] for a Gaussian mixture with
+    Gaussian-Wishart factors (Bishop PRML 10.46, 10.64-10.66):
+      logits[n,k] = log_pi[k] + 1/2 E[log|L_k|] - D/2 log 2pi - D/(2 beta_k)
+                    - nu_k/2 (x_n - m_k)^T W_k (x_n - m_k)"""
+    X = np.asarray(X, dtype=np.float64)
+    n, d = X.shape
+    k = m.shape[0]
+    out = np.empty((n, k))
+    for j in range(k):
+        _, logdet_w = np.linalg.slogdet(W[j])
+        e_logdet = digamma(0.5 * (nu[j] - np.arange(d))).sum() + d * np.log(2.0) + logdet_w
+        diff = X - m[j]
+        quad = np.einsum('nd,de,ne->n', diff, W[j], diff)
+        out[:, j] = log_pi[j] + 0.5 * e_logdet - 0.5 * d * LOG_2PI - 0.5 * d / beta[j] - 0.5 * nu[j] * quad
+    return out
+
+
+def gmm_vmp_step(X, log_pi, m, beta, W, nu):
+    """One local step of mean-field VMP for a GMM: logits -> log-softmax responsibilities ->
+    {N_k, sum r x, sum r x x^T} and sum_n logsumexp (the data-dependent part of the ELBO)."""
+    logits = gmm_expected_logits(X, log_pi, m, beta, W, nu)
+    log_r, lse = log_responsibilities(logits)
+    nk, rx, rxx = weighted_suffstats(X, np.exp(log_r))
+    return {'logits': logits, 'log_resp': log_r, 'nk': nk, 'rx': rx, 'rxx': rxx, 'sum_lse': lse.sum()}
+
+
+def linreg_svi_step(X, y, eta1, eta2, tau, n_total, rho, eta1_prior, eta2_prior):
+    """Conjugate natural-gradient SVI step for Bayesian linear regression with known noise
+    precision tau (Hoffman et al. 2013, README.md:69-80): minibatch statistics
+    {X^T X, X^T y, y^T y, B}, then
+      eta <- (1 - rho) eta + rho (eta_prior + (N_total / B) [tau X^T y, -1/2 tau X^T X]),
+    and the expected log-likelihood of the minibatch under q(w) = N(mean, cov) (from the
+    updated natural parameters)."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    b, d = X.shape
+    xtx, xty, yty = X.T @ X, X.T @ y, y @ y
+    scale = n_total / float(b)
+    new1 = (1 - rho) * eta1 + rho * (eta1_prior + scale * tau * xty)
+    new2 = (1 - rho) * eta2 + rho * (eta2_prior - 0.5 * scale * tau * xtx)
+    cov = np.linalg.inv(-2.0 * new2)
+    mean = cov @ new1
+    e_wwT = cov + np.outer(mean, mean)
+    ell = 0.5 * b * (np.log(tau) - LOG_2PI) - 0.5 * tau * (yty - 2 * mean @ xty + np.sum(e_wwT * xtx))
+    return {'xtx': xtx, 'xty': xty, 'yty': yty, 'eta1': new1, 'eta2': new2, 'ell': ell}
+
+
+def logistic_reparam_gradient(X, y, mu, log_sigma, eps):
+    """Reparameterised ELBO gradient for Bayesian logistic regression with q(w) = N(mu,
+    diag sigma^2), prior N(0, I) and S fixed standard-normal draws eps[S, D] (README.md:47-51):
+      W_s = mu + sigma * eps_s;  Z = X W^T;  l = y z - softplus(z)
+      elbo = mean_s sum_n l - KL;  G = X^T (y - sigmoid(Z))  [D, S]
+      grad_mu = mean_s G_s - mu;  grad_log_sigma = mean_s G_s * eps_s * sigma - sigma^2 + 1"""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    sigma = np.exp(log_sigma)
+    Wm = mu[None, :] + sigma[None, :] * eps                  # [S, D]
+    Z = X @ Wm.T                                             # [B, S]
+    softplus = np.logaddexp(0.0, Z)
+    ll = (y[:, None] * Z - softplus).sum(axis=0)             # [S]
+    G = X.T @ (y[:, None] - 1.0 / (1.0 + np.exp(-Z)))        # [D, S]
+    kl = 0.5 * np.sum(sigma ** 2 + mu ** 2 - 1.0 - 2.0 * log_sigma)
+    grad_mu = G.mean(axis=1) - mu
+    grad_ls = (G * eps.T).mean(axis=1) * sigma - sigma ** 2 + 1.0
+    return {'Z': Z, 'elbo': ll.mean() - kl, 'G': G, 'grad_mu': grad_mu, 'grad_log_sigma': grad_ls}

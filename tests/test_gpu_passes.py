@@ -1,0 +1,101 @@
+"""GPU parity of the five BASELINE-config passes (bayesic_b200/passes.py) against their float64
+restatements in oracle/closed_forms.py, at sizes the oracle finishes in seconds.  Tolerance:
+rtol 1e-4 (north-star), atol scaled to the magnitude of each output."""
+import numpy as np
+import pytest
+
+import bayesic_b200.passes as P
+from oracle import closed_forms as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, want, rtol=1e-4, scale_atol=2e-6):
+    got = np.asarray(got.detach().cpu().numpy() if hasattr(got, 'detach') else got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=scale_atol * max(1.0, np.abs(want).max()))
+
+
+def _spd(rng, d):
+    a = rng.randn(d, d)
+    return a @ a.T / d + np.eye(d)
+
+
+def test_cfg2_gaussian_pass():
+    import torch
+    rng = np.random.RandomState(0)
+    n, d = 20000, 64
+    X = (rng.randn(n, d) * 1.2 + 0.3).astype(np.float32)
+    ex = O.gaussian_wishart_expectations(rng.randn(d) * 0.1, 2.0, np.linalg.inv(_spd(rng, d)) / (d + 4.0), d + 4.0)
+    cnt, s1, s2, ell = P.gaussian_pass(torch.from_numpy(X).cuda(), *ex)
+    rn, r1, r2 = O.gaussian_suffstats(X)
+    _close(s1, r1)
+    _close(s2, r2)
+    _close(ell, [O.gaussian_expected_loglik(rn, r1, r2, *ex)])
+
+
+def test_cfg3_gmm_vmp_step():
+    import torch
+    rng = np.random.RandomState(1)
+    n, d, k = 4096, 16, 8
+    centers = rng.randn(k, d) * 3
+    X = (centers[rng.randint(k, size=n)] + rng.randn(n, d)).astype(np.float32)
+    log_pi = np.log(rng.dirichlet(np.ones(k)))
+    m = centers + rng.randn(k, d) * 0.1
+    beta = rng.rand(k) * 5 + 1
+    nu = d + 2 + rng.rand(k) * 5
+    W = np.stack([np.linalg.inv(_spd(rng, d)) / nu[j] for j in range(k)])
+    want = O.gmm_vmp_step(X, log_pi, m, beta, W, nu)
+    step = P.GmmStep()
+    Ak, bk, ck = step.expectations(log_pi, m, beta, W, nu)
+    got = step(torch.from_numpy(X).cuda(), torch.from_numpy(Ak).cuda(), torch.from_numpy(bk).cuda(),
+               torch.from_numpy(ck).cuda())
+    # log-responsibilities: float32 logits of magnitude ~1e2 limit the absolute accuracy
+    np.testing.assert_allclose(got['log_resp'].cpu().numpy(), want['log_resp'], rtol=1e-4, atol=2e-3)
+    _close(got['nk'], want['nk'], rtol=1e-4, scale_atol=1e-5)
+    _close(got['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
+    _close(got['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
+    assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
+
+
+def test_cfg4_linreg_svi_step():
+    import torch
+    rng = np.random.RandomState(2)
+    b, d = 8192, 128
+    X = rng.randn(b, d).astype(np.float32)
+    w_true = rng.randn(d) / np.sqrt(d)
+    y = (X @ w_true + 0.1 * rng.randn(b)).astype(np.float32)
+    tau, n_total, rho = 100.0, 10 * b, 0.3
+    eta1_prior, eta2_prior = np.zeros(d), -0.5 * np.eye(d)
+    eta1, eta2 = rng.randn(d) * 0.1, -0.5 * _spd(rng, d) * 10
+    want = O.linreg_svi_step(X, y, eta1, eta2, tau, n_total, rho, eta1_prior, eta2_prior)
+    dev = torch.device('cuda')
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    got = P.LinRegSviStep()(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), t(eta1), t(eta2), tau,
+                            n_total, rho, t(eta1_prior), t(eta2_prior))
+    _close(got['xtx'], want['xtx'], scale_atol=1e-5)
+    _close(got['xty'], want['xty'], scale_atol=1e-5)
+    _close(got['yty'], want['yty'])
+    _close(got['eta1'], want['eta1'], scale_atol=1e-5)
+    _close(got['eta2'], want['eta2'], scale_atol=1e-5)
+    assert abs(float(got['ell']) - want['ell']) <= 1e-4 * abs(want['ell'])
+
+
+def test_cfg5_logistic_reparam_gradient():
+    import torch
+    rng = np.random.RandomState(3)
+    b, d, s = 4096, 64, 16
+    X = rng.randn(b, d).astype(np.float32)
+    w_true = rng.randn(d) / np.sqrt(d)
+    y = (rng.rand(b) < 1 / (1 + np.exp(-X @ w_true))).astype(np.float32)
+    mu, log_sigma = rng.randn(d) * 0.1, np.log(0.1 + 0.05 * rng.rand(d))
+    eps = rng.randn(s, d)
+    want = O.logistic_reparam_gradient(X, y, mu, log_sigma, eps)
+    dev = torch.device('cuda')
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    got = P.LogisticReparamGrad()(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), t(mu), t(log_sigma), t(eps))
+    _close(got['G'], want['G'], scale_atol=2e-5)
+    _close(got['grad_mu'], want['grad_mu'], scale_atol=2e-5)
+    _close(got['grad_log_sigma'], want['grad_log_sigma'], scale_atol=2e-5)
+    assert abs(float(got['elbo']) - want['elbo']) <= 1e-4 * abs(want['elbo'])
