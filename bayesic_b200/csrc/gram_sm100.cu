@@ -20,7 +20,7 @@
 //     <= 2^-16 relative, unbiased because both splits round to nearest).  Three kind::f16 MMAs
 //     cost 1.5x one TF32 pass (3xTF32 would cost 3x);
 //   * no fp32 staging: 16 converter warps load X with coalesced 128-bit loads straight into
-//     registers (prefetched one stage ahead), split, and store b1/b2 into shared memory in the
+//     registers (each warp group two stages ahead), split, and store b1/b2 into shared memory in the
 //     UMMA MN-major SWIZZLE_128B canonical layout (the data axis is the MMA K axis, so X's
 //     row-major layout IS MN-major: no transpose).  Shared memory therefore carries only the
 //     bf16 tiles (1 KB/row written, 1.5 KB/row read by the tensor core);
@@ -39,6 +39,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -56,17 +57,19 @@ constexpr int kTileBytes = kHalf * kStageRows * 2;      // one bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;             // A.b1, A.b2, B.b1, B.b2: 32 KB
 constexpr int kFlushIters = 64;           // TMEM accumulators drained every 64 stages = 2048 rows
 constexpr int kConvWarps = 16;
+constexpr int kConvGroups = 2;           // warp groups taking alternate stages
+constexpr int kRowsPerWarp = kStageRows / (kConvWarps / kConvGroups);   // 4
+constexpr int kXtyFlushIters = 8;         // X^T y: fp32 partial sums over 8 x 4 rows, then float64
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = kConvWarps + kEpiWarps;        // warp 20 (20 % 4 == 0 is irrelevant for it)
 constexpr int kThreads = (kMmaWarp + 1) * 32;           // 672
 constexpr int kTmemCols = 512;            // 2 accumulator buffers x 256 columns
-constexpr int kPrefetchDist = 6;          // stages ahead for the L2 prefetch hints
 
 struct __align__(1024) SmemLayout {
   uint8_t stage[kStages][kStageBytes];
   double xty[kHalf];
   double yty;
-  uint64_t full[kStages];        // leader: 2 CTAs x kConvWarps arrivals
+  uint64_t full[kStages];        // leader: 2 CTAs x (kConvWarps / kConvGroups) arrivals (one warp group per stage)
   uint64_t empty[kStages];       // each CTA: one multicast MMA commit
   uint64_t acc_full[2];          // each CTA: one multicast MMA commit
   uint64_t acc_empty[2];         // leader: 2 CTAs x kEpiWarps arrivals
@@ -91,6 +94,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(ptx::smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+// Same without a release fence: ordering is provided by the caller (every lane has executed
+// fence.proxy.async -- SASS: MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC -- so its shared-memory stores
+// have completed, then __syncwarp).  A release.cluster arrive compiles to MEMBAR.ALL.GPU, which
+// on the per-stage path costs more than the whole MMA budget.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
       ::"r"(ptx::smem_u32(bar)), "r"(rank)
       : "memory");
 }
@@ -182,17 +197,134 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
   b2[1] = *reinterpret_cast<uint32_t*>(&q1);
 }
 
-struct RowRegs {
-  float4 a, b;
-  float y;
+
+struct ConvArgs {
+  const float* x;
+  const float* y;
+  int64_t n, row_begin;
+  int d, feat_a, feat_b, n_iters, warp, lane;
+  bool want_yty;
 };
+
+// Converter warps.  Two groups of eight warps; group g = warp & 1 owns every 2nd stage
+// (it = g, g + 2, ...), warp wi = warp >> 1 of the group owns four rows of that stage.  A warp
+// issues the loads of its NEXT stage right after publishing the current one, so they have two
+// stage periods to land and no load is in flight across the fence of the arrive (a release with
+// loads outstanding stalls until they return -- measured: 3.6x slower).  Lane l holds A features
+// [4l, 4l+4) and B features [4l, 4l+4) of this CTA's 128-feature halves.
+// kAlias: diagonal block, the B tiles ARE the A tiles (nothing loaded or stored for B).
+// kXty:   also accumulate X^T y (and y^T y) for this CTA's A features.
+// The loop is issue-bound (the first version spent 349 instructions per 4 rows, 698 issue cycles
+// per stage against a 768-cycle MMA budget), hence the hoisted pointers, the bounds-check-free
+// fast path and the precomputed swizzled offsets.
+template <bool kAlias, bool kXty>
+__device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& ca) {
+  const int lane = ca.lane;
+  const int group = ca.warp & (kConvGroups - 1);
+  const int wi = ca.warp / kConvGroups;
+  const int64_t d = ca.d;
+  // shared-memory offset of this lane's 8-byte piece inside an operand tile, for row k = 4 wi + j:
+  // [mn block (64 features) 4 KB][k group (k >> 3) 1 KB][k & 7 -> 128 B][16-byte chunk ^ (k & 7)]
+  uint32_t soff[kRowsPerWarp];
+#pragma unroll
+  for (int j = 0; j < kRowsPerWarp; ++j) {
+    const int k = wi * kRowsPerWarp + j;
+    soff[j] = (lane >> 4) * 4096 + (k >> 3) * 1024 + (k & 7) * 128 +
+              ((((lane >> 1) & 7) ^ (k & 7)) << 4) + (lane & 1) * 8;
+  }
+  const uint32_t stage0 = ptx::smem_u32(sm.stage[0]);
+  // first row of this warp in its first stage, and the pointers that walk from there
+  int64_t row0 = ca.row_begin + static_cast<int64_t>(group) * kStageRows + wi * kRowsPerWarp;
+  const float* pa = ca.x + row0 * d + ca.feat_a + lane * 4;
+  const float* pb = ca.x + row0 * d + ca.feat_b + lane * 4;
+  const float* py = ca.y + row0;
+  const int64_t step = static_cast<int64_t>(kConvGroups) * kStageRows * d;
+  const bool do_yty = kXty && ca.want_yty && lane == 0;
+
+  float4 ra[kRowsPerWarp], rb[kRowsPerWarp];
+  float ry[kRowsPerWarp];
+  auto load_rows = [&]() {
+    if (row0 + kRowsPerWarp <= ca.n) {          // whole group of rows in range: no per-row checks
+#pragma unroll
+      for (int j = 0; j < kRowsPerWarp; ++j) {
+        ra[j] = ldg_f4(pa + j * d);
+        if (!kAlias) rb[j] = ldg_f4(pb + j * d);
+        if (kXty) ry[j] = __ldg(py + j);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRowsPerWarp; ++j) {
+        const bool ok = row0 + j < ca.n;
+        ra[j] = ok ? ldg_f4(pa + j * d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!kAlias) rb[j] = ok ? ldg_f4(pb + j * d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kXty) ry[j] = ok ? __ldg(py + j) : 0.f;
+      }
+    }
+    row0 += kConvGroups * kStageRows;
+    pa += step;
+    pb += step;
+    py += kConvGroups * kStageRows;
+  };
+
+  double xty_acc[4] = {0.0, 0.0, 0.0, 0.0};
+  double yty_acc = 0.0;
+  float xty_f[4] = {0.f, 0.f, 0.f, 0.f};
+  float yty_f = 0.f;
+  int since_flush = 0;
+
+  if (group < ca.n_iters) load_rows();
+  for (int it = group; it < ca.n_iters; it += kConvGroups) {
+    const int s = it % kStages;
+    ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
+    const uint32_t stage_addr = stage0 + s * kStageBytes;
+#pragma unroll
+    for (int j = 0; j < kRowsPerWarp; ++j) {
+      const uint32_t addr = stage_addr + soff[j];
+      uint32_t b1[2], b2[2];
+      split_bf16(ra[j], b1, b2);
+      sts_u2(addr, b1[0], b1[1]);
+      sts_u2(addr + kTileBytes, b2[0], b2[1]);
+      if (!kAlias) {
+        split_bf16(rb[j], b1, b2);
+        sts_u2(addr + 2 * kTileBytes, b1[0], b1[1]);
+        sts_u2(addr + 3 * kTileBytes, b2[0], b2[1]);
+      }
+      if (kXty) {
+        xty_f[0] = fmaf(ra[j].x, ry[j], xty_f[0]);
+        xty_f[1] = fmaf(ra[j].y, ry[j], xty_f[1]);
+        xty_f[2] = fmaf(ra[j].z, ry[j], xty_f[2]);
+        xty_f[3] = fmaf(ra[j].w, ry[j], xty_f[3]);
+        yty_f = fmaf(ry[j], ry[j], yty_f);
+      }
+    }
+    fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster_relaxed(&sm.full[s], 0);
+    if (it + kConvGroups < ca.n_iters) load_rows();
+    if (kXty && ++since_flush == kXtyFlushIters) {     // fp32 over 32 rows, then float64 (DADD is slow)
+      since_flush = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        xty_acc[c] += static_cast<double>(xty_f[c]);
+        xty_f[c] = 0.f;
+      }
+      yty_acc += static_cast<double>(yty_f);
+      yty_f = 0.f;
+    }
+  }
+  if (kXty) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) atomicAdd(&sm.xty[lane * 4 + c], xty_acc[c] + static_cast<double>(xty_f[c]));
+    if (do_yty) atomicAdd(&sm.yty, yty_acc + static_cast<double>(yty_f));
+  }
+}
 
 // grid = 2 * n_blocks * n_splits CTAs; pair p = blockIdx.x / 2: block = p % n_blocks,
 // split = p / n_blocks (pairs of one split walk the same rows at the same time -> L2 reuse).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n, int d,
-                 int n_blocks, int n_splits,
-                 float* __restrict__ partial,          // [pair][2][128][256] fp32
+                 int n_blocks, int n_splits, int ablate,
+                 float* __restrict__ partial,          // [pair][2][256 cols][128 rows] fp32
                  double* __restrict__ partial_xty,     // [split][d]
                  double* __restrict__ partial_yty) {   // [split]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -216,6 +348,7 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
     ij.y = i + rem;
   }
   const bool diag = ij.x == ij.y;
+  const bool alias_b = diag;                       // diagonal block: the B tiles ARE the A tiles
   const int feat_a = ij.x * kBlock + static_cast<int>(rank) * kHalf;
   const int feat_b = ij.y * kBlock + static_cast<int>(rank) * kHalf;
   // rows of this split, in whole stages
@@ -228,7 +361,7 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
-        ptx::mbar_init(&sm.full[s], 2 * kConvWarps);
+        ptx::mbar_init(&sm.full[s], 2 * kConvWarps / kConvGroups);
         ptx::mbar_init(&sm.empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
@@ -250,109 +383,22 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
 
   if (warp < kConvWarps) {
     // ---------------- converter warps: global fp32 -> registers -> bf16 b1/b2 tiles ----------------
-    // warp w handles rows w and w + 16 of every stage; lane l holds A features [4l, 4l+4) and
-    // B features [4l, 4l+4) of this CTA's 128-feature halves.
-    const bool do_xty = (y != nullptr) && diag;
-    const bool do_yty = do_xty && blk == 0 && rank == 0 && lane == 0;
-    const float* xa = x + feat_a + lane * 4;
-    const float* xb = x + feat_b + lane * 4;
-    // shared-memory offset of this lane's 8-byte piece inside an operand tile, for row k:
-    // [mn block (64 features) 4 KB][k group 1 KB][k & 7 -> 128 B][16-byte chunk ^ (k & 7)]
-    const uint32_t mn_off = (lane >> 4) * 4096;
-    const uint32_t chunk = (lane >> 1) & 7;
-    const uint32_t half8 = (lane & 1) * 8;
-    double xty_acc[4] = {0.0, 0.0, 0.0, 0.0};
-    double yty_acc = 0.0;
-    float xty_f[4] = {0.f, 0.f, 0.f, 0.f};
-    float yty_f = 0.f;
-
-    auto load_rows = [&](int it, RowRegs (&regs)[2]) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int64_t row = row_begin + static_cast<int64_t>(it) * kStageRows + warp + 16 * j;
-        if (it < n_iters && row < n) {
-          regs[j].a = ldg_f4(xa + row * d);
-          regs[j].b = ldg_f4(xb + row * d);
-          regs[j].y = do_xty ? __ldg(y + row) : 0.f;
-        } else {
-          regs[j].a = make_float4(0.f, 0.f, 0.f, 0.f);
-          regs[j].b = make_float4(0.f, 0.f, 0.f, 0.f);
-          regs[j].y = 0.f;
-        }
-      }
-      // L2 prefetch hint for a stage further ahead (one 128-byte line per 8 lanes)
-      const int pit = it + kPrefetchDist;
-      if ((lane & 7) == 0 && pit < n_iters) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int64_t row = row_begin + static_cast<int64_t>(pit) * kStageRows + warp + 16 * j;
-          if (row < n) {
-            prefetch_l2(xa + row * d);
-            prefetch_l2(xb + row * d);
-          }
-        }
-      }
-    };
-    auto convert_store = [&](int it, const RowRegs (&regs)[2]) {
-      const int s = it % kStages;
-      ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
-      const uint32_t stage_addr = ptx::smem_u32(sm.stage[s]);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = warp + 16 * j;
-        const uint32_t off = mn_off + (k >> 3) * 1024 + (k & 7) * 128 + ((chunk ^ (k & 7)) << 4) + half8;
-        uint32_t b1[2], b2[2];
-        split_bf16(regs[j].a, b1, b2);
-        sts_u2(stage_addr + off, b1[0], b1[1]);
-        sts_u2(stage_addr + kTileBytes + off, b2[0], b2[1]);
-        split_bf16(regs[j].b, b1, b2);
-        sts_u2(stage_addr + 2 * kTileBytes + off, b1[0], b1[1]);
-        sts_u2(stage_addr + 3 * kTileBytes + off, b2[0], b2[1]);
-        if (do_xty) {
-          xty_f[0] = fmaf(regs[j].a.x, regs[j].y, xty_f[0]);
-          xty_f[1] = fmaf(regs[j].a.y, regs[j].y, xty_f[1]);
-          xty_f[2] = fmaf(regs[j].a.z, regs[j].y, xty_f[2]);
-          xty_f[3] = fmaf(regs[j].a.w, regs[j].y, xty_f[3]);
-          yty_f = fmaf(regs[j].y, regs[j].y, yty_f);
-        }
-      }
-      fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&sm.full[s], 0);
-      if (do_xty && (it & 15) == 15) {          // fp32 partial sums over 32 rows, then float64
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          xty_acc[c] += static_cast<double>(xty_f[c]);
-          xty_f[c] = 0.f;
-        }
-        yty_acc += static_cast<double>(yty_f);
-        yty_f = 0.f;
-      }
-    };
-
-    RowRegs r0[2], r1[2];
-    load_rows(0, r0);
-    for (int it = 0; it < n_iters; it += 2) {
-      load_rows(it + 1, r1);
-      convert_store(it, r0);
-      if (it + 1 < n_iters) {
-        load_rows(it + 2, r0);
-        convert_store(it + 1, r1);
-      }
-    }
-    if (do_xty) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) atomicAdd(&sm.xty[lane * 4 + c], xty_acc[c] + static_cast<double>(xty_f[c]));
-      if (do_yty) atomicAdd(&sm.yty, yty_acc + static_cast<double>(yty_f));
-    }
+    ConvArgs ca;
+    ca.x = x; ca.y = y; ca.n = n; ca.d = d; ca.feat_a = feat_a; ca.feat_b = feat_b;
+    ca.row_begin = row_begin; ca.n_iters = n_iters; ca.warp = warp; ca.lane = lane;
+    ca.want_yty = blk == 0 && rank == 0;
+    if (!diag) converter_loop<false, false>(sm, ca);
+    else if (y == nullptr) converter_loop<true, false>(sm, ca);
+    else converter_loop<true, true>(sm, ca);
   } else if (warp < kMmaWarp) {
     // ---------------- epilogue warps: TMEM fp32 -> fp32 partial block (RMW through L2) ----------------
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access
     const int n_intervals = (n_iters + kFlushIters - 1) / kFlushIters;
-    float* my_partial = partial + ((static_cast<int64_t>(pair) * 2 + rank) * kHalf + q * 32 + lane) * kBlock;
+    // partial block layout [256 columns][128 rows]: for a fixed column the 32 lanes of a warp
+    // touch 128 contiguous bytes (one fully used line per access)
+    float* my_partial = partial + (static_cast<int64_t>(pair) * 2 + rank) * kHalf * kBlock + q * 32 + lane;
     if (n_intervals == 0) {
-      for (int c = 0; c < kBlock; c += 4)
-        *reinterpret_cast<float4*>(my_partial + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < kBlock; ++c) my_partial[c * kHalf] = 0.f;
     }
     for (int interval = 0; interval < n_intervals; ++interval) {
       const int buf = interval & 1;
@@ -363,29 +409,24 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
       for (int cc = 0; cc < kBlock / 32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_addr + cc * 32, v);
-        float4* dst = reinterpret_cast<float4*>(my_partial + cc * 32);
-        float4 old[8];
-        if (interval != 0) {
+        float* dst = my_partial + cc * 32 * kHalf;
+        float old[32];
+        if (interval != 0 && !(ablate & 32)) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) old[j] = dst[j];
+          for (int j = 0; j < 32; ++j) old[j] = dst[j * kHalf];
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) old[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 32; ++j) old[j] = 0.f;
         }
         ptx::tmem_wait_ld();
+        if (!(ablate & 32)) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = old[j];
-          o.x += __uint_as_float(v[4 * j + 0]);
-          o.y += __uint_as_float(v[4 * j + 1]);
-          o.z += __uint_as_float(v[4 * j + 2]);
-          o.w += __uint_as_float(v[4 * j + 3]);
-          dst[j] = o;
+          for (int j = 0; j < 32; ++j) dst[j * kHalf] = old[j] + __uint_as_float(v[j]);
         }
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&sm.acc_empty[buf], 0);
+      if (lane == 0) mbar_arrive_cluster_relaxed(&sm.acc_empty[buf], 0);   // TMEM reads done (wait::ld above)
     }
   } else if (rank == 0) {
     // ---------------- MMA issuer (leader CTA, one elected thread) ----------------
@@ -396,7 +437,7 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
         const int buf = interval & 1;
         const bool first = (it % kFlushIters) == 0;
         if (first) mbar_wait_cluster(&sm.acc_empty[buf], ((interval >> 1) & 1) ^ 1);
-        mbar_wait_cluster(&sm.full[s], (it / kStages) & 1);
+        ptx::mbar_wait(&sm.full[s], (it / kStages) & 1);   // the data is read by the async proxy, not by this thread
         ptx::tc_fence_after_sync();
         const uint32_t stage_addr = ptx::smem_u32(sm.stage[s]);
         const uint32_t d_tmem = tmem + buf * kBlock;
@@ -406,9 +447,11 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
           const uint32_t base = stage_addr + ks * 2048;
           const uint64_t a1 = ptx::make_smem_desc(base, 4096, 1024, ptx::kLayoutSwizzle128B);
           const uint64_t a2 = ptx::make_smem_desc(base + kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
-          const uint64_t b1 = ptx::make_smem_desc(base + 2 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
-          const uint64_t b2 = ptx::make_smem_desc(base + 3 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
+          const uint64_t b1 = alias_b ? a1 : ptx::make_smem_desc(base + 2 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
+          const uint64_t b2 = alias_b ? a2 : ptx::make_smem_desc(base + 3 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
+          if (ablate & 1) continue;
           mma_bf16_pair(d_tmem, a1, b1, kIdesc, (first && ks == 0) ? 0u : 1u);
+          if (ablate & 16) continue;
           mma_bf16_pair(d_tmem, a1, b2, kIdesc, 1u);
           mma_bf16_pair(d_tmem, a2, b1, kIdesc, 1u);
         }
@@ -446,7 +489,7 @@ gram_finalize_kernel(const float* __restrict__ partial, const double* __restrict
     double acc = 0.0;
     for (int s = 0; s < n_splits; ++s) {
       const int64_t pair = static_cast<int64_t>(s) * n_blocks + blk;
-      acc += static_cast<double>(partial[((pair * 2 + rr / kHalf) * kHalf + rr % kHalf) * kBlock + cc]);
+      acc += static_cast<double>(partial[((pair * 2 + rr / kHalf) * kBlock + cc) * kHalf + rr % kHalf]);
     }
     xtx[idx] = acc;
   }
@@ -524,7 +567,9 @@ int launch_gram_tc(const float* x, const float* y, int64_t n, int d, double* xtx
     attr_set = true;
   }
   const int grid = static_cast<int>(2 * pairs);
-  gram_pair_kernel<<<grid, kThreads, smem_bytes, stream>>>(x, y, n, d, g.n_blocks, g.n_splits, partial,
+  // developer ablation switches (timing experiments only; results are wrong when set)
+  static const int ablate = getenv("BB_GRAM_ABLATE") ? atoi(getenv("BB_GRAM_ABLATE")) : 0;
+  gram_pair_kernel<<<grid, kThreads, smem_bytes, stream>>>(x, y, n, d, g.n_blocks, g.n_splits, ablate, partial,
                                                            partial_xty, partial_yty);
   BB_CHECK_LAUNCH("gram_pair_kernel");
   const int64_t total = static_cast<int64_t>(d) * d;

@@ -154,7 +154,7 @@ int main(int argc, char** argv) {
   fails += run_case(1000, 256, 2, true, 0);
   fails += run_case(5000, 512, 2, true, 0);
   fails += run_case(70001, 256, 2, true, 0);
-  fails += run_case(300000, 1024, 2, true, 0);
+  fails += run_case(150000, 1024, 2, true, 0);
   printf(fails ? "FAILED %d cases\n" : "all cases ok\n", fails);
   if (!fails) run_case(1 << 20, 1024, 2, false, 10);
   return fails ? 1 : 0;
