@@ -253,6 +253,54 @@ BB_API int bb_release_staging(void) {
   return BB_OK;
 }
 
+BB_API int64_t bb_suffstats_regression_workspace(int64_t n, int32_t d) {
+  // generic path: float32 results (d*d + d + 1) + the largest split-K scratch of the three GEMMs
+  int64_t need = align_up((static_cast<int64_t>(d) * d + d + 1) * 4, 256) +
+                 std::max(gemm_workspace_bytes(d, d, n, 1),
+                          std::max(gemm_workspace_bytes(d, 1, n, 1), gemm_workspace_bytes(1, 1, n, 1))) + 1024;
+  if (d >= 256 && d % 256 == 0 && d <= 4096 && n > 0) need = std::max(need, gram_tc_workspace(n, d) + 256);
+  return need;
+}
+
+BB_API int bb_suffstats_regression(const float* X, const float* y, int64_t n, int32_t d, double* xtx,
+                            double* xty, double* yty, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((X == nullptr && n > 0) || xtx == nullptr || n < 0 || d < 1 || (xty == nullptr) != (yty == nullptr) ||
+      (n > 0 && (y == nullptr) != (xty == nullptr))) {
+    set_error("suffstats_regression: bad arguments (n=%lld d=%d; y, xty, yty go together)",
+              static_cast<long long>(n), d);
+    return BB_ERR_INVALID;
+  }
+  if (workspace == nullptr || workspace_bytes < bb_suffstats_regression_workspace(n, d)) {
+    set_error("suffstats_regression: workspace %lld < %lld bytes", static_cast<long long>(workspace_bytes),
+              static_cast<long long>(bb_suffstats_regression_workspace(n, d)));
+    return BB_ERR_WORKSPACE;
+  }
+  if (n == 0) {
+    BB_CUDA_OK(cudaMemsetAsync(xtx, 0, sizeof(double) * d * d, st));
+    if (xty) BB_CUDA_OK(cudaMemsetAsync(xty, 0, sizeof(double) * d, st));
+    if (yty) BB_CUDA_OK(cudaMemsetAsync(yty, 0, sizeof(double), st));
+    return BB_OK;
+  }
+  if (gram_tc_supported(n, d, X) && (y == nullptr || reinterpret_cast<uintptr_t>(y) % 4 == 0))
+    return launch_gram_tc(X, y, n, d, xtx, xty, yty, workspace, workspace_bytes, st);
+  // generic path: three split-K contractions over the data axis
+  char* ws = static_cast<char*>(workspace);
+  float* out32 = reinterpret_cast<float*>(ws);
+  ws += align_up((static_cast<int64_t>(d) * d + d + 1) * 4, 256);
+  BB_TRY(launch_gemm(X, X, out32, d, d, n, 1, 0, 1, d, 0, d, 1, ws, st));
+  BB_TRY(launch_f32_to_f64(out32, xtx, static_cast<int64_t>(d) * d, st));
+  if (y != nullptr) {
+    float* xty32 = out32 + static_cast<int64_t>(d) * d;
+    BB_TRY(launch_gemm(X, y, xty32, d, 1, n, 1, 0, 1, d, 0, 1, 1, ws, st));
+    BB_TRY(launch_f32_to_f64(xty32, xty, d, st));
+    BB_TRY(launch_gemm(y, y, xty32 + d, 1, 1, n, 1, 0, 1, 1, 0, 1, 1, ws, st));
+    BB_TRY(launch_f32_to_f64(xty32 + d, yty, 1, st));
+  }
+  return BB_OK;
+}
+
 BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xxT, double n,
                                 const double* E_Lambda, const double* E_Lambda_mu, double E_muLmu,
                                 double E_logdet, int32_t d, double* out, void* stream) {

@@ -442,10 +442,20 @@ int run_node(Exec& ex, int idx) {
           BB_TRY(ex.alloc_scratch(d * d * 8, &s2));
           BB_TRY(ex.alloc_scratch(ws_bytes, &ws));
         }
+        const bool gram_shape = d >= 256 && d % 256 == 0 && d <= 4096 && n > 0;   // tcgen05 CTA-pair kernel
+        if (gram_shape) {
+          ws_bytes = gram_tc_workspace(n, static_cast<int>(d));
+          BB_TRY(ex.alloc_scratch(d * d * 8, &s2));
+          BB_TRY(ex.alloc_scratch(ws_bytes, &ws));
+        }
         const int64_t gemm_bytes = gemm_workspace_bytes(d, d, n, 1);
         if (gemm_bytes > 0) BB_TRY(ex.alloc_scratch(gemm_bytes, &gws));
         if (!ex.dry()) {
-          if (tc_shape && suffstats_tc_supported(n, static_cast<int>(d), X.ptr)) {
+          if (gram_shape && gram_tc_supported(n, static_cast<int>(d), X.ptr)) {
+            BB_TRY(launch_gram_tc(X.ptr, nullptr, n, static_cast<int>(d), static_cast<double*>(s2), nullptr,
+                                  nullptr, ws, ws_bytes, ex.stream));
+            BB_TRY(launch_f64_to_f32(static_cast<const double*>(s2), out.ptr, d * d, ex.stream));
+          } else if (tc_shape && suffstats_tc_supported(n, static_cast<int>(d), X.ptr)) {
             BB_TRY(launch_suffstats_tc(X.ptr, n, static_cast<int>(d), nullptr, static_cast<double*>(s2),
                                        ws, ws_bytes, ex.stream));
             BB_TRY(launch_f64_to_f32(static_cast<const double*>(s2), out.ptr, d * d, ex.stream));

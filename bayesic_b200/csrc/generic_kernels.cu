@@ -351,6 +351,7 @@ struct GemmParams {
   int64_t sAb, sAm, sAk, sBb, sBk, sBn;
   int64_t k_per_split;
   int splits;
+  int m_on_x;             // M tiles on grid.x (else N tiles)
 };
 
 constexpr int kGemmTile = 64;
@@ -362,8 +363,9 @@ __global__ void __launch_bounds__(256) gemm_splitk_kernel(const GemmParams p) {
   __shared__ __align__(16) float Bs[kGemmK][kGemmTile + 4];
   const int t = threadIdx.x;
   const int tx = t % 16, ty = t / 16;
-  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * kGemmTile;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kGemmTile;
+  // the longer tile axis rides on grid.x (2^31 - 1 blocks), the other on grid.y (65535)
+  const int64_t m0 = static_cast<int64_t>(p.m_on_x ? blockIdx.x : blockIdx.y) * kGemmTile;
+  const int64_t n0 = static_cast<int64_t>(p.m_on_x ? blockIdx.y : blockIdx.x) * kGemmTile;
   const int64_t bz = blockIdx.z;
   const int64_t split = bz / p.batch, batch = bz % p.batch;
   const int64_t k_begin = split * p.k_per_split;
@@ -470,12 +472,14 @@ int launch_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, 
   p.C = (p.splits > 1) ? static_cast<float*>(workspace) : C;
   const int64_t gx = (N + kGemmTile - 1) / kGemmTile, gy = (M + kGemmTile - 1) / kGemmTile;
   const int64_t gz = batch * p.splits;
-  if (gy > 65535 || gz > 65535) {
-    set_error("gemm: grid too large (M tiles %lld, batch*splits %lld)", static_cast<long long>(gy),
-              static_cast<long long>(gz));
+  p.m_on_x = gy > gx ? 1 : 0;
+  if (std::min(gx, gy) > 65535 || std::max(gx, gy) > 2147483647LL || gz > 65535) {
+    set_error("gemm: grid too large (M tiles %lld, N tiles %lld, batch*splits %lld)",
+              static_cast<long long>(gy), static_cast<long long>(gx), static_cast<long long>(gz));
     return BB_ERR_UNSUPPORTED;
   }
-  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy), static_cast<unsigned>(gz));
+  dim3 grid(static_cast<unsigned>(p.m_on_x ? gy : gx), static_cast<unsigned>(p.m_on_x ? gx : gy),
+            static_cast<unsigned>(gz));
   const bool a_k = (sAk == 1), b_n = (sBn == 1);
   if (a_k && b_n) gemm_splitk_kernel<true, true><<<grid, 256, 0, stream>>>(p);
   else if (a_k) gemm_splitk_kernel<true, false><<<grid, 256, 0, stream>>>(p);

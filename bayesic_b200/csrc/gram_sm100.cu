@@ -88,16 +88,8 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (release at cluster scope) on the barrier at the same shared-memory offset in CTA `rank`
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
-      ::"r"(ptx::smem_u32(bar)), "r"(rank)
-      : "memory");
-}
-// Same without a release fence: ordering is provided by the caller (every lane has executed
+// Arrive on the barrier at the same shared-memory offset in CTA `rank`, without a release fence:
+// ordering is provided by the caller (every lane has executed
 // fence.proxy.async -- SASS: MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC -- so its shared-memory stores
 // have completed, then __syncwarp).  A release.cluster arrive compiles to MEMBAR.ALL.GPU, which
 // on the per-stage path costs more than the whole MMA budget.
@@ -160,9 +152,6 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");

@@ -28,6 +28,12 @@ int64_t suffstats_tc_workspace(int64_t n);
 int launch_suffstats_tc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,
                         int64_t workspace_bytes, cudaStream_t stream);
 
+// gram_sm100.cu: X^T X (+ X^T y, y^T y) for d % 256 == 0 on tcgen05 CTA pairs (BF16x3)
+bool gram_tc_supported(int64_t n, int d, const void* x);
+int64_t gram_tc_workspace(int64_t n, int d);
+int launch_gram_tc(const float* x, const float* y, int64_t n, int d, double* xtx, double* xty,
+                   double* yty, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+
 // mixture_kernels.cu
 int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_resp, float* lse,
                            double* sum_lse, cudaStream_t stream);

@@ -76,22 +76,31 @@ class GmmStep(object):
 
 class LinRegSviStep(object):
     """cfg4: conjugate natural-gradient SVI for Bayesian linear regression (noise precision tau).
-    The minibatch statistics {X^T X, X^T y, y^T y} come from ONE compiled plan; the natural
-    parameter blend and the expected log-likelihood are float64 parameter-space arithmetic."""
+    The minibatch statistics {X^T X, X^T y, y^T y} -- the plans of ``dot(X.T, X)``,
+    ``dot(X.T, y)``, ``dot(y, y)`` -- come from ONE fused pass over X
+    (``stats.regression_suffstats``; tcgen05 CTA pairs when D % 256 == 0), or with
+    ``fused=False`` from one compiled multi-output plan; the natural-parameter blend and the
+    expected log-likelihood are float64 parameter-space arithmetic."""
 
-    def __init__(self):
+    def __init__(self, fused=True):
+        self.fused = fused
         X, y = A.var('X', 2), A.var('y', 1)
         self.stats_fn = compile_many([A.dot(X.T, X), A.dot(X.T, y), A.dot(y, y)])
 
     def __call__(self, X, y, eta1, eta2, tau, n_total, rho, eta1_prior, eta2_prior):
         import torch
-        xtx, xty, yty = self.stats_fn(X=X, y=y)
+        if self.fused:
+            xtx, xty, yty = stats.regression_suffstats(X, y)
+            yty = yty.reshape(())
+        else:
+            xtx, xty, yty = self.stats_fn(X=X, y=y)
         b = X.shape[0]
         xtx, xty, yty = xtx.double(), xty.double(), yty.double()
         scale = float(n_total) / float(b)
         new1 = (1 - rho) * eta1 + rho * (eta1_prior + scale * tau * xty)
         new2 = (1 - rho) * eta2 + rho * (eta2_prior - 0.5 * scale * tau * xtx)
-        cov = torch.linalg.inv(-2.0 * new2)
+        chol = torch.linalg.cholesky(-2.0 * new2)                 # precision of q(w) is SPD
+        cov = torch.cholesky_inverse(chol)
         mean = cov @ new1
         e_wwT = cov + torch.outer(mean, mean)
         ell = 0.5 * b * (math.log(tau) - _LOG_2PI) - 0.5 * tau * (yty - 2 * mean @ xty + (e_wwT * xtx).sum())

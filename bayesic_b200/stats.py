@@ -18,7 +18,7 @@ import numpy as np
 from .backend import library as L
 
 __all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'log_responsibilities',
-           'weighted_suffstats', 'launch_count']
+           'weighted_suffstats', 'regression_suffstats', 'launch_count']
 
 _scratch = {}
 
@@ -173,3 +173,29 @@ def weighted_suffstats(X, R):
                                           rx.data_ptr(), rxx.data_ptr(), ws.data_ptr(), ws.numel(),
                                           _stream(dev)), 'bb_suffstats_weighted')
     return nk, rx, rxx
+
+
+def regression_suffstats(X, y=None):
+    """``(X^T X [d, d], X^T y [d], y^T y [1])`` float64 CUDA tensors in one pass over ``X[n, d]``
+    (``y`` omitted: just the Gram matrix).  ``d % 256 == 0`` runs the tcgen05 CTA-pair kernel."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    n, d = X.shape
+    dev = X.device
+    if y is not None:
+        y = _as_device_f32(y, 1, 'y')
+        if y.shape[0] != n:
+            raise ValueError("X and y disagree on the data axis (%d vs %d)" % (n, y.shape[0]))
+    with torch.cuda.device(dev):
+        xtx = torch.empty((d, d), dtype=torch.float64, device=dev)
+        xty = torch.empty(d, dtype=torch.float64, device=dev) if y is not None else None
+        yty = torch.empty(1, dtype=torch.float64, device=dev) if y is not None else None
+        need = lib.bb_suffstats_regression_workspace(n, d)
+        ws = _workspace(need, dev)
+        L.check(lib.bb_suffstats_regression(X.data_ptr(), y.data_ptr() if y is not None else None, n, d,
+                                            xtx.data_ptr(), xty.data_ptr() if y is not None else None,
+                                            yty.data_ptr() if y is not None else None,
+                                            ws.data_ptr(), ws.numel(), _stream(dev)),
+                'bb_suffstats_regression')
+    return xtx, xty, yty

@@ -182,6 +182,19 @@ BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xx
                                 double E_muLmu, double E_logdet, int32_t d,
                                 double* out, void* stream);
 
+/* Minibatch statistics of conjugate Bayesian linear regression / factor analysis
+ * (natural-gradient SVI, README.md:69-80), i.e. the plans
+ *   _tensordot(_dimshuffle(X,1,0), X, [1],[0]), _tensordot(_dimshuffle(X,1,0), y, [1],[0]),
+ *   _tensordot(y, y, [0],[0])                                  (algebra.py:527-551, 1347-1351)
+ * in ONE pass over X:  xtx[d,e] = sum_n X[n,d] X[n,e];  xty[d] = sum_n X[n,d] y[n];
+ * yty = sum_n y[n]^2   (float64 out, device).  y, xty, yty may all be NULL (Gram matrix only).
+ * d % 256 == 0 runs the tcgen05 CTA-pair kernel (error-compensated BF16); other d use the
+ * generic contraction kernels. */
+BB_API int64_t bb_suffstats_regression_workspace(int64_t n, int32_t d);
+BB_API int bb_suffstats_regression(const float* X, const float* y, int64_t n, int32_t d,
+                            double* xtx, double* xty, double* yty,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- mixture responsibilities ------------------------------------------------
  * log r[n,k] = logits[n,k] - logsumexp_k logits[n,:]  (max-subtracted; the
  * reference can only spell the unstabilised form, algebra.py:1435-1448).

@@ -108,6 +108,14 @@ def gmm_vmp_step(X, log_pi, m, beta, W, nu):
     return {'logits': logits, 'log_resp': log_r, 'nk': nk, 'rx': rx, 'rxx': rxx, 'sum_lse': lse.sum()}
 
 
+def regression_suffstats(X, y):
+    """float64 X^T X, X^T y, y^T y: the declared value of the plans of dot(X.T, X), dot(X.T, y),
+    dot(y, y) (bayesic/algebra.py:1151-1158 -> 527-551)."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    return X.T @ X, X.T @ y, float(y @ y)
+
+
 def linreg_svi_step(X, y, eta1, eta2, tau, n_total, rho, eta1_prior, eta2_prior):
     """Conjugate natural-gradient SVI step for Bayesian linear regression with known noise
     precision tau (Hoffman et al. 2013, README.md:69-80): minibatch statistics

@@ -1,0 +1,75 @@
+"""Developer timing of the BASELINE cfg3/cfg4/cfg5 passes (not a pytest file)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bayesic_b200.passes as P  # noqa: E402
+import bayesic_b200.stats as S  # noqa: E402
+
+
+def timeit(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def cfg4():
+    n, d = 1 << 20, 1024
+    X = torch.randn(n, d, device='cuda')
+    y = X @ (torch.randn(d, device='cuda') / d ** 0.5) + 0.1 * torch.randn(n, device='cuda')
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device='cuda')
+    eta1, eta2 = t(np.zeros(d)), t(-0.5 * np.eye(d))
+    for fused in (True, False):
+        step = P.LinRegSviStep(fused=fused)
+        ms = timeit(lambda: step(X, y, eta1, eta2, 100.0, 10 * n, 0.3, eta1, eta2))
+        print('cfg4 LinRegSviStep fused=%s: %.2f ms/step  %.1f M rows/s' % (fused, ms, n / ms / 1e3), flush=True)
+    ms = timeit(lambda: S.regression_suffstats(X, y), reps=10)
+    print('cfg4 regression_suffstats alone: %.3f ms  %.1f M rows/s' % (ms, n / ms / 1e3), flush=True)
+
+
+def cfg5():
+    n, d, s = 1 << 22, 512, 64
+    X = torch.randn(n, d, device='cuda')
+    y = (torch.rand(n, device='cuda') < 0.5).float()
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device='cuda')
+    mu, ls, eps = t(np.zeros(d)), t(np.full(d, -2.0)), t(np.random.RandomState(0).randn(s, d))
+    step = P.LogisticReparamGrad()
+    ms = timeit(lambda: step(X, y, mu, ls, eps), reps=2)
+    print('cfg5 LogisticReparamGrad: %.2f ms/step  %.1f M rows/s (launches %d)'
+          % (ms, n / ms / 1e3, step.fn.plan.last_launches), flush=True)
+
+
+def cfg3():
+    n, d, k = 1 << 21, 64, 256
+    X = torch.randn(n, d, device='cuda')
+    Ak = torch.eye(d, device='cuda').repeat(k, 1, 1).contiguous()
+    bk = torch.randn(k, d, device='cuda')
+    ck = torch.randn(k, device='cuda')
+    step = P.GmmStep()
+    ms = timeit(lambda: step(X, Ak, bk, ck), reps=2)
+    print('cfg3 GmmStep (N = %d): %.2f ms/step  %.2f M rows/s' % (n, ms, n / ms / 1e3), flush=True)
+    ms = timeit(lambda: step.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck), reps=2)
+    print('  logits plan: %.2f ms (launches %d)' % (ms, step.logits_fn.plan.last_launches), flush=True)
+    R = torch.softmax(torch.randn(n, k, device='cuda'), 1)
+    ms = timeit(lambda: S.weighted_suffstats(X, R), reps=2)
+    print('  weighted stats: %.2f ms' % ms, flush=True)
+    ms = timeit(lambda: S.log_responsibilities(R), reps=5)
+    print('  log-softmax: %.2f ms' % ms, flush=True)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['cfg4', 'cfg5', 'cfg3']
+    for name in which:
+        globals()[name]()

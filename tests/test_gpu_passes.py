@@ -99,3 +99,31 @@ def test_cfg5_logistic_reparam_gradient():
     _close(got['grad_mu'], want['grad_mu'], scale_atol=2e-5)
     _close(got['grad_log_sigma'], want['grad_log_sigma'], scale_atol=2e-5)
     assert abs(float(got['elbo']) - want['elbo']) <= 1e-4 * abs(want['elbo'])
+
+
+def test_cfg4_linreg_svi_step_on_the_cta_pair_kernel():
+    """Same step at D = 256 (the tcgen05 CTA-pair Gram kernel), fused pass and compiled-plan route
+    (dot(X.T, X) lowers to the SYRK node, which dispatches to the same kernel)."""
+    import torch
+    rng = np.random.RandomState(4)
+    b, d = 6000, 256
+    X = rng.randn(b, d).astype(np.float32)
+    w_true = rng.randn(d) / np.sqrt(d)
+    y = (X @ w_true + 0.1 * rng.randn(b)).astype(np.float32)
+    tau, n_total, rho = 100.0, 10 * b, 0.3
+    eta1_prior, eta2_prior = np.zeros(d), -0.5 * np.eye(d)
+    eta1, eta2 = rng.randn(d) * 0.1, -0.5 * _spd(rng, d) * 10
+    want = O.linreg_svi_step(X, y, eta1, eta2, tau, n_total, rho, eta1_prior, eta2_prior)
+    dev = torch.device('cuda')
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    for fused in (True, False):
+        got = P.LinRegSviStep(fused=fused)(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), t(eta1),
+                                          t(eta2), tau, n_total, rho, t(eta1_prior), t(eta2_prior))
+        _close(got['xtx'], want['xtx'], scale_atol=3e-5)
+        _close(got['xty'], want['xty'], scale_atol=1e-5)
+        _close(got['yty'], want['yty'])
+        _close(got['eta1'], want['eta1'], scale_atol=1e-5)
+        _close(got['eta2'], want['eta2'], scale_atol=3e-5)
+        # ell = const - tau/2 (yty - 2 m.xty + <E[ww^T], xtx>) cancels ~100-fold here (tau = 100,
+        # residual variance 0.01), so 1e-4 is taken relative to the terms that cancel
+        assert abs(float(got['ell']) - want['ell']) <= 1e-4 * 0.5 * tau * want['yty']

@@ -180,3 +180,98 @@ def test_weighted_suffstats_sum_over_components_is_the_plain_statistic():
                                atol=1e-6 * float(s2.abs().max()))
     np.testing.assert_allclose(rx.sum(0).cpu().numpy(), Xw.sum(0).cpu().numpy(), rtol=1e-5)
     assert abs(float(nk.sum()) - float(rowsum.sum())) <= 1e-6 * n
+
+
+# ---- regression / Gram statistics (cfg4): X^T X, X^T y, y^T y in one pass -------------------
+
+def _close_gram(got, want, tol=3e-5):
+    """Elementwise |err| <= rtol |want| + tol sqrt(S_aa S_bb): the Cauchy-Schwarz scale of entry
+    (a, b) is the natural unit for an off-diagonal sum that cancels (float32 BLAS has the same
+    shape of error).  Measured on B200: <= 1.2e-5 (BF16x3 products, fp32 TMEM accumulate drained
+    every 2048 rows)."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
+    assert got.shape == want.shape
+    assert np.all(np.abs(got - want) <= RTOL * np.abs(want) + tol * scale + 1e-30)
+
+
+@pytest.mark.parametrize('n,d', [(1, 256), (31, 256), (32, 256), (33, 256), (1000, 256), (4097, 512),
+                                 (20000, 1024), (70001, 256), (0, 256), (500, 96), (300, 130), (64, 768)])
+def test_regression_suffstats(n, d):
+    import torch
+    rng = np.random.RandomState(n * 7 + d)
+    X = (rng.randn(n, d) * 1.3 + 0.2).astype(np.float32)
+    y = (X[:, : min(d, 8)].sum(1) + rng.randn(n)).astype(np.float32)
+    before = S.launch_count()
+    xtx, xty, yty = S.regression_suffstats(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda())
+    w_xtx, w_xty, w_yty = O.regression_suffstats(X, y)
+    if n > 0:
+        assert S.launch_count() > before
+        _close_gram(xtx.cpu().numpy(), w_xtx)
+    else:
+        assert float(xtx.abs().max()) == 0.0
+    _close(xty.cpu().numpy(), w_xty, scale_atol=2e-6)
+    assert abs(float(yty) - w_yty) <= 1e-6 * max(1.0, w_yty)
+    # Gram matrix only (no y) is the same matrix, and exactly symmetric
+    only, none1, none2 = S.regression_suffstats(torch.from_numpy(X).cuda())
+    assert none1 is None and none2 is None
+    assert torch.equal(only, xtx)
+    assert torch.equal(xtx, xtx.T)
+
+
+def test_regression_suffstats_exact_on_integers():
+    """Small integers are exact in bf16, so every product and every fp32 partial sum is exact:
+    any layout / quadrant / pipeline mistake in the CTA-pair kernel shows up as a whole-number error."""
+    import torch
+    n, d = 777, 512
+    i, j = np.meshgrid(np.arange(n), np.arange(d), indexing='ij')
+    X = (((i * 3 + j * 5) % 11) - 5).astype(np.float32)
+    y = ((np.arange(n) % 5) - 2).astype(np.float32)
+    xtx, xty, yty = S.regression_suffstats(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda())
+    w_xtx, w_xty, w_yty = O.regression_suffstats(X, y)
+    assert np.array_equal(xtx.cpu().numpy(), w_xtx)
+    assert np.array_equal(xty.cpu().numpy(), w_xty)
+    assert float(yty) == w_yty
+
+
+def test_regression_suffstats_is_additive_over_row_shards():
+    """The statistic is a sum over the data axis (the axis sharded across GPUs): two shards add up."""
+    import torch
+    rng = np.random.RandomState(5)
+    n, d = 30000, 256
+    X = torch.from_numpy(rng.randn(n, d).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.randn(n).astype(np.float32)).cuda()
+    full = S.regression_suffstats(X, y)
+    a = S.regression_suffstats(X[:11111], y[:11111])
+    b = S.regression_suffstats(X[11111:], y[11111:])
+    for f, pa, pb in zip(full, a, b):
+        s = (pa + pb).cpu().numpy()
+        np.testing.assert_allclose(s, f.cpu().numpy(), rtol=1e-4, atol=3e-5 * float(full[0].diagonal().max()))
+
+
+def test_full_size_cfg4_properties():
+    """BASELINE cfg4 (minibatch 1 Mi, D = 1024) is too large for the CPU oracle, so check
+    size-independent properties against float64 device arithmetic on the same data: exact
+    symmetry, the trace (= sum of squares), and the action on a random vector."""
+    import torch
+    n, d = 1 << 20, 1024
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    X = torch.randn(n, d, device='cuda', generator=g)
+    w = torch.randn(d, device='cuda', generator=g) / d ** 0.5
+    y = X @ w + 0.1 * torch.randn(n, device='cuda', generator=g)
+    xtx, xty, yty = S.regression_suffstats(X, y)
+    assert torch.equal(xtx, xtx.T)
+    sq = torch.zeros((), dtype=torch.float64, device='cuda')
+    v = torch.randn(d, dtype=torch.float64, device='cuda', generator=g)
+    xtxv = torch.zeros(d, dtype=torch.float64, device='cuda')
+    ref_xty = torch.zeros(d, dtype=torch.float64, device='cuda')
+    for lo in range(0, n, 1 << 17):                     # float64 in slabs of 128 Ki rows
+        Xd = X[lo:lo + (1 << 17)].double()
+        sq += (Xd * Xd).sum()
+        xtxv += Xd.T @ (Xd @ v)
+        ref_xty += Xd.T @ y[lo:lo + (1 << 17)].double()
+    assert abs(float(xtx.diagonal().sum() - sq)) <= 2e-5 * float(sq)
+    err = (xtx @ v - xtxv).abs().max() / xtxv.abs().max()
+    assert float(err) <= 2e-5
+    assert float((xty - ref_xty).abs().max() / ref_xty.abs().max()) <= 1e-5
+    assert abs(float(yty) - float((y.double() ** 2).sum())) <= 1e-6 * float(yty)
