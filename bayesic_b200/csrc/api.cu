@@ -301,6 +301,63 @@ BB_API int bb_suffstats_regression(const float* X, const float* y, int64_t n, in
   return BB_OK;
 }
 
+BB_API int64_t bb_rowproj_workspace(int64_t n, int32_t d, int32_t q) { return rowproj_tc_workspace(n, d, q) + 256; }
+
+BB_API int bb_rowproj(const float* X, const float* W, int64_t n, int32_t d, int32_t q, float* Z, void* workspace,
+               int64_t workspace_bytes, void* stream) {
+  if (n < 0 || !W || !Z || (n > 0 && !X)) { set_error("rowproj: bad arguments"); return BB_ERR_INVALID; }
+  if (n == 0) return BB_OK;
+  return launch_rowproj_tc(X, W, nullptr, n, d, q, Z, nullptr, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+BB_API int64_t bb_colproj_workspace(int64_t n, int32_t d, int32_t q) { return colproj_tc_workspace(n, d, q) + 256; }
+
+BB_API int bb_colproj(const float* X, const float* R, int64_t n, int32_t d, int32_t q, double* G, void* workspace,
+               int64_t workspace_bytes, void* stream) {
+  if (n < 0 || !G || (n > 0 && (!X || !R))) { set_error("colproj: bad arguments"); return BB_ERR_INVALID; }
+  if (n == 0) {
+    BB_CUDA_OK(cudaMemsetAsync(G, 0, sizeof(double) * d * q, static_cast<cudaStream_t>(stream)));
+    return BB_OK;
+  }
+  return launch_colproj_tc(X, R, n, d, q, G, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int64_t bb_logistic_reparam_workspace(int64_t n, int32_t d, int32_t s) {
+  return align_up(n * static_cast<int64_t>(s) * 4, 256) +
+         std::max(rowproj_tc_workspace(n, d, s), colproj_tc_workspace(n, d, s)) + 512;
+}
+
+BB_API int bb_logistic_reparam_pass(const float* X, const float* y, const float* W, int64_t n, int32_t d, int32_t s,
+                             double* loglik, double* G, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n < 0 || !W || !loglik || !G || (n > 0 && (!X || !y))) { set_error("logistic_reparam_pass: bad arguments"); return BB_ERR_INVALID; }
+  if (n == 0) {
+    BB_CUDA_OK(cudaMemsetAsync(loglik, 0, sizeof(double) * s, st));
+    BB_CUDA_OK(cudaMemsetAsync(G, 0, sizeof(double) * d * s, st));
+    return BB_OK;
+  }
+  if (!rowproj_tc_supported(n, d, s, X) || !colproj_tc_supported(n, d, s, X, X)) {
+    set_error("logistic_reparam_pass: unsupported shape n=%lld d=%d s=%d (needs d %% 128 == 0, s %% 64 == 0, "
+              "s d <= 32768, (d/128)(s/64) <= 4); use the compiled plan instead",
+              static_cast<long long>(n), d, s);
+    return BB_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < bb_logistic_reparam_workspace(n, d, s)) {
+    set_error("logistic_reparam_pass: workspace %lld < %lld bytes", static_cast<long long>(workspace_bytes),
+              static_cast<long long>(bb_logistic_reparam_workspace(n, d, s)));
+    return BB_ERR_WORKSPACE;
+  }
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  float* resid = reinterpret_cast<float*>(ws);
+  ws += align_up(n * static_cast<int64_t>(s) * 4, 256);
+  const int64_t rest = workspace_bytes - (ws - static_cast<char*>(workspace));
+  BB_TRY(launch_rowproj_tc(X, W, y, n, d, s, resid, loglik, ws, rest, st));
+  BB_TRY(launch_colproj_tc(X, resid, n, d, s, G, ws, rest, st));
+  return BB_OK;
+}
+
 BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xxT, double n,
                                 const double* E_Lambda, const double* E_Lambda_mu, double E_muLmu,
                                 double E_logdet, int32_t d, double* out, void* stream) {

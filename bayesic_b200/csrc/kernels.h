@@ -34,6 +34,19 @@ int64_t gram_tc_workspace(int64_t n, int d);
 int launch_gram_tc(const float* x, const float* y, int64_t n, int d, double* xtx, double* xty,
                    double* yty, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 
+// rowproj_sm100.cu: Z = X W^T per data row on tcgen05 (W resident in shared memory), optional
+// fused logistic epilogue (out = y - sigmoid(z), colsum[q] = sum_n y z - log(1 + exp z))
+bool rowproj_tc_supported(int64_t n, int d, int q, const void* x);
+int64_t rowproj_tc_workspace(int64_t n, int d, int q);
+int launch_rowproj_tc(const float* x, const float* w, const float* y, int64_t n, int d, int q, float* out,
+                      double* colsum, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+
+// colproj_sm100.cu: G = X^T R over the data axis on tcgen05 (float64 out)
+bool colproj_tc_supported(int64_t n, int d, int q, const void* x, const void* r);
+int64_t colproj_tc_workspace(int64_t n, int d, int q);
+int launch_colproj_tc(const float* x, const float* r, int64_t n, int d, int q, double* out, void* workspace,
+                      int64_t workspace_bytes, cudaStream_t stream);
+
 // mixture_kernels.cu
 int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_resp, float* lse,
                            double* sum_lse, cudaStream_t stream);

@@ -121,11 +121,15 @@ class LogisticReparamGrad(object):
         G = A.dot(X.T, resid)                                         # [D, S]
         self.fn = compile_many([loglik, G])
 
-    def __call__(self, X, y, mu, log_sigma, eps):
+    def __call__(self, X, y, mu, log_sigma, eps, fused=True):
         import torch
         sigma = torch.exp(log_sigma)
         Wm = (mu[None, :] + sigma[None, :] * eps).to(torch.float32)
-        loglik, G = self.fn(X=X, y=y, Wm=Wm)
+        if fused and stats.logistic_reparam_supported(X.shape[1], Wm.shape[0]):
+            # the same two plans on the tcgen05 projection kernels, elementwise chain fused
+            loglik, G = stats.logistic_reparam_stats(X, y, Wm)
+        else:
+            loglik, G = self.fn(X=X, y=y, Wm=Wm)
         G = G.double()
         kl = 0.5 * torch.sum(sigma ** 2 + mu ** 2 - 1.0 - 2.0 * log_sigma)
         grad_mu = G.mean(dim=1) - mu

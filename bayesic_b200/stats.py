@@ -18,7 +18,8 @@ import numpy as np
 from .backend import library as L
 
 __all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'log_responsibilities',
-           'weighted_suffstats', 'regression_suffstats', 'launch_count']
+           'weighted_suffstats', 'regression_suffstats', 'row_projection', 'column_projection',
+           'logistic_reparam_stats', 'logistic_reparam_supported', 'launch_count']
 
 _scratch = {}
 
@@ -199,3 +200,69 @@ def regression_suffstats(X, y=None):
                                             ws.data_ptr(), ws.numel(), _stream(dev)),
                 'bb_suffstats_regression')
     return xtx, xty, yty
+
+
+def row_projection(X, W):
+    """``Z[n, q] = X @ W.T`` (float32 CUDA tensor) on the tcgen05 row-projection kernel."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    W = _as_device_f32(W, 2, 'W')
+    n, d = X.shape
+    q = W.shape[0]
+    if W.shape[1] != d:
+        raise ValueError("X and W disagree on the feature axis (%d vs %d)" % (d, W.shape[1]))
+    dev = X.device
+    with torch.cuda.device(dev):
+        Z = torch.empty((n, q), dtype=torch.float32, device=dev)
+        ws = _workspace(lib.bb_rowproj_workspace(n, d, q), dev)
+        L.check(lib.bb_rowproj(X.data_ptr(), W.data_ptr(), n, d, q, Z.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _stream(dev)), 'bb_rowproj')
+    return Z
+
+
+def column_projection(X, R):
+    """``G[d, q] = X.T @ R`` over the data axis (float64 CUDA tensor) on the tcgen05 kernel."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    R = _as_device_f32(R, 2, 'R')
+    n, d = X.shape
+    q = R.shape[1]
+    if R.shape[0] != n:
+        raise ValueError("X and R disagree on the data axis (%d vs %d)" % (n, R.shape[0]))
+    dev = X.device
+    with torch.cuda.device(dev):
+        G = torch.empty((d, q), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.bb_colproj_workspace(n, d, q), dev)
+        L.check(lib.bb_colproj(X.data_ptr(), R.data_ptr(), n, d, q, G.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _stream(dev)), 'bb_colproj')
+    return G
+
+
+def logistic_reparam_supported(d, s):
+    """Shapes the fused logistic pass serves (others go through the compiled plan)."""
+    return (d % 128 == 0 and s % 64 == 0 and s * d <= 32768 and (d // 128) * (s // 64) <= 4)
+
+
+def logistic_reparam_stats(X, y, W):
+    """``(loglik[s], G[d, s])`` float64 CUDA tensors for S parameter draws ``W[s, d]``:
+    ``loglik[s] = sum_n y z - log(1 + exp z)``, ``G = X.T @ (y - sigmoid(Z))``, ``Z = X @ W.T``."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    y = _as_device_f32(y, 1, 'y')
+    W = _as_device_f32(W, 2, 'W')
+    n, d = X.shape
+    s = W.shape[0]
+    if W.shape[1] != d or y.shape[0] != n:
+        raise ValueError("logistic_reparam_stats: inconsistent shapes")
+    dev = X.device
+    with torch.cuda.device(dev):
+        loglik = torch.empty(s, dtype=torch.float64, device=dev)
+        G = torch.empty((d, s), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.bb_logistic_reparam_workspace(n, d, s), dev)
+        L.check(lib.bb_logistic_reparam_pass(X.data_ptr(), y.data_ptr(), W.data_ptr(), n, d, s,
+                                             loglik.data_ptr(), G.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             _stream(dev)), 'bb_logistic_reparam_pass')
+    return loglik, G

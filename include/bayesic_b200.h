@@ -195,6 +195,32 @@ BB_API int bb_suffstats_regression(const float* X, const float* y, int64_t n, in
                             double* xtx, double* xty, double* yty,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- tensor-core contractions of the plan executor ---------------------------
+ * Z[n,q] = sum_d X[n,d] W[q,d]: the plan _tensordot(X, _dimshuffle(W,1,0), [1],[0])
+ * ("dot(X, W.T)", algebra.py:1151-1158 -> 1347-1351) on tcgen05, W resident in shared memory.
+ * Needs d % 64 == 0, q % 16 == 0, q <= 256, q * d <= 32768 (BB_ERR_UNSUPPORTED otherwise). */
+BB_API int64_t bb_rowproj_workspace(int64_t n, int32_t d, int32_t q);
+BB_API int bb_rowproj(const float* X, const float* W, int64_t n, int32_t d, int32_t q, float* Z,
+               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* G[d,q] = sum_n X[n,d] R[n,q] (float64 out): the plan _tensordot(_dimshuffle(X,1,0), R, [1],[0])
+ * ("dot(X.T, R)") on tcgen05.  Needs d % 128 == 0, q % 64 == 0, (d/128)(q/64) <= 4. */
+BB_API int64_t bb_colproj_workspace(int64_t n, int32_t d, int32_t q);
+BB_API int bb_colproj(const float* X, const float* R, int64_t n, int32_t d, int32_t q, double* G,
+               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Reparameterised-gradient pass of Bayesian logistic regression (README.md:47-51) for S parameter
+ * draws W[s,d] at once:  Z = X W^T;  loglik[s] = sum_n (y_n z_ns - log(1 + exp z_ns));
+ * G[d,s] = sum_n X[n,d] (y_n - (1 + exp(-z_ns))^-1)     (float64 out, device).
+ * These are the plans of  sum(ycol * Z - log(1 + exp(Z)), axis=0)  and
+ * dot(X.T, ycol - (1 + exp(-1 * Z)) ** -1)  (algebra.py:1435-1448 vocabulary) with the
+ * elementwise chain fused into the TMEM epilogue of the first contraction; the workspace holds
+ * the n x s residual.  Same shape limits as bb_rowproj (q = s) and bb_colproj. */
+BB_API int64_t bb_logistic_reparam_workspace(int64_t n, int32_t d, int32_t s);
+BB_API int bb_logistic_reparam_pass(const float* X, const float* y, const float* W, int64_t n, int32_t d,
+                             int32_t s, double* loglik, double* G,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- mixture responsibilities ------------------------------------------------
  * log r[n,k] = logits[n,k] - logsumexp_k logits[n,:]  (max-subtracted; the
  * reference can only spell the unstabilised form, algebra.py:1435-1448).

@@ -127,3 +127,26 @@ def test_cfg4_linreg_svi_step_on_the_cta_pair_kernel():
         # ell = const - tau/2 (yty - 2 m.xty + <E[ww^T], xtx>) cancels ~100-fold here (tau = 100,
         # residual variance 0.01), so 1e-4 is taken relative to the terms that cancel
         assert abs(float(got['ell']) - want['ell']) <= 1e-4 * 0.5 * tau * want['yty']
+
+
+def test_cfg5_logistic_reparam_gradient_on_the_projection_kernels():
+    """Same pass at D = 512, S = 64 (BASELINE cfg5's feature/sample extents) through the fused
+    tcgen05 projection kernels, and through the compiled plans (fused=False) as a cross-check."""
+    import torch
+    rng = np.random.RandomState(6)
+    b, d, s = 6000, 512, 64
+    X = rng.randn(b, d).astype(np.float32)
+    w_true = rng.randn(d) / np.sqrt(d)
+    y = (rng.rand(b) < 1 / (1 + np.exp(-X @ w_true))).astype(np.float32)
+    mu, log_sigma = rng.randn(d) * 0.05, np.log(0.05 + 0.02 * rng.rand(d))
+    eps = rng.randn(s, d)
+    want = O.logistic_reparam_gradient(X, y, mu, log_sigma, eps)
+    dev = torch.device('cuda')
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    step = P.LogisticReparamGrad()
+    for fused in (True, False):
+        got = step(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), t(mu), t(log_sigma), t(eps), fused=fused)
+        _close(got['G'], want['G'], scale_atol=2e-5)
+        _close(got['grad_mu'], want['grad_mu'], scale_atol=2e-5)
+        _close(got['grad_log_sigma'], want['grad_log_sigma'], scale_atol=2e-5)
+        assert abs(float(got['elbo']) - want['elbo']) <= 1e-4 * abs(want['elbo'])

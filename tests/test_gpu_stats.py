@@ -275,3 +275,58 @@ def test_full_size_cfg4_properties():
     assert float(err) <= 2e-5
     assert float((xty - ref_xty).abs().max() / ref_xty.abs().max()) <= 1e-5
     assert abs(float(yty) - float((y.double() ** 2).sum())) <= 1e-6 * float(yty)
+
+
+# ---- tcgen05 projections (cfg5): Z = X W^T per row, G = X^T R over the data axis ---------------
+
+@pytest.mark.parametrize('n,d,q', [(1, 64, 16), (127, 64, 64), (128, 128, 64), (129, 512, 64), (1000, 256, 128),
+                                   (5000, 128, 48), (20000, 512, 64), (257, 64, 256)])
+def test_row_projection(n, d, q):
+    """dot(X, W.T) on the tcgen05 row-projection kernel vs float64; error measured against
+    |x_n| |w_q| (the Cauchy-Schwarz scale of entry (n, q))."""
+    import torch
+    rng = np.random.RandomState(n + d + q)
+    X = (rng.randn(n, d) * 1.3 + 0.2).astype(np.float32)
+    W = (rng.randn(q, d) / np.sqrt(d)).astype(np.float32)
+    before = S.launch_count()
+    Z = S.row_projection(torch.from_numpy(X).cuda(), torch.from_numpy(W).cuda()).cpu().numpy().astype(np.float64)
+    assert S.launch_count() > before
+    want = X.astype(np.float64) @ W.astype(np.float64).T
+    scale = np.linalg.norm(X.astype(np.float64), axis=1)[:, None] * np.linalg.norm(W.astype(np.float64), axis=1)[None, :]
+    assert np.all(np.abs(Z - want) <= RTOL * np.abs(want) + 1e-5 * scale)
+
+
+@pytest.mark.parametrize('n,d,q', [(1, 128, 64), (15, 128, 64), (16, 128, 64), (17, 256, 64), (1000, 512, 64),
+                                   (5000, 256, 128), (333, 128, 256), (4097, 384, 64), (70001, 128, 64)])
+def test_column_projection(n, d, q):
+    """dot(X.T, R) over the data axis on the tcgen05 column-projection kernel vs float64."""
+    import torch
+    rng = np.random.RandomState(n + 3 * d + q)
+    X = (rng.randn(n, d) * 1.3 + 0.2).astype(np.float32)
+    R = rng.randn(n, q).astype(np.float32)
+    G = S.column_projection(torch.from_numpy(X).cuda(), torch.from_numpy(R).cuda()).cpu().numpy()
+    want = X.astype(np.float64).T @ R.astype(np.float64)
+    scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(R.astype(np.float64), axis=0)[None, :]
+    assert np.all(np.abs(G - want) <= RTOL * np.abs(want) + 3e-5 * scale)
+
+
+def test_projections_exact_on_integers():
+    import torch
+    rng = np.random.RandomState(11)
+    X = rng.randint(-4, 5, size=(1000, 512)).astype(np.float32)
+    W = rng.randint(-3, 4, size=(64, 512)).astype(np.float32)
+    R = rng.randint(-3, 4, size=(1000, 64)).astype(np.float32)
+    Z = S.row_projection(torch.from_numpy(X).cuda(), torch.from_numpy(W).cuda()).cpu().numpy()
+    G = S.column_projection(torch.from_numpy(X).cuda(), torch.from_numpy(R).cuda()).cpu().numpy()
+    assert np.array_equal(Z.astype(np.float64), X.astype(np.float64) @ W.astype(np.float64).T)
+    assert np.array_equal(G, X.astype(np.float64).T @ R.astype(np.float64))
+
+
+def test_projection_unsupported_shapes_fail_loudly():
+    import torch
+    from bayesic_b200.backend.library import BackendError
+    X = torch.zeros(64, 96, device='cuda')
+    with pytest.raises(BackendError):
+        S.row_projection(X, torch.zeros(64, 96, device='cuda'))        # d % 64 != 0
+    with pytest.raises(BackendError):
+        S.column_projection(X, torch.zeros(64, 64, device='cuda'))     # d % 128 != 0
