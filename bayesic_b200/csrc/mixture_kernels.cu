@@ -331,6 +331,8 @@ int launch_weighted_stats(const float* x, const float* r, int64_t n, int d, int 
 int64_t weighted_stats_auto_workspace(int64_t n, int d, int k) {
   int64_t need = 256;
   if (d >= 4 && d <= 64 && d % 4 == 0 && k % 4 == 0 && n > 0) need = std::max(need, weighted_tc_workspace(n, k));
+  if (d >= 8 && d <= 64 && d % 8 == 0 && k >= 4 && k <= 256 && k % 4 == 0 && n > 0)
+    need = std::max(need, weighted_pairs_workspace(n, d, k));
   return need;
 }
 
@@ -338,6 +340,11 @@ int launch_weighted_stats_auto(const float* x, const float* r, int64_t n, int d,
                                double* sum_rx, double* sum_rxx, void* workspace,
                                int64_t workspace_bytes, cudaStream_t stream) {
   static const bool force_simt = getenv("BB_WEIGHTED_SIMT") != nullptr;
+  static const bool no_pairs = getenv("BB_WEIGHTED_NO_PAIRS") != nullptr;
+  // R^T . (X (x) X) grouping on BF16 tcgen05 (weighted_pairs_sm100.cu): tensor-pipe bound
+  if (!force_simt && !no_pairs && n >= 1024 && weighted_pairs_supported(n, d, k, x, r) && workspace != nullptr &&
+      workspace_bytes >= weighted_pairs_workspace(n, d, k))
+    return launch_weighted_pairs(x, r, n, d, k, nk, sum_rx, sum_rxx, workspace, workspace_bytes, stream);
   // the tensor-core kernel pays off once there are enough rows to amortise its per-CTA setup
   if (!force_simt && n >= 1024 && weighted_tc_supported(n, d, k, x, r) && workspace != nullptr &&
       workspace_bytes >= weighted_tc_workspace(n, k))

@@ -1,0 +1,500 @@
+// Responsibility-weighted sufficient statistics as ONE tensor-core contraction over the data axis
+// (D % 8 == 0, D <= 64, K % 4 == 0, K <= 256):
+//     Nk[k] = sum_n r_nk      Srx[k,d] = sum_n r_nk x_nd      Srxx[k,d,e] = sum_n r_nk x_nd x_ne
+//
+// What it replaces: the reference's plan for sum_n R[n,k] X[n,d] X[n,e],
+//     _tensordot(_mul(_dimshuffle(R,1,'x',0), _dimshuffle(X,'x',1,0)), X, [2],[0])
+// (bayesic/algebra.py:741-765 -> 1297-1306 -> 1347-1351), which groups the
+// factors as (R (x) X) . X and materialises a K x D x N tensor.  The same einsum
+// (algebra.py:314-346 declares only the index pattern) regrouped as  R^T . (X (x) X):
+//     Srxx[k, (d,e)] = sum_n R[n,k] Phi[n,(d,e)],      Phi[n,(d,e)] = x_nd x_ne
+// is a plain GEMM with M = K, contraction over n, whose B operand Phi does not depend on k -- so
+// it is generated once per row instead of once per (row, component) -- and whose symmetric half
+// (d <= e by 8 x 8 feature blocks: 36 blocks of 64 columns at D = 64) is all that is needed.
+// weighted_sm100.cu (the (r x) . x grouping, TF32, N = 64 tiles) is ALU-bound on forming the A
+// operand; this grouping is tensor-pipe bound:
+//   * CTA = (column tile of up to 4 pair blocks = 256 columns, contiguous range of rows);
+//     M = K components in up to two 128-lane blocks -> 2 x 256 TMEM columns (all of TMEM);
+//   * error-compensated BF16 (r = r1 + r2, phi = p1 + p2; r1 p1 + r1 p2 + r2 p1; see
+//     gram_sm100.cu), both operands MN-major SWIZZLE_128B as they are produced: 16 converter warps
+//     load R with coalesced 128-bit loads, form Phi in fp32 from the row of X, split, store;
+//   * the linear statistics ride along as one more 64-column block (Phi = x_d), Nk in the
+//     converter warps of the first column tile;
+//   * FP32 TMEM accumulation drained every 2048 rows into the CTA's fp32 partial block
+//     (coalesced read-modify-write); finalize adds the row ranges in float64 and unpacks the
+//     symmetric blocks.
+// Algorithmic traffic: 4 (K + D) bytes/row; flops issued: 3 x 2 K x 64 x (#blocks) per row.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace bb {
+
+namespace {
+
+constexpr int kStageRows = 16;
+constexpr int kStages = 6;
+constexpr int kMaxK = 256;                       // components (MMA M, two 128-lane blocks)
+constexpr int kTileCols = 256;                   // pair-feature columns per CTA (MMA N)
+constexpr int kRPart = kStageRows * kMaxK * 2;   // 8 KB: R tile, one bf16 part
+constexpr int kPPart = kStageRows * kTileCols * 2;   // 8 KB: Phi tile, one bf16 part
+constexpr int kStageBytes = 2 * kRPart + 2 * kPPart; // 32 KB
+constexpr int kFlushIters = 128;                 // 2048 rows per TMEM accumulation chain
+constexpr int kConvWarps = 16;
+constexpr int kConvGroups = 2;
+constexpr int kEpiWarps = 4;
+constexpr int kMmaWarp = kConvWarps + kEpiWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
+constexpr int kTmemCols = 512;
+
+struct __align__(1024) SmemLayout {
+  uint8_t stage[kStages][kStageBytes];
+  double nk[kMaxK];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_full;
+  uint64_t acc_empty;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], uint32_t (&b2)[2]) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y);
+  __nv_bfloat162 p1 = __floats2bfloat162_rn(x.z, x.w);
+  b1[0] = *reinterpret_cast<uint32_t*>(&p0);
+  b1[1] = *reinterpret_cast<uint32_t*>(&p1);
+  const float rx = x.x - __uint_as_float(b1[0] << 16);
+  const float ry = x.y - __uint_as_float(b1[0] & 0xFFFF0000u);
+  const float rz = x.z - __uint_as_float(b1[1] << 16);
+  const float rw = x.w - __uint_as_float(b1[1] & 0xFFFF0000u);
+  __nv_bfloat162 q0 = __floats2bfloat162_rn(rx, ry);
+  __nv_bfloat162 q1 = __floats2bfloat162_rn(rz, rw);
+  b2[0] = *reinterpret_cast<uint32_t*>(&q0);
+  b2[1] = *reinterpret_cast<uint32_t*>(&q1);
+}
+
+// Column blocks of 64: block b < n_pair is the feature-group pair (ga, gb), ga <= gb, enumerated
+// row-major over the upper triangle; column (i, j) -> x[8 ga + i] * x[8 gb + j].  Block n_pair is
+// the linear block: column c -> x[c] (c < d).
+struct Geometry {
+  int d, k, n_groups, n_pair, n_blocks, n_tiles;
+  int base, rem;      // tile t holds base + (t < rem) blocks, starting at block t * base + min(t, rem)
+};
+
+__host__ __device__ __forceinline__ int tile_first_block(const Geometry& g, int t) {
+  return t * g.base + (t < g.rem ? t : g.rem);
+}
+__host__ __device__ __forceinline__ int tile_block_count(const Geometry& g, int t) { return g.base + (t < g.rem ? 1 : 0); }
+
+__device__ __forceinline__ void pair_of(int b, int n_groups, int* ga, int* gb) {
+  int a = 0, rem = b;
+  while (rem >= n_groups - a) {
+    rem -= n_groups - a;
+    ++a;
+  }
+  *ga = a;
+  *gb = a + rem;
+}
+
+// grid = n_tiles * n_splits: CTA -> (tile = blockIdx / n_splits, row range = blockIdx % n_splits).
+// The blocks are spread evenly over the tiles (3 or 4 each at D = 64): every CTA converts the same
+// R rows whatever its column count, so equal row ranges keep the CTAs in step.
+__global__ void __launch_bounds__(kThreads, 1)
+weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t n, Geometry g,
+                      int n_splits,
+                      float* __restrict__ partial,        // [cta][2 m-blocks][256 cols][128 lanes]
+                      double* __restrict__ partial_nk) {  // [split of tile 0][k]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / n_splits;
+  const int split = blockIdx.x % n_splits;
+  const int block0 = tile_first_block(g, tile);
+  const int tile_blocks = tile_block_count(g, tile);
+  const int m_blocks = (g.k + 127) / 128;
+  const int64_t total_iters = (n + kStageRows - 1) / kStageRows;
+  const int64_t it_begin = total_iters * split / n_splits;
+  const int64_t it_end = total_iters * (split + 1) / n_splits;
+  const int n_iters = static_cast<int>(it_end - it_begin);
+  const int64_t row_begin = it_begin * kStageRows;
+
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        ptx::mbar_init(&sm.full[s], kConvWarps / kConvGroups);
+        ptx::mbar_init(&sm.empty[s], 1);
+      }
+      ptx::mbar_init(&sm.acc_full, 1);
+      ptx::mbar_init(&sm.acc_empty, kEpiWarps);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
+  }
+  for (int i = threadIdx.x; i < kMaxK; i += kThreads) sm.nk[i] = 0.0;
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < kConvWarps) {
+    // ---------------- converter warps ----------------
+    // group = warp & 1 takes every 2nd stage; warp wi of the group owns rows 2 wi, 2 wi + 1.
+    // R: lane l holds components [4 l + 128 h, +4), h = 0, 1, of both rows.
+    // Phi: item (row j, block bl, lane) -> 4 columns: 16 lanes per 64-column block row
+    //      (i = (lane & 15) >> 1, j0 = 4 (lane & 1)); lanes >= 16 take the odd block of a pair of blocks.
+    const int group = warp & (kConvGroups - 1);
+    const int wi = warp / kConvGroups;
+    const bool do_nk = tile == 0;
+    uint32_t off[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kk = 2 * wi + j;      // row within the stage = MMA k index
+      off[j] = (kk >> 3) * 1024 + (kk & 7) * 128 + ((((lane & 15) >> 1) ^ (kk & 7)) << 4) + (lane & 1) * 8;
+    }
+    // per-lane Phi sources for the (up to) two blocks this lane serves: blocks 2 t2 + (lane >> 4).
+    // Every load is unconditional (clamped addresses, masked values) so the compiler can batch
+    // them: the branchy first version serialised on divergent-branch reconvergence.
+    int src_a[2], src_b[2];        // element offsets into the row of X
+    float lin[2], mask_b[2];       // lin = 1: linear block (left factor is 1); mask_b = 0: padding columns
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+      const int bl = 2 * t2 + (lane >> 4);
+      const int b = block0 + bl;
+      const int i = (lane & 15) >> 1, j0 = (lane & 1) * 4;
+      src_a[t2] = 0;
+      src_b[t2] = 0;
+      lin[t2] = 0.f;
+      mask_b[t2] = 0.f;
+      if (bl < tile_blocks) {
+        if (b < g.n_pair) {
+          int ga, gb;
+          pair_of(b, g.n_groups, &ga, &gb);
+          src_a[t2] = 8 * ga + i;
+          src_b[t2] = 8 * gb + j0;
+          mask_b[t2] = 1.f;
+        } else {
+          lin[t2] = 1.f;
+          if (8 * i + j0 < g.d) {        // linear block: column c = 8 i + j0 .. +3
+            src_b[t2] = 8 * i + j0;
+            mask_b[t2] = 1.f;
+          }
+        }
+      }
+    }
+    const uint32_t stage0 = ptx::smem_u32(sm.stage[0]);
+    int64_t row0 = row_begin + static_cast<int64_t>(group) * kStageRows + 2 * wi;
+    const int kc0 = min(4 * lane, g.k - 4), kc1 = min(4 * lane + 128, g.k - 4);
+    const bool k_ok0 = 4 * lane < g.k, k_ok1 = 4 * lane + 128 < g.k;
+    float4 rr[2][2];
+    float rmask[2][2];
+    float xa[2][2];          // [row][block slot]: the left factor of the pair product (1 for the linear block)
+    float4 xb[2][2];         // the four right factors
+    float nk_f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    double nk_d[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    int since_flush = 0;
+    // everything a stage needs is loaded one iteration ahead (nothing is fetched between the
+    // barrier wait and the stores: dependent loads there serialise on the L2 latency)
+    auto load_all = [&]() {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool row_ok = row0 + j < n;
+        const int64_t rowc = row_ok ? row0 + j : n - 1;            // clamped: always a valid address
+        const float* rp = r + rowc * g.k;
+        const float* xr = x + rowc * g.d;
+        rr[j][0] = ldg_f4(rp + kc0);
+        rr[j][1] = ldg_f4(rp + kc1);
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+          xa[j][t2] = __ldg(xr + src_a[t2]);
+          xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xr + src_b[t2]));
+        }
+        // rows past the end and components past k contribute nothing: their weights are zeroed
+        // when the tile is formed (not here: touching the values would wait for the loads)
+        rmask[j][0] = (row_ok && k_ok0) ? 1.f : 0.f;
+        rmask[j][1] = (row_ok && k_ok1) ? 1.f : 0.f;
+      }
+    };
+    if (group < n_iters) load_all();
+    for (int it = group; it < n_iters; it += kConvGroups) {
+      const int s = it % kStages;
+      ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
+      const uint32_t stage_addr = stage0 + s * kStageBytes;
+      // ---- R tile: [m block (64 components) 2 KB][k group][8][128 B] ----
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t b1[2], b2[2];
+          const float m = rmask[j][h];
+          rr[j][h] = make_float4(rr[j][h].x * m, rr[j][h].y * m, rr[j][h].z * m, rr[j][h].w * m);
+          split_bf16(rr[j][h], b1, b2);
+          const uint32_t addr = stage_addr + (2 * h + (lane >> 4)) * 2048 + off[j];
+          sts_u2(addr, b1[0], b1[1]);
+          sts_u2(addr + kRPart, b2[0], b2[1]);
+          if (do_nk) {
+            nk_f[h][0] += rr[j][h].x;
+            nk_f[h][1] += rr[j][h].y;
+            nk_f[h][2] += rr[j][h].z;
+            nk_f[h][3] += rr[j][h].w;
+          }
+        }
+      // ---- Phi tile: [block (64 columns) 2 KB][k group][8][128 B] ----
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+          const float a = (lin[t2] != 0.f ? 1.f : xa[j][t2]) * mask_b[t2];
+          const float4 p = make_float4(a * xb[j][t2].x, a * xb[j][t2].y, a * xb[j][t2].z, a * xb[j][t2].w);
+          uint32_t b1[2], b2[2];
+          split_bf16(p, b1, b2);
+          const uint32_t addr = stage_addr + 2 * kRPart + (2 * t2 + (lane >> 4)) * 2048 + off[j];
+          sts_u2(addr, b1[0], b1[1]);
+          sts_u2(addr + kPPart, b2[0], b2[1]);
+        }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.full[s]);
+      row0 += kConvGroups * kStageRows;
+      if (it + kConvGroups < n_iters) load_all();
+      if (do_nk && ++since_flush == 16) {
+        since_flush = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            nk_d[h][c] += static_cast<double>(nk_f[h][c]);
+            nk_f[h][c] = 0.f;
+          }
+      }
+    }
+    if (do_nk) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int kc = 4 * lane + 128 * h + c;
+          if (kc < g.k) atomicAdd(&sm.nk[kc], nk_d[h][c] + static_cast<double>(nk_f[h][c]));
+        }
+    }
+  } else if (warp < kMmaWarp) {
+    // ---------------- epilogue warps: TMEM fp32 -> fp32 partial (coalesced RMW), single-buffered ----------------
+    const int qd = warp & 3;
+    const int n_intervals = (n_iters + kFlushIters - 1) / kFlushIters;
+    const int cols = tile_blocks * 64;
+    float* my_partial = partial + static_cast<int64_t>(blockIdx.x) * 2 * kTileCols * 128 + qd * 32 + lane;
+    if (n_intervals == 0) {
+      for (int c = 0; c < 2 * kTileCols; ++c) my_partial[c * 128] = 0.f;
+    }
+    for (int interval = 0; interval < n_intervals; ++interval) {
+      ptx::mbar_wait(&sm.acc_full, interval & 1);
+      ptx::tc_fence_after_sync();
+      for (int mb = 0; mb < m_blocks; ++mb) {
+        const uint32_t t_addr = tmem + (static_cast<uint32_t>(qd * 32) << 16) + mb * kTileCols;
+#pragma unroll 1
+        for (int cc = 0; cc < cols / 32; ++cc) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + cc * 32, v);
+          float* dst = my_partial + (mb * kTileCols + cc * 32) * 128;
+          float old[32];
+          if (interval != 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = dst[j * 128];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = 0.f;
+          }
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[j * 128] = old[j] + __uint_as_float(v[j]);
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.acc_empty);
+    }
+  } else {
+    // ---------------- MMA issuer ----------------
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc(128, static_cast<uint32_t>(tile_blocks * 64), /*bf16*/ 1, 1, 1);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % kStages;
+        const int interval = it / kFlushIters;
+        const bool first = (it % kFlushIters) == 0;
+        if (first && interval > 0) ptx::mbar_wait(&sm.acc_empty, (interval - 1) & 1);
+        ptx::mbar_wait(&sm.full[s], (it / kStages) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t base = ptx::smem_u32(sm.stage[s]);
+        const uint64_t p1 = ptx::make_smem_desc(base + 2 * kRPart, 2048, 1024, ptx::kLayoutSwizzle128B);
+        const uint64_t p2 = ptx::make_smem_desc(base + 2 * kRPart + kPPart, 2048, 1024, ptx::kLayoutSwizzle128B);
+        for (int mb = 0; mb < m_blocks; ++mb) {
+          const uint64_t r1 = ptx::make_smem_desc(base + mb * 4096, 2048, 1024, ptx::kLayoutSwizzle128B);
+          const uint64_t r2 = ptx::make_smem_desc(base + kRPart + mb * 4096, 2048, 1024, ptx::kLayoutSwizzle128B);
+          const uint32_t d_tmem = tmem + mb * kTileCols;
+          mma_bf16_ss(d_tmem, r1, p1, idesc, first ? 0u : 1u);
+          mma_bf16_ss(d_tmem, r1, p2, idesc, 1u);
+          mma_bf16_ss(d_tmem, r2, p1, idesc, 1u);
+        }
+        ptx::mma_commit(&sm.empty[s]);
+        if ((it % kFlushIters) == kFlushIters - 1 || it == n_iters - 1) ptx::mma_commit(&sm.acc_full);
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (tile == 0 && partial_nk != nullptr)
+    for (int i = threadIdx.x; i < g.k; i += kThreads) partial_nk[static_cast<int64_t>(split) * g.k + i] = sm.nk[i];
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
+}
+
+// One thread per (k, d, e): add the row ranges of the CTA tile that owns the pair block (min, max),
+// in float64; blocks (ga, ga) hold both (i, j) and (j, i) -- use i <= j so the result is symmetric.
+__global__ void __launch_bounds__(256)
+weighted_pairs_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ partial_nk, Geometry g,
+                               int n_splits, double* __restrict__ nk,
+                               double* __restrict__ srx, double* __restrict__ srxx) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto column_sum = [&](int k, int block, int col) -> double {
+    // tile that owns `block`: the first `rem` tiles hold base + 1 blocks
+    const int big = g.rem * (g.base + 1);
+    const int tile = block < big ? block / (g.base + 1) : g.rem + (block - big) / g.base;
+    const int within = block - tile_first_block(g, tile);
+    const int64_t off = (static_cast<int64_t>(k / 128) * kTileCols + within * 64 + col) * 128 + k % 128;
+    double acc = 0.0;
+    for (int s = 0; s < n_splits; ++s)
+      acc += static_cast<double>(partial[static_cast<int64_t>(tile * n_splits + s) * 2 * kTileCols * 128 + off]);
+    return acc;
+  };
+  const int64_t n_xx = static_cast<int64_t>(g.k) * g.d * g.d;
+  if (idx < n_xx) {
+    const int k = static_cast<int>(idx / (g.d * g.d));
+    const int de = static_cast<int>(idx % (g.d * g.d));
+    const int dd = de / g.d, ee = de % g.d;
+    const int lo = dd < ee ? dd : ee, hi = dd < ee ? ee : dd;
+    const int ga = lo / 8, gb = hi / 8;
+    const int block = ga * g.n_groups - ga * (ga - 1) / 2 + (gb - ga);
+    srxx[idx] = column_sum(k, block, (lo % 8) * 8 + hi % 8);
+  } else if (idx < n_xx + static_cast<int64_t>(g.k) * g.d) {
+    const int64_t j = idx - n_xx;
+    if (srx != nullptr) srx[j] = column_sum(static_cast<int>(j / g.d), g.n_pair, static_cast<int>(j % g.d));
+  } else if (idx < n_xx + static_cast<int64_t>(g.k) * g.d + g.k) {
+    const int k = static_cast<int>(idx - n_xx - static_cast<int64_t>(g.k) * g.d);
+    if (nk != nullptr) {
+      double acc = 0.0;
+      for (int s = 0; s < n_splits; ++s) acc += partial_nk[static_cast<int64_t>(s) * g.k + k];
+      nk[k] = acc;
+    }
+  }
+}
+
+struct PairsPlan {
+  Geometry g;
+  int n_splits, grid;
+};
+
+PairsPlan plan_pairs(int64_t n, int d, int k) {
+  PairsPlan p;
+  p.g.d = d;
+  p.g.k = k;
+  p.g.n_groups = d / 8;
+  p.g.n_pair = p.g.n_groups * (p.g.n_groups + 1) / 2;
+  p.g.n_blocks = p.g.n_pair + 1;
+  p.g.n_tiles = (p.g.n_blocks + 3) / 4;
+  p.g.base = p.g.n_blocks / p.g.n_tiles;
+  p.g.rem = p.g.n_blocks % p.g.n_tiles;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int64_t iters = (n + kStageRows - 1) / kStageRows;
+  p.n_splits = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sms / p.g.n_tiles, iters)));
+  p.grid = p.g.n_tiles * p.n_splits;
+  return p;
+}
+
+}  // namespace
+
+bool weighted_pairs_supported(int64_t n, int d, int k, const void* x, const void* r) {
+  return n > 0 && d >= 8 && d <= 64 && d % 8 == 0 && k >= 4 && k <= kMaxK && k % 4 == 0 &&
+         reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(r) % 16 == 0;
+}
+
+int64_t weighted_pairs_workspace(int64_t n, int d, int k) {
+  const PairsPlan p = plan_pairs(n, d, k);
+  return static_cast<int64_t>(p.grid) * 2 * kTileCols * 128 * static_cast<int64_t>(sizeof(float)) +
+         static_cast<int64_t>(p.n_splits) * k * static_cast<int64_t>(sizeof(double)) + 1024;
+}
+
+int launch_weighted_pairs(const float* x, const float* r, int64_t n, int d, int k, double* nk, double* sum_rx,
+                          double* sum_rxx, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (!weighted_pairs_supported(n, d, k, x, r)) {
+    set_error("weighted_pairs: unsupported shape n=%lld d=%d k=%d", static_cast<long long>(n), d, k);
+    return BB_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < weighted_pairs_workspace(n, d, k)) {
+    set_error("weighted_pairs: workspace %lld < %lld bytes", static_cast<long long>(workspace_bytes),
+              static_cast<long long>(weighted_pairs_workspace(n, d, k)));
+    return BB_ERR_WORKSPACE;
+  }
+  const PairsPlan p = plan_pairs(n, d, k);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  float* partial = reinterpret_cast<float*>(ws);
+  ws += static_cast<int64_t>(p.grid) * 2 * kTileCols * 128 * sizeof(float);
+  double* partial_nk = reinterpret_cast<double*>(ws);
+  const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
+  static bool attr_set = false;
+  if (!attr_set) {
+    BB_CUDA_OK(cudaFuncSetAttribute(weighted_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  weighted_pairs_kernel<<<p.grid, kThreads, smem_bytes, stream>>>(x, r, n, p.g, p.n_splits, partial, partial_nk);
+  BB_CHECK_LAUNCH("weighted_pairs_kernel");
+  const int64_t total = static_cast<int64_t>(k) * d * d + static_cast<int64_t>(k) * d + k;
+  weighted_pairs_finalize_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
+      partial, partial_nk, p.g, p.n_splits, nk, sum_rx, sum_rxx);
+  BB_CHECK_LAUNCH("weighted_pairs_finalize_kernel");
+  return BB_OK;
+}
+
+}  // namespace bb
