@@ -47,6 +47,13 @@ int64_t colproj_tc_workspace(int64_t n, int d, int q);
 int launch_colproj_tc(const float* x, const float* r, int64_t n, int d, int q, double* out, void* workspace,
                       int64_t workspace_bytes, cudaStream_t stream);
 
+// mixture_logits_sm100.cu: logit[n,k] = c_k - 1/2 |U_k x_n - t_k|^2 (+ row log-sum-exp) on tcgen05
+bool mixture_logits_supported(int64_t n, int d, int k, const void* x);
+int64_t mixture_logits_workspace(int64_t n, int d, int k);
+int launch_mixture_logits(const float* x, const float* u, const float* t, const float* c, int64_t n, int d, int k,
+                          float* logits, float* lse, double* sum_lse, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t stream);
+
 // mixture_kernels.cu
 int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_resp, float* lse,
                            double* sum_lse, cudaStream_t stream);

@@ -1,0 +1,428 @@
+// Gaussian-mixture expected log-densities (the "logits" of the responsibility softmax) on tcgen05
+// (D in {16, 32, 48, 64}, K % 4 == 0):
+//     logit[n, k] = c_k - 1/2 || U_k x_n - t_k ||^2          (+ lse[n] = logsumexp_k logit[n, :])
+// i.e.  c'_k + x.b_k - 1/2 x^T A_k x  with A_k = U_k^T U_k (Cholesky), t_k = U_k m_k -- the
+// expression  dot(X, bk.T) + (-0.5) * einsum(X_nd Ak_kde X_ne) + ck  that a user of the reference
+// writes for the VMP local step (README.md:30-37).  The reference plans the quadratic form as
+//     _tensordot(_tensordot(X, Ak', ...), X^T, batch axes ...)          
+// whose batched evaluation is broken (bayesic/algebra.py:1370-1373, :1380) and which would
+// materialise an N x K x D intermediate; in the whitened form the same value is ONE projection
+// Z = X [U_1; ...; U_K]^T (2 K D^2 flop/row) whose N x (K D) result is consumed on chip.
+//
+// Design (tensor-pipe bound: 2 K D^2 flop/row against 4 D bytes in, 4 K bytes out per row):
+//   * persistent CTAs over 128-row tiles; the X tile is split once into error-compensated BF16
+//     (x = b1 + b2, see gram_sm100.cu), K-major SWIZZLE_128B, and stays in shared memory while
+//     the CTA sweeps all component groups (4 components = 256 columns per MMA group);
+//   * the stacked factors are split and laid out in the UMMA shared-memory layout ONCE by a
+//     pre-kernel, so a group's 64 KB operand tile arrives with two plain bulk copies
+//     (cp.async.bulk, no tensor map) through a 2-stage mbarrier ring; it is L2-resident (4 MB);
+//   * per group 3 x D/16 kind::f16 MMAs (b1 w1 + b1 w2 + b2 w1), M = 128, N = 256, FP32 in TMEM,
+//     double-buffered (2 x 256 columns) so the epilogue of group g overlaps the MMAs of g + 1;
+//   * eight epilogue warps (lane = data row, two warps per TMEM lane quadrant, 2 components each)
+//     read Z from TMEM, subtract t (fetched coalesced, broadcast by shuffle), square-accumulate,
+//     write the logit and keep an online log-sum-exp per row.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace bb {
+
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kGroupComps = 4;                     // components per MMA group
+constexpr int kGroupCols = 256;                    // = 4 x 64 padded factor rows
+constexpr int kAPart = kTileRows * 128;            // 16 KB: one bf16 part of the X tile (128-byte rows)
+constexpr int kABytes = 2 * kAPart;                // 32 KB
+constexpr int kWPart = kGroupCols * 128;           // 32 KB
+constexpr int kWBytes = 2 * kWPart;                // 64 KB per group
+constexpr int kWStages = 2;
+constexpr int kEpiWarps = 8;                       // warps 0-7
+constexpr int kProdWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kConvWarp0 = 10;                     // warps 10-13
+constexpr int kConvWarps = 4;
+constexpr int kThreads = (kConvWarp0 + kConvWarps) * 32;   // 448
+constexpr int kTmemCols = 512;
+
+struct __align__(1024) SmemLayout {
+  uint8_t a[2][kABytes];
+  uint8_t w[kWStages][kWBytes];
+  float lse_m[2][kTileRows];       // partial (max, sum) of the upper column half, per row
+  float lse_s[2][kTileRows];
+  double sum_lse;
+  uint64_t a_full[2], a_empty[2];
+  uint64_t w_full[kWStages], w_empty[kWStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t lse_ready[2], lse_taken[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// plain (non-tensor) bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(ptx::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], uint32_t (&b2)[2]) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y);
+  __nv_bfloat162 p1 = __floats2bfloat162_rn(x.z, x.w);
+  b1[0] = *reinterpret_cast<uint32_t*>(&p0);
+  b1[1] = *reinterpret_cast<uint32_t*>(&p1);
+  const float rx = x.x - __uint_as_float(b1[0] << 16);
+  const float ry = x.y - __uint_as_float(b1[0] & 0xFFFF0000u);
+  const float rz = x.z - __uint_as_float(b1[1] << 16);
+  const float rw = x.w - __uint_as_float(b1[1] & 0xFFFF0000u);
+  __nv_bfloat162 q0 = __floats2bfloat162_rn(rx, ry);
+  __nv_bfloat162 q1 = __floats2bfloat162_rn(rz, rw);
+  b2[0] = *reinterpret_cast<uint32_t*>(&q0);
+  b2[1] = *reinterpret_cast<uint32_t*>(&q1);
+}
+
+// U[k, j, i] float32 (row j of factor k) -> wprep[group][part][256 rows x 128 B] bf16 in the K-major
+// SWIZZLE_128B layout (row r = 64 (k % 4) + j; features i >= d and rows j >= d are zero);
+// t[k, j] -> tprep[k][64] zero-padded.
+__global__ void prep_factors_kernel(const float* __restrict__ u, const float* __restrict__ t, int k_total, int d,
+                                    uint8_t* __restrict__ wprep, float* __restrict__ tprep) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // (k, j, chunk of 8 features)
+  const int64_t total = static_cast<int64_t>(k_total) * 64 * 8;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % 8);
+  const int j = static_cast<int>((idx / 8) % 64);
+  const int k = static_cast<int>(idx / (8 * 64));
+  __align__(16) __nv_bfloat16 b1[8], b2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int i = c * 8 + e;
+    const float x = (j < d && i < d) ? u[(static_cast<int64_t>(k) * d + j) * d + i] : 0.f;
+    b1[e] = __float2bfloat16_rn(x);
+    b2[e] = __float2bfloat16_rn(x - __bfloat162float(b1[e]));
+  }
+  const int group = k / kGroupComps, r = (k % kGroupComps) * 64 + j;
+  const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+  uint8_t* base = wprep + static_cast<int64_t>(group) * kWBytes;
+  *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(b1);
+  *reinterpret_cast<uint4*>(base + kWPart + off) = *reinterpret_cast<const uint4*>(b2);
+  if (c == 0) tprep[static_cast<int64_t>(k) * 64 + j] = j < d ? t[static_cast<int64_t>(k) * d + j] : 0.f;
+}
+
+struct LogitParams {
+  const float* x;
+  const uint8_t* wprep;
+  const float* tprep;       // [k][64]
+  const float* c;           // [k]
+  float* logits;            // [n, k]
+  float* lse;               // [n] or nullptr
+  double* partial_sum_lse;  // [grid] or nullptr
+  int64_t n;
+  int d, k;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const LogitParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_groups = p.k / kGroupComps;
+  const int k_steps = p.d / 16;
+  const int64_t n_tiles = (p.n + kTileRows - 1) / kTileRows;
+  const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&sm.a_full[b], kConvWarps);
+        ptx::mbar_init(&sm.a_empty[b], 1);
+        ptx::mbar_init(&sm.acc_full[b], 1);
+        ptx::mbar_init(&sm.acc_empty[b], kEpiWarps);
+        ptx::mbar_init(&sm.lse_ready[b], 4);
+        ptx::mbar_init(&sm.lse_taken[b], 4);
+      }
+      for (int s = 0; s < kWStages; ++s) {
+        ptx::mbar_init(&sm.w_full[s], 1);
+        ptx::mbar_init(&sm.w_empty[s], 1);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
+  }
+  if (threadIdx.x == 0) sm.sum_lse = 0.0;
+  // zero the padding features of both X tile buffers once (d < 64: chunks beyond d stay zero)
+  for (int i = threadIdx.x; i < 2 * kABytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(&sm.a[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < kEpiWarps) {
+    // ---------------- epilogue: lane = data row; warp = (quadrant q, column half h) ----------------
+    const int q = warp & 3, h = warp >> 2;
+    double sum_lse = 0.0;
+    int64_t gi = 0;
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int64_t tile = blockIdx.x + t * gridDim.x;
+      const int64_t row = tile * kTileRows + q * 32 + lane;
+      const bool valid = row < p.n;
+      float run_m = -INFINITY, run_s = 0.f;
+      for (int g = 0; g < n_groups; ++g, ++gi) {
+        const int ab = static_cast<int>(gi & 1);
+        ptx::mbar_wait(&sm.acc_full[ab], static_cast<uint32_t>(gi >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + ab * kGroupCols + h * 128;
+        float logit[2];
+#pragma unroll
+        for (int cidx = 0; cidx < 2; ++cidx) {
+          const int comp = g * kGroupComps + h * 2 + cidx;
+          float acc = 0.f;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_addr + cidx * 64 + half * 32, v);
+            const float tl = __ldg(p.tprep + static_cast<int64_t>(comp) * 64 + half * 32 + lane);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float dz = __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, tl, j);
+              acc = fmaf(dz, dz, acc);
+            }
+          }
+          logit[cidx] = fmaf(-0.5f, acc, __ldg(p.c + comp));
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm.acc_empty[ab]);
+        if (valid)
+          *reinterpret_cast<float2*>(p.logits + row * p.k + g * kGroupComps + h * 2) = make_float2(logit[0], logit[1]);
+        // online log-sum-exp over this warp's components
+        const float m_new = fmaxf(run_m, fmaxf(logit[0], logit[1]));
+        run_s = run_s * __expf(run_m - m_new) + __expf(logit[0] - m_new) + __expf(logit[1] - m_new);
+        run_m = m_new;
+      }
+      // combine the two column halves of each row: h = 1 hands (m, s) to h = 0 through shared memory
+      const int tb = static_cast<int>(t & 1);
+      const uint32_t ph = static_cast<uint32_t>(t >> 1) & 1;
+      if (h == 1) {
+        ptx::mbar_wait(&sm.lse_taken[tb], ph ^ 1);
+        sm.lse_m[tb][q * 32 + lane] = run_m;
+        sm.lse_s[tb][q * 32 + lane] = run_s;
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm.lse_ready[tb]);
+      } else {
+        ptx::mbar_wait(&sm.lse_ready[tb], ph);
+        const float om = sm.lse_m[tb][q * 32 + lane], os = sm.lse_s[tb][q * 32 + lane];
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm.lse_taken[tb]);
+        const float m = fmaxf(run_m, om);
+        const float s = run_s * __expf(run_m - m) + os * __expf(om - m);
+        const float lse = m + __logf(s);
+        if (valid) {
+          if (p.lse != nullptr) p.lse[row] = lse;
+          sum_lse += static_cast<double>(lse);
+        }
+      }
+    }
+    if (h == 0 && p.partial_sum_lse != nullptr) atomicAdd(&sm.sum_lse, sum_lse);
+  } else if (warp == kProdWarp) {
+    // ---------------- factor-tile producer: two 32 KB bulk copies per group ----------------
+    if (ptx::elect_one()) {
+      int64_t gi = 0;
+      for (int64_t t = 0; t < my_tiles; ++t)
+        for (int g = 0; g < n_groups; ++g, ++gi) {
+          const int s = static_cast<int>(gi % kWStages);
+          ptx::mbar_wait(&sm.w_empty[s], (static_cast<uint32_t>(gi / kWStages) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&sm.w_full[s], kWBytes);
+          const uint8_t* src = p.wprep + static_cast<int64_t>(g) * kWBytes;
+          bulk_load(sm.w[s], src, kWPart, &sm.w_full[s]);
+          bulk_load(sm.w[s] + kWPart, src + kWPart, kWPart, &sm.w_full[s]);
+        }
+    }
+  } else if (warp == kMmaWarp) {
+    // ---------------- MMA issuer ----------------
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc(128, kGroupCols, /*bf16*/ 1, /*A K-major*/ 0, /*B K-major*/ 0);
+      int64_t gi = 0;
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const int tb = static_cast<int>(t & 1);
+        ptx::mbar_wait(&sm.a_full[tb], static_cast<uint32_t>(t >> 1) & 1);
+        const uint32_t a_base = ptx::smem_u32(sm.a[tb]);
+        for (int g = 0; g < n_groups; ++g, ++gi) {
+          const int s = static_cast<int>(gi % kWStages);
+          const int ab = static_cast<int>(gi & 1);
+          ptx::mbar_wait(&sm.w_full[s], static_cast<uint32_t>(gi / kWStages) & 1);
+          ptx::mbar_wait(&sm.acc_empty[ab], (static_cast<uint32_t>(gi >> 1) & 1) ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t w_base = ptx::smem_u32(sm.w[s]);
+          const uint32_t d_tmem = tmem + ab * kGroupCols;
+          for (int ks = 0; ks < k_steps; ++ks) {
+            const uint64_t a1 = ptx::make_smem_desc(a_base + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
+            const uint64_t a2 = ptx::make_smem_desc(a_base + kAPart + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
+            const uint64_t b1 = ptx::make_smem_desc(w_base + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
+            const uint64_t b2 = ptx::make_smem_desc(w_base + kWPart + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
+            mma_bf16_ss(d_tmem, a1, b1, idesc, ks == 0 ? 0u : 1u);
+            mma_bf16_ss(d_tmem, a1, b2, idesc, 1u);
+            mma_bf16_ss(d_tmem, a2, b1, idesc, 1u);
+          }
+          ptx::mma_commit(&sm.w_empty[s]);
+          ptx::mma_commit(&sm.acc_full[ab]);
+        }
+        ptx::mma_commit(&sm.a_empty[tb]);
+      }
+    }
+  } else {
+    // ---------------- X tile converter: 4 warps x 32 rows, lane covers float4 (lane & 15) of 2 rows ----------------
+    const int wi = warp - kConvWarp0;
+    const int sub = lane >> 4, c4 = lane & 15;
+    const bool col_ok = c4 * 4 < p.d;
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int tb = static_cast<int>(t & 1);
+      const int64_t tile = blockIdx.x + t * gridDim.x;
+      float4 rx[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int64_t row = tile * kTileRows + wi * 32 + 2 * i + sub;
+        rx[i] = (col_ok && row < p.n) ? ldg_f4(p.x + row * p.d + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ptx::mbar_wait(&sm.a_empty[tb], (static_cast<uint32_t>(t >> 1) & 1) ^ 1);
+      const uint32_t a_base = ptx::smem_u32(sm.a[tb]);
+      if (col_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = wi * 32 + 2 * i + sub;
+          const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
+          uint32_t b1[2], b2[2];
+          split_bf16(rx[i], b1, b2);
+          sts_u2(a_base + off, b1[0], b1[1]);
+          sts_u2(a_base + kAPart + off, b2[0], b2[1]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.a_full[tb]);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0 && p.partial_sum_lse != nullptr) p.partial_sum_lse[blockIdx.x] = sm.sum_lse;
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc += partial[i];
+    *out = acc;
+  }
+}
+
+int logits_grid(int64_t n) {
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sms, tiles)));
+}
+
+}  // namespace
+
+bool mixture_logits_supported(int64_t n, int d, int k, const void* x) {
+  return n > 0 && d >= 16 && d <= 64 && d % 16 == 0 && k >= 4 && k % 4 == 0 && k <= 4096 &&
+         reinterpret_cast<uintptr_t>(x) % 16 == 0;
+}
+
+int64_t mixture_logits_workspace(int64_t n, int d, int k) {
+  (void)d;
+  return static_cast<int64_t>(k / kGroupComps) * kWBytes + static_cast<int64_t>(k) * 64 * 4 +
+         static_cast<int64_t>(logits_grid(n)) * 8 + 1024;
+}
+
+// u [k, d, d] (upper Cholesky factors, row-major), t [k, d], c [k]: device float32.
+// logits [n, k] float32 (required), lse [n] float32 and sum_lse (float64) optional.
+int launch_mixture_logits(const float* x, const float* u, const float* t, const float* c, int64_t n, int d, int k,
+                          float* logits, float* lse, double* sum_lse, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t stream) {
+  if (!mixture_logits_supported(n, d, k, x) || reinterpret_cast<uintptr_t>(logits) % 8 != 0) {
+    set_error("mixture_logits: unsupported shape n=%lld d=%d k=%d", static_cast<long long>(n), d, k);
+    return BB_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < mixture_logits_workspace(n, d, k)) {
+    set_error("mixture_logits: workspace %lld < %lld bytes", static_cast<long long>(workspace_bytes),
+              static_cast<long long>(mixture_logits_workspace(n, d, k)));
+    return BB_ERR_WORKSPACE;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  uint8_t* wprep = ws;
+  ws += static_cast<int64_t>(k / kGroupComps) * kWBytes;
+  float* tprep = reinterpret_cast<float*>(ws);
+  ws += static_cast<int64_t>(k) * 64 * 4;
+  double* partial = reinterpret_cast<double*>(ws);
+  const int64_t prep_items = static_cast<int64_t>(k) * 64 * 8;
+  prep_factors_kernel<<<static_cast<int>((prep_items + 255) / 256), 256, 0, stream>>>(u, t, k, d, wprep, tprep);
+  BB_CHECK_LAUNCH("prep_factors_kernel");
+  LogitParams p;
+  p.x = x; p.wprep = wprep; p.tprep = tprep; p.c = c; p.logits = logits; p.lse = lse;
+  p.partial_sum_lse = sum_lse != nullptr ? partial : nullptr;
+  p.n = n; p.d = d; p.k = k;
+  const int grid = logits_grid(n);
+  const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
+  static bool attr_set = false;
+  if (!attr_set) {
+    BB_CUDA_OK(cudaFuncSetAttribute(mixture_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  mixture_logits_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  BB_CHECK_LAUNCH("mixture_logits_kernel");
+  if (sum_lse != nullptr) {
+    sum_partials_kernel<<<1, 32, 0, stream>>>(partial, grid, sum_lse);
+    BB_CHECK_LAUNCH("sum_partials_kernel");
+  }
+  return BB_OK;
+}
+
+}  // namespace bb

@@ -65,9 +65,25 @@ class GmmStep(object):
               - 0.5 * np.einsum('kd,kd->k', bk, m))
         return Ak.astype(np.float32), bk.astype(np.float32), ck.astype(np.float32)
 
-    def __call__(self, X, Ak, bk, ck):
+    @staticmethod
+    def whiten(Ak, bk, ck):
+        """(U_k, t_k, c'_k) with A_k = U_k^T U_k, t_k = U_k m_k = U_k^-T b_k, c'_k = c_k + |t_k|^2 / 2,
+        so that  c_k + x.b_k - x^T A_k x / 2  =  c'_k - |U_k x - t_k|^2 / 2   (float64 on the device)."""
         import torch
-        logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
+        A64 = Ak.double()
+        U = torch.linalg.cholesky(A64, upper=True)
+        t = torch.linalg.solve_triangular(U.transpose(1, 2), bk.double().unsqueeze(-1), upper=False).squeeze(-1)
+        c = ck.double() + 0.5 * (t * t).sum(1)
+        return U.float().contiguous(), t.float().contiguous(), c.float().contiguous()
+
+    def __call__(self, X, Ak, bk, ck, fused=True):
+        import torch
+        if fused and stats.mixture_logits_supported(X.shape[1], Ak.shape[0]):
+            # same value as the einsum plan, as one tcgen05 projection with the quadratic form
+            # consumed on chip (the plan route materialises N x K x D and cannot run at cfg3 size)
+            logits, _, _ = stats.mixture_logits(X, *self.whiten(Ak, bk, ck), want_lse=False, want_sum=False)
+        else:
+            logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
         log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place
         resp = torch.exp(log_resp)
         nk, rx, rxx = stats.weighted_suffstats(X, resp)

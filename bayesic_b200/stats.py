@@ -19,7 +19,8 @@ from .backend import library as L
 
 __all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'log_responsibilities',
            'weighted_suffstats', 'regression_suffstats', 'row_projection', 'column_projection',
-           'logistic_reparam_stats', 'logistic_reparam_supported', 'launch_count']
+           'logistic_reparam_stats', 'logistic_reparam_supported', 'mixture_logits',
+           'mixture_logits_supported', 'launch_count']
 
 _scratch = {}
 
@@ -266,3 +267,34 @@ def logistic_reparam_stats(X, y, W):
                                              loglik.data_ptr(), G.data_ptr(), ws.data_ptr(), ws.numel(),
                                              _stream(dev)), 'bb_logistic_reparam_pass')
     return loglik, G
+
+
+def mixture_logits_supported(d, k):
+    """Shapes the tcgen05 mixture-logit kernel serves."""
+    return d in (16, 32, 48, 64) and k % 4 == 0 and k >= 4
+
+
+def mixture_logits(X, U, t, c, want_lse=True, want_sum=True):
+    """``logits[n, k] = c[k] - 0.5 * ||U[k] @ x_n - t[k]||**2`` (float32 CUDA tensor) and,
+    optionally, the row log-sum-exp ``lse[n]`` and its sum (float64[1])."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    U = _as_device_f32(U, 3, 'U')
+    t = _as_device_f32(t, 2, 't')
+    c = _as_device_f32(c, 1, 'c')
+    n, d = X.shape
+    k = U.shape[0]
+    if tuple(U.shape) != (k, d, d) or tuple(t.shape) != (k, d) or c.shape[0] != k:
+        raise ValueError("mixture_logits: inconsistent shapes")
+    dev = X.device
+    with torch.cuda.device(dev):
+        logits = torch.empty((n, k), dtype=torch.float32, device=dev)
+        lse = torch.empty(n, dtype=torch.float32, device=dev) if want_lse else None
+        total = torch.empty(1, dtype=torch.float64, device=dev) if want_sum else None
+        ws = _workspace(lib.bb_mixture_logits_workspace(n, d, k), dev)
+        L.check(lib.bb_mixture_logits(X.data_ptr(), U.data_ptr(), t.data_ptr(), c.data_ptr(), n, d, k,
+                                      logits.data_ptr(), lse.data_ptr() if want_lse else None,
+                                      total.data_ptr() if want_sum else None, ws.data_ptr(), ws.numel(),
+                                      _stream(dev)), 'bb_mixture_logits')
+    return logits, lse, total

@@ -228,6 +228,18 @@ BB_API int bb_logistic_reparam_pass(const float* X, const float* y, const float*
 BB_API int bb_logsoftmax_rows(const float* logits, int64_t n, int32_t k,
                        float* log_resp, float* lse, double* sum_lse, void* stream);
 
+/* Gaussian-mixture expected log-densities in whitened form (VMP local step, README.md:30-37):
+ *   logits[n,k] = c[k] - 1/2 || U[k] x_n - t[k] ||^2      (= c' + x.b_k - 1/2 x^T A_k x with
+ *   A_k = U_k^T U_k, t_k = U_k m_k), optionally lse[n] = logsumexp_k logits[n,:] and
+ *   sum_lse = sum_n lse[n] (float64).  U [k,d,d], t [k,d], c [k], logits [n,k], lse [n]: device
+ *   float32.  This is the value of the user expression dot(X, bk.T) - 0.5 einsum(X, Ak, X) + ck
+ *   (the reference's plan for it is a batched _tensordot whose evaluation is broken,
+ *   algebra.py:1370-1373, :1380).  Needs d in {16,32,48,64}, k % 4 == 0 (BB_ERR_UNSUPPORTED otherwise). */
+BB_API int64_t bb_mixture_logits_workspace(int64_t n, int32_t d, int32_t k);
+BB_API int bb_mixture_logits(const float* X, const float* U, const float* t, const float* c,
+                      int64_t n, int32_t d, int32_t k, float* logits, float* lse, double* sum_lse,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Responsibility-weighted statistics in one pass over (R, X):
  *   Nk[k] = sum_n R[n,k];  sum_rx[k,d] = sum_n R[n,k] X[n,d];
  *   sum_rxx[k,d,e] = sum_n R[n,k] X[n,d] X[n,e]           (float64 out, device) */

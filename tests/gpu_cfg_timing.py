@@ -60,8 +60,10 @@ def cfg3():
     step = P.GmmStep()
     ms = timeit(lambda: step(X, Ak, bk, ck), reps=2)
     print('cfg3 GmmStep (N = %d): %.2f ms/step  %.2f M rows/s' % (n, ms, n / ms / 1e3), flush=True)
-    ms = timeit(lambda: step.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck), reps=2)
-    print('  logits plan: %.2f ms (launches %d)' % (ms, step.logits_fn.plan.last_launches), flush=True)
+    U, t, c = step.whiten(Ak, bk, ck)
+    ms = timeit(lambda: S.mixture_logits(X, U, t, c), reps=3)
+    print('  mixture logits kernel: %.2f ms  %.1f M rows/s  %.0f TFLOP/s issued bf16'
+          % (ms, n / ms / 1e3, 3 * 2.0 * k * d * d * n / ms / 1e9), flush=True)
     R = torch.softmax(torch.randn(n, k, device='cuda'), 1)
     ms = timeit(lambda: S.weighted_suffstats(X, R), reps=2)
     print('  weighted stats: %.2f ms' % ms, flush=True)

@@ -150,3 +150,29 @@ def test_cfg5_logistic_reparam_gradient_on_the_projection_kernels():
         _close(got['grad_mu'], want['grad_mu'], scale_atol=2e-5)
         _close(got['grad_log_sigma'], want['grad_log_sigma'], scale_atol=2e-5)
         assert abs(float(got['elbo']) - want['elbo']) <= 1e-4 * abs(want['elbo'])
+
+
+def test_cfg3_gmm_vmp_step_on_the_tensor_core_kernels():
+    """Same step at D = 64 with enough rows for the tcgen05 kernels (whitened logits, regrouped
+    weighted statistics), and the plan route (fused=False) at the same inputs as a cross-check."""
+    import torch
+    rng = np.random.RandomState(7)
+    n, d, k = 6000, 64, 8
+    centers = rng.randn(k, d) * 1.5
+    X = (centers[rng.randint(k, size=n)] + rng.randn(n, d)).astype(np.float32)
+    log_pi = np.log(rng.dirichlet(np.ones(k)))
+    m = centers + rng.randn(k, d) * 0.05
+    beta = rng.rand(k) * 5 + 1
+    nu = d + 2 + rng.rand(k) * 5
+    W = np.stack([np.linalg.inv(_spd(rng, d)) / nu[j] for j in range(k)])
+    want = O.gmm_vmp_step(X, log_pi, m, beta, W, nu)
+    step = P.GmmStep()
+    Ak, bk, ck = step.expectations(log_pi, m, beta, W, nu)
+    for fused in (True, False):
+        got = step(torch.from_numpy(X).cuda(), torch.from_numpy(Ak).cuda(), torch.from_numpy(bk).cuda(),
+                   torch.from_numpy(ck).cuda(), fused=fused)
+        np.testing.assert_allclose(got['log_resp'].cpu().numpy(), want['log_resp'], rtol=1e-4, atol=3e-3)
+        _close(got['nk'], want['nk'], rtol=1e-4, scale_atol=2e-5)
+        _close(got['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
+        _close(got['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
+        assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])

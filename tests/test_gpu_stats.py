@@ -330,3 +330,38 @@ def test_projection_unsupported_shapes_fail_loudly():
         S.row_projection(X, torch.zeros(64, 96, device='cuda'))        # d % 64 != 0
     with pytest.raises(BackendError):
         S.column_projection(X, torch.zeros(64, 64, device='cuda'))     # d % 128 != 0
+
+
+# ---- mixture logits (cfg3): c_k - 1/2 |U_k x - t_k|^2 on tcgen05 --------------------------------
+
+@pytest.mark.parametrize('n,d,k', [(1, 64, 4), (127, 64, 8), (128, 64, 4), (129, 16, 12), (1000, 32, 8),
+                                   (5000, 48, 20), (20000, 64, 256), (4097, 64, 64)])
+def test_mixture_logits(n, d, k):
+    """Whitened Gaussian-mixture logits + row log-sum-exp vs float64.  The logits are O(1e2) in
+    magnitude and come out of a float32 epilogue, hence the absolute term."""
+    import torch
+    from scipy.special import logsumexp
+    rng = np.random.RandomState(n + d + k)
+    centers = rng.randn(k, d) * 2
+    X = (centers[rng.randint(k, size=n)] + rng.randn(n, d)).astype(np.float32)
+    A = np.stack([_spd_np(rng, d) for _ in range(k)])
+    U = np.stack([np.linalg.cholesky(a).T for a in A])                  # A = U^T U
+    t = np.einsum('kji,ki->kj', U, centers)
+    c = rng.randn(k)
+    before = S.launch_count()
+    logits, lse, total = S.mixture_logits(torch.from_numpy(X).cuda(), torch.from_numpy(U.astype(np.float32)).cuda(),
+                                          torch.from_numpy(t.astype(np.float32)).cuda(),
+                                          torch.from_numpy(c.astype(np.float32)).cuda())
+    assert S.launch_count() > before
+    U32, t32, c32 = U.astype(np.float32).astype(np.float64), t.astype(np.float32).astype(np.float64), c.astype(np.float32).astype(np.float64)
+    z = np.einsum('kji,ni->nkj', U32, X.astype(np.float64)) - t32[None]
+    want = c32[None, :] - 0.5 * (z * z).sum(-1)
+    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=1e-4, atol=2e-3)
+    want_lse = logsumexp(want, axis=1)
+    np.testing.assert_allclose(lse.cpu().numpy(), want_lse, rtol=1e-4, atol=2e-3)
+    assert abs(float(total) - want_lse.sum()) <= 1e-4 * abs(want_lse.sum()) + 1e-3
+
+
+def _spd_np(rng, d):
+    a = rng.randn(d, d)
+    return a @ a.T / d + np.eye(d)
