@@ -233,7 +233,6 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     float xa[2][2];          // [row][block slot]: the left factor of the pair product (1 for the linear block)
     float4 xb[2][2];         // the four right factors
     float nk_f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    double nk_d[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
     int since_flush = 0;
     // everything a stage needs is loaded one iteration ahead (nothing is fetched between the
     // barrier wait and the stores: dependent loads there serialise on the L2 latency)
@@ -299,13 +298,14 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       if (lane == 0) ptx::mbar_arrive(&sm.full[s]);
       row0 += kConvGroups * kStageRows;
       if (it + kConvGroups < n_iters) load_all();
-      if (do_nk && ++since_flush == 16) {
+      if (do_nk && ++since_flush == 16) {      // fp32 over 32 rows, then float64 in shared memory
         since_flush = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            nk_d[h][c] += static_cast<double>(nk_f[h][c]);
+            const int kc = 4 * lane + 128 * h + c;
+            if (kc < g.k) atomicAdd(&sm.nk[kc], static_cast<double>(nk_f[h][c]));
             nk_f[h][c] = 0.f;
           }
       }
@@ -316,7 +316,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int kc = 4 * lane + 128 * h + c;
-          if (kc < g.k) atomicAdd(&sm.nk[kc], nk_d[h][c] + static_cast<double>(nk_f[h][c]));
+          if (kc < g.k) atomicAdd(&sm.nk[kc], static_cast<double>(nk_f[h][c]));
         }
     }
   } else if (warp < kMmaWarp) {
