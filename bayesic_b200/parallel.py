@@ -13,7 +13,8 @@ packed float64 buffer so the collective is a single latency-bound call.
 """
 import numpy as np
 
-__all__ = ['shard_bounds', 'PackedStats', 'allreduce_packed', 'gaussian_suffstats_sharded']
+__all__ = ['shard_bounds', 'PackedStats', 'allreduce_packed', 'gaussian_suffstats_sharded',
+           'regression_suffstats_sharded', 'mixture_suffstats_sharded', 'logistic_reparam_sharded']
 
 
 def shard_bounds(n, world_size, rank):
@@ -45,6 +46,14 @@ class PackedStats(object):
     @classmethod
     def mixture(cls, k, d):
         return cls([('rxx', (k, d, d)), ('rx', (k, d)), ('nk', (k,)), ('sum_lse', (1,)), ('count', (1,))])
+
+    @classmethod
+    def regression(cls, d):
+        return cls([('xtx', (d, d)), ('xty', (d,)), ('yty', (1,)), ('count', (1,))])
+
+    @classmethod
+    def logistic(cls, d, s):
+        return cls([('G', (d, s)), ('loglik', (s,)), ('count', (1,))])
 
     def allocate(self, device=None):
         import torch
@@ -81,3 +90,48 @@ def gaussian_suffstats_sharded(X_local, layout=None, buffer=None, group=None):
     views['count'].fill_(float(n_local))
     allreduce_packed(buffer, group)
     return views
+
+
+def _reduce_into(layout, device, parts, n_local, buffer, group):
+    if buffer is None:
+        buffer = layout.allocate(device)
+    views = layout.views(buffer)
+    for name, value in parts.items():
+        views[name].copy_(value.reshape(views[name].shape))
+    views['count'].fill_(float(n_local))
+    allreduce_packed(buffer, group)
+    return views
+
+
+def regression_suffstats_sharded(X_local, y_local, buffer=None, group=None):
+    """cfg4: ``{xtx, xty, yty, count}`` of the whole minibatch from this rank's rows: local fused
+    pass (tcgen05 CTA pairs when D % 256 == 0), then one all-reduce of D^2 + D + 2 float64."""
+    from . import stats
+    n_local, d = X_local.shape
+    xtx, xty, yty = stats.regression_suffstats(X_local, y_local)
+    return _reduce_into(PackedStats.regression(d), X_local.device, {'xtx': xtx, 'xty': xty, 'yty': yty},
+                        n_local, buffer, group)
+
+
+def mixture_suffstats_sharded(X_local, R_local, sum_lse_local=None, buffer=None, group=None):
+    """cfg3: ``{nk, rx, rxx, sum_lse, count}`` of the whole data set from this rank's rows and
+    responsibilities (which stay sharded); one all-reduce of K (D^2 + D + 1) + 2 float64."""
+    from . import stats
+    n_local, d = X_local.shape
+    k = R_local.shape[1]
+    nk, rx, rxx = stats.weighted_suffstats(X_local, R_local)
+    parts = {'nk': nk, 'rx': rx, 'rxx': rxx}
+    if sum_lse_local is not None:
+        parts['sum_lse'] = sum_lse_local
+    return _reduce_into(PackedStats.mixture(k, d), X_local.device, parts, n_local, buffer, group)
+
+
+def logistic_reparam_sharded(X_local, y_local, W, buffer=None, group=None):
+    """cfg5: ``{loglik[S], G[D, S], count}`` summed over all ranks' rows for the replicated
+    parameter draws ``W[S, D]``; one all-reduce of S (D + 1) + 1 float64."""
+    from . import stats
+    n_local, d = X_local.shape
+    s = W.shape[0]
+    loglik, G = stats.logistic_reparam_stats(X_local, y_local, W)
+    return _reduce_into(PackedStats.logistic(d, s), X_local.device, {'loglik': loglik, 'G': G}, n_local,
+                        buffer, group)

@@ -90,3 +90,63 @@ def test_two_rank_allreduce_reproduces_the_full_statistics():
         np.testing.assert_allclose(v['s1'], s1, rtol=1e-12)
         assert v['count'][0] == cnt
     np.testing.assert_array_equal(results[0], results[1])    # replicas agree bit for bit
+
+
+def _worker_all_layouts(rank, world, port, queue):
+    """Every packed layout through the same one-collective path, local parts from the oracle."""
+    import torch
+    import torch.distributed as dist
+    from oracle import closed_forms as O
+    from bayesic_b200.parallel import _reduce_into
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(7)
+        n, d, k, s = 501, 4, 3, 2
+        X = rng.randn(n, d).astype(np.float32)
+        y = rng.randn(n).astype(np.float32)
+        R = rng.dirichlet(np.ones(k), size=n).astype(np.float32)
+        lo, hi = shard_bounds(n, world, rank)
+        t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))
+        xtx, xty, yty = O.regression_suffstats(X[lo:hi], y[lo:hi])
+        reg = _reduce_into(PackedStats.regression(d), None, {'xtx': t(xtx), 'xty': t(xty), 'yty': t([yty])},
+                           hi - lo, None, None)
+        nk, rx, rxx = O.weighted_suffstats(X[lo:hi], R[lo:hi])
+        mix = _reduce_into(PackedStats.mixture(k, d), None, {'nk': t(nk), 'rx': t(rx), 'rxx': t(rxx)},
+                           hi - lo, None, None)
+        queue.put((rank, {name: v.numpy().copy() for name, v in reg.items()},
+                   {name: v.numpy().copy() for name, v in mix.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_of_the_regression_and_mixture_layouts():
+    import torch.multiprocessing as mp
+    from oracle import closed_forms as O
+    world = 2
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_all_layouts, args=(r, world, port, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.RandomState(7)
+    n, d, k = 501, 4, 3
+    X = rng.randn(n, d).astype(np.float32)
+    y = rng.randn(n).astype(np.float32)
+    R = rng.dirichlet(np.ones(k), size=n).astype(np.float32)
+    xtx, xty, yty = O.regression_suffstats(X, y)
+    nk, rx, rxx = O.weighted_suffstats(X, R)
+    for _, reg, mix in results:
+        np.testing.assert_allclose(reg['xtx'], xtx, rtol=1e-12)
+        np.testing.assert_allclose(reg['xty'], xty, rtol=1e-12)
+        np.testing.assert_allclose(reg['yty'][0], yty, rtol=1e-12)
+        assert reg['count'][0] == n and mix['count'][0] == n
+        np.testing.assert_allclose(mix['nk'], nk, rtol=1e-12)
+        np.testing.assert_allclose(mix['rx'], rx, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(mix['rxx'], rxx, rtol=1e-12, atol=1e-12)
