@@ -275,9 +275,56 @@ int run_tensordot(Exec& ex, int idx, const bb_node_desc& nd) {
   void* ws = nullptr;
   const int64_t ws_bytes = gemm_workspace_bytes(M, N, K, batch);
   if (ws_bytes > 0) BB_TRY(ex.alloc_scratch(ws_bytes, &ws));
-  if (!ex.dry())
-    BB_TRY(launch_gemm(X.ptr, Y.ptr, out.ptr, M, N, K, batch, xs[0], xs[1], xs[2], ys[0], ys[2],
-                       ys[1], ws, ex.stream));
+
+  // Large contractions of the two shapes the hot path is made of go to the tcgen05 kernels
+  // (decided from extents and strides only, so the dry pass reserves the same scratch):
+  //   rows x features . (q x features)^T  -> rowproj   (dot(X, W.T): per-row projection)
+  //   (rows x d)^T . rows x q             -> colproj   (dot(X.T, R): contraction over the data axis)
+  const int64_t kMinRows = 4096;
+  const bool small_dims = M <= 2147483647LL && N <= 4096 && K <= 2147483647LL;
+  const bool x_k_major = xs[2] == 1 && xs[1] == K, y_k_major = ys[2] == 1 && ys[1] == K;
+  const bool x_mn_major = xs[1] == 1 && xs[2] == M, y_mn_major = ys[1] == 1 && ys[2] == N;
+  const bool row_shape = batch == 1 && small_dims && M >= kMinRows && x_k_major && (y_k_major || y_mn_major) &&
+                         K >= 64 && K % 64 == 0 && K <= 32768 && N >= 16 && N % 16 == 0 && N <= 256 && N * K <= 32768;
+  const bool col_shape = batch == 1 && small_dims && K >= kMinRows && x_mn_major && y_mn_major && M >= 128 &&
+                         M % 128 == 0 && N >= 64 && N % 64 == 0 && (M / 128) * (N / 64) <= 4;
+  void* tc_ws = nullptr;
+  void* tc_aux = nullptr;      // rowproj: W transposed to (q, features); colproj: float64 result
+  int64_t tc_ws_bytes = 0;
+  if (row_shape) {
+    tc_ws_bytes = rowproj_tc_workspace(M, static_cast<int>(K), static_cast<int>(N));
+    BB_TRY(ex.alloc_scratch(tc_ws_bytes, &tc_ws));
+    if (!y_k_major) BB_TRY(ex.alloc_scratch(N * K * 4, &tc_aux));
+  } else if (col_shape) {
+    tc_ws_bytes = colproj_tc_workspace(K, static_cast<int>(M), static_cast<int>(N));
+    BB_TRY(ex.alloc_scratch(tc_ws_bytes, &tc_ws));
+    BB_TRY(ex.alloc_scratch(M * N * 8, &tc_aux));
+  }
+  if (!ex.dry()) {
+    bool done = false;
+    if (row_shape && rowproj_tc_supported(M, static_cast<int>(K), static_cast<int>(N), X.ptr) &&
+        reinterpret_cast<uintptr_t>(out.ptr) % 16 == 0) {
+      const float* w = Y.ptr;
+      if (!y_k_major) {      // W given as (features, q): dense transposed copy (tiny)
+        View src, dst;
+        src.ptr = Y.ptr; src.ndim = 2; src.shape[0] = N; src.shape[1] = K; src.stride[0] = ys[1]; src.stride[1] = ys[2];
+        dst = src; dst.ptr = static_cast<float*>(tc_aux); dst.set_contiguous_strides();
+        BB_TRY(launch_strided_copy(dst, src, ex.stream));
+        w = dst.ptr;
+      }
+      BB_TRY(launch_rowproj_tc(X.ptr, w, nullptr, M, static_cast<int>(K), static_cast<int>(N), out.ptr, nullptr,
+                               tc_ws, tc_ws_bytes, ex.stream));
+      done = true;
+    } else if (col_shape && colproj_tc_supported(K, static_cast<int>(M), static_cast<int>(N), X.ptr, Y.ptr)) {
+      BB_TRY(launch_colproj_tc(X.ptr, Y.ptr, K, static_cast<int>(M), static_cast<int>(N),
+                               static_cast<double*>(tc_aux), tc_ws, tc_ws_bytes, ex.stream));
+      BB_TRY(launch_f64_to_f32(static_cast<const double*>(tc_aux), out.ptr, M * N, ex.stream));
+      done = true;
+    }
+    if (!done)
+      BB_TRY(launch_gemm(X.ptr, Y.ptr, out.ptr, M, N, K, batch, xs[0], xs[1], xs[2], ys[0], ys[2],
+                         ys[1], ws, ex.stream));
+  }
   ex.vals[idx] = out;
   return BB_OK;
 }

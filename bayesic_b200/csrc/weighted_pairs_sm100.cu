@@ -30,6 +30,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -142,7 +143,7 @@ __device__ __forceinline__ void pair_of(int b, int n_groups, int* ga, int* gb) {
 // R rows whatever its column count, so equal row ranges keep the CTAs in step.
 __global__ void __launch_bounds__(kThreads, 1)
 weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t n, Geometry g,
-                      int n_splits,
+                      int n_splits, int prefetch_iters,
                       float* __restrict__ partial,        // [cta][2 m-blocks][256 cols][128 lanes]
                       double* __restrict__ partial_nk) {  // [split of tile 0][k]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -159,6 +160,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
   const int64_t it_end = total_iters * (split + 1) / n_splits;
   const int n_iters = static_cast<int>(it_end - it_begin);
   const int64_t row_begin = it_begin * kStageRows;
+  const int64_t row_end = min(n, it_end * kStageRows);
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -174,6 +176,11 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
   }
   for (int i = threadIdx.x; i < kMaxK; i += kThreads) sm.nk[i] = 0.0;
+  // Every tile issues N = 256 MMAs so that all CTAs of a row range run at the same pace and share
+  // the R rows through L2; the unused blocks of a 3-block tile are never written and stay zero.
+  for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(&sm.stage[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -227,59 +234,97 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     const uint32_t stage0 = ptx::smem_u32(sm.stage[0]);
     int64_t row0 = row_begin + static_cast<int64_t>(group) * kStageRows + 2 * wi;
     const int kc0 = min(4 * lane, g.k - 4), kc1 = min(4 * lane + 128, g.k - 4);
-    const bool k_ok0 = 4 * lane < g.k, k_ok1 = 4 * lane + 128 < g.k;
+    const float km0 = 4 * lane < g.k ? 1.f : 0.f, km1 = 4 * lane + 128 < g.k ? 1.f : 0.f;
+    const bool k_partial = g.k < kMaxK;                  // some lanes hold components past k
+    // walking pointers (row0, this lane's columns); the loop is issue-bound, so no per-iteration
+    // address arithmetic beyond one add each
+    const float* rp = r + row0 * g.k;
+    const float* xp = x + row0 * g.d;
+    const int64_t r_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.k;
+    const int64_t x_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.d;
     float4 rr[2][2];
-    float rmask[2][2];
-    float xa[2][2];          // [row][block slot]: the left factor of the pair product (1 for the linear block)
+    float xa[2][2];          // [row][block slot]: the left factor of the pair product
     float4 xb[2][2];         // the four right factors
     float nk_f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     int since_flush = 0;
+    bool rows_ok = true;     // both rows of the prefetched stage are inside [0, n)
     // everything a stage needs is loaded one iteration ahead (nothing is fetched between the
     // barrier wait and the stores: dependent loads there serialise on the L2 latency)
     auto load_all = [&]() {
+      rows_ok = row0 + 2 <= n;
+      if (rows_ok) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const bool row_ok = row0 + j < n;
-        const int64_t rowc = row_ok ? row0 + j : n - 1;            // clamped: always a valid address
-        const float* rp = r + rowc * g.k;
-        const float* xr = x + rowc * g.d;
-        rr[j][0] = ldg_f4(rp + kc0);
-        rr[j][1] = ldg_f4(rp + kc1);
+        for (int j = 0; j < 2; ++j) {
+          rr[j][0] = ldg_f4(rp + j * g.k + kc0);
+          rr[j][1] = ldg_f4(rp + j * g.k + kc1);
 #pragma unroll
-        for (int t2 = 0; t2 < 2; ++t2) {
-          xa[j][t2] = __ldg(xr + src_a[t2]);
-          xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xr + src_b[t2]));
+          for (int t2 = 0; t2 < 2; ++t2) {
+            xa[j][t2] = __ldg(xp + j * g.d + src_a[t2]);
+            xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xp + j * g.d + src_b[t2]));
+          }
         }
-        // rows past the end and components past k contribute nothing: their weights are zeroed
-        // when the tile is formed (not here: touching the values would wait for the loads)
-        rmask[j][0] = (row_ok && k_ok0) ? 1.f : 0.f;
-        rmask[j][1] = (row_ok && k_ok1) ? 1.f : 0.f;
+      } else {                                            // ragged last stage: clamp, zero the weights
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool ok = row0 + j < n;
+          const int64_t back = ok ? 0 : (row0 + j) - (n - 1);     // rows to step back to stay in range
+          rr[j][0] = ldg_f4(rp + (j - back) * g.k + kc0);
+          rr[j][1] = ldg_f4(rp + (j - back) * g.k + kc1);
+#pragma unroll
+          for (int t2 = 0; t2 < 2; ++t2) {
+            xa[j][t2] = __ldg(xp + (j - back) * g.d + src_a[t2]);
+            xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xp + (j - back) * g.d + src_b[t2]));
+          }
+        }
       }
+      if (prefetch_iters > 0 && lane < 20) {             // L2 prefetch hints a few stages ahead
+        const bool is_r = lane < 16;
+        const int prow = is_r ? (lane >> 3) : ((lane - 16) >> 1);
+        const int64_t ahead = row0 + static_cast<int64_t>(prefetch_iters) * kConvGroups * kStageRows + prow;
+        if (ahead < row_end) {
+          const float* pp = is_r ? r + ahead * g.k + (lane & 7) * 32 : x + ahead * g.d + (lane & 1) * 32;
+          if ((is_r ? (lane & 7) * 32 : (lane & 1) * 32) < (is_r ? g.k : g.d)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+        }
+      }
+      row0 += kConvGroups * kStageRows;
+      rp += r_step;
+      xp += x_step;
     };
     if (group < n_iters) load_all();
     for (int it = group; it < n_iters; it += kConvGroups) {
       const int s = it % kStages;
       ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
       const uint32_t stage_addr = stage0 + s * kStageBytes;
+      if (!rows_ok || k_partial) {                        // rare: zero what lies past n or past k
+        const int64_t first = row0 - kConvGroups * kStageRows;   // row0 was advanced by load_all
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float rowm = first + j < n ? 1.f : 0.f;
+          const float m0 = rowm * km0, m1 = rowm * km1;
+          rr[j][0] = make_float4(rr[j][0].x * m0, rr[j][0].y * m0, rr[j][0].z * m0, rr[j][0].w * m0);
+          rr[j][1] = make_float4(rr[j][1].x * m1, rr[j][1].y * m1, rr[j][1].z * m1, rr[j][1].w * m1);
+        }
+      }
       // ---- R tile: [m block (64 components) 2 KB][k group][8][128 B] ----
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t b1[2], b2[2];
-          const float m = rmask[j][h];
-          rr[j][h] = make_float4(rr[j][h].x * m, rr[j][h].y * m, rr[j][h].z * m, rr[j][h].w * m);
           split_bf16(rr[j][h], b1, b2);
           const uint32_t addr = stage_addr + (2 * h + (lane >> 4)) * 2048 + off[j];
           sts_u2(addr, b1[0], b1[1]);
           sts_u2(addr + kRPart, b2[0], b2[1]);
-          if (do_nk) {
-            nk_f[h][0] += rr[j][h].x;
-            nk_f[h][1] += rr[j][h].y;
-            nk_f[h][2] += rr[j][h].z;
-            nk_f[h][3] += rr[j][h].w;
-          }
         }
+      if (do_nk) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          nk_f[h][0] += rr[0][h].x + rr[1][h].x;
+          nk_f[h][1] += rr[0][h].y + rr[1][h].y;
+          nk_f[h][2] += rr[0][h].z + rr[1][h].z;
+          nk_f[h][3] += rr[0][h].w + rr[1][h].w;
+        }
+      }
       // ---- Phi tile: [block (64 columns) 2 KB][k group][8][128 B] ----
 #pragma unroll
       for (int j = 0; j < 2; ++j)
@@ -296,7 +341,6 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&sm.full[s]);
-      row0 += kConvGroups * kStageRows;
       if (it + kConvGroups < n_iters) load_all();
       if (do_nk && ++since_flush == 16) {      // fp32 over 32 rows, then float64 in shared memory
         since_flush = 0;
@@ -358,7 +402,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
   } else {
     // ---------------- MMA issuer ----------------
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc(128, static_cast<uint32_t>(tile_blocks * 64), /*bf16*/ 1, 1, 1);
+      const uint32_t idesc = ptx::make_idesc(128, kTileCols, /*bf16*/ 1, 1, 1);
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % kStages;
         const int interval = it / kFlushIters;
@@ -488,7 +532,9 @@ int launch_weighted_pairs(const float* x, const float* r, int64_t n, int d, int 
     BB_CUDA_OK(cudaFuncSetAttribute(weighted_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
-  weighted_pairs_kernel<<<p.grid, kThreads, smem_bytes, stream>>>(x, r, n, p.g, p.n_splits, partial, partial_nk);
+  static const int prefetch_iters = getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) : 0;
+  weighted_pairs_kernel<<<p.grid, kThreads, smem_bytes, stream>>>(x, r, n, p.g, p.n_splits, prefetch_iters, partial,
+                                                                  partial_nk);
   BB_CHECK_LAUNCH("weighted_pairs_kernel");
   const int64_t total = static_cast<int64_t>(k) * d * d + static_cast<int64_t>(k) * d + k;
   weighted_pairs_finalize_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(

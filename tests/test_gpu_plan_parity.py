@@ -122,3 +122,46 @@ def test_logsoftmax_expression_is_stabilised():
     from scipy.special import log_softmax
     got = expr.compile()(Lg=logits)     # the unfused float32 spelling overflows to -inf here
     np.testing.assert_allclose(got, log_softmax(logits.astype('f8'), axis=1), rtol=RTOL, atol=ATOL)
+
+
+# ---- large contractions of compiled plans land on the tcgen05 projection / Gram kernels ---------
+
+def _scale_close(got, want, left_norms, right_norms, tol=3e-5):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    assert np.all(np.abs(got - want) <= RTOL * np.abs(want) + tol * np.outer(left_norms, right_norms))
+
+
+def test_compiled_dot_x_wt_runs_on_the_row_projection_kernel():
+    rng = np.random.RandomState(21)
+    Xh = (rng.randn(8192, 128) * 1.2 + 0.1).astype(np.float32)
+    Wh = (rng.randn(64, 128) / 11.0).astype(np.float32)
+    X, W, V = A.var('X', 2), A.var('W', 2), A.var('V', 2)
+    want = Xh.astype(np.float64) @ Wh.astype(np.float64).T
+    norms = (np.linalg.norm(Xh.astype(np.float64), axis=1), np.linalg.norm(Wh.astype(np.float64), axis=1))
+    fn = A.dot(X, W.T).compile()                       # plan: _tensordot(X, _dimshuffle(W,1,0), [1],[0])
+    _scale_close(fn(X=Xh, W=Wh), want, *norms)
+    assert fn.plan.last_launches <= 3                  # split W, projection (not the split-K SIMT GEMM + reduce)
+    fn2 = A.dot(X, V).compile()                        # W given as (features, q): transposed copy first
+    _scale_close(fn2(X=Xh, V=np.ascontiguousarray(Wh.T)), want, *norms)
+
+
+def test_compiled_dot_xt_r_runs_on_the_column_projection_kernel():
+    rng = np.random.RandomState(22)
+    Xh = (rng.randn(8192, 256) * 1.2 + 0.1).astype(np.float32)
+    Rh = rng.randn(8192, 64).astype(np.float32)
+    X, R = A.var('X', 2), A.var('R', 2)
+    fn = A.dot(X.T, R).compile()                       # plan: _tensordot(_dimshuffle(X,1,0), R, [1],[0])
+    want = Xh.astype(np.float64).T @ Rh.astype(np.float64)
+    _scale_close(fn(X=Xh, R=Rh), want, np.linalg.norm(Xh.astype(np.float64), axis=0),
+                 np.linalg.norm(Rh.astype(np.float64), axis=0))
+
+
+def test_compiled_syrk_large_d_runs_on_the_cta_pair_kernel():
+    rng = np.random.RandomState(23)
+    Xh = (rng.randn(5000, 256) * 1.2 + 0.1).astype(np.float32)
+    X = A.var('X', 2)
+    fn = A.dot(X.T, X).compile()
+    want = Xh.astype(np.float64).T @ Xh.astype(np.float64)
+    nrm = np.linalg.norm(Xh.astype(np.float64), axis=0)
+    _scale_close(fn(X=Xh), want, nrm, nrm)
