@@ -365,3 +365,66 @@ def test_mixture_logits(n, d, k):
 def _spd_np(rng, d):
     a = rng.randn(d, d)
     return a @ a.T / d + np.eye(d)
+
+
+# ---- full-size property checks for the tensor-pipe configs (too large for the CPU oracle) ------
+
+def test_full_size_cfg5_properties():
+    """BASELINE cfg5 extents (minibatch 4 Mi, D = 512, S = 64): the fused pass against float64
+    device arithmetic on the same data, in slabs."""
+    import torch
+    n, d, s = 1 << 22, 512, 64
+    g = torch.Generator(device='cuda').manual_seed(99)
+    X = torch.randn(n, d, device='cuda', generator=g)
+    W = torch.randn(s, d, device='cuda', generator=g) / d ** 0.5
+    y = (torch.rand(n, device='cuda', generator=g) < torch.sigmoid(X @ W[0])).float()
+    loglik, G = S.logistic_reparam_stats(X, y, W)
+    ll_ref = torch.zeros(s, dtype=torch.float64, device='cuda')
+    G_ref = torch.zeros(d, s, dtype=torch.float64, device='cuda')
+    Wd = W.double()
+    for lo in range(0, n, 1 << 18):
+        Xd, yd = X[lo:lo + (1 << 18)].double(), y[lo:lo + (1 << 18)].double()[:, None]
+        Z = Xd @ Wd.T
+        ll_ref += (yd * Z - torch.nn.functional.softplus(Z)).sum(0)
+        G_ref += Xd.T @ (yd - torch.sigmoid(Z))
+    assert float(((loglik - ll_ref).abs() / ll_ref.abs()).max()) <= 1e-5
+    # G entries are sums of 4 Mi zero-mean-ish terms: scale by |x_d| |resid_s| ~ sqrt(n) * sqrt(n)/2
+    assert float((G - G_ref).abs().max()) <= 3e-5 * n ** 0.5 * (n ** 0.5) * 0.5
+    assert float((G - G_ref).abs().max() / G_ref.abs().max()) <= 1e-4
+
+
+def test_large_cfg3_properties():
+    """cfg3 extents (K = 256, D = 64) at 2 Mi rows: responsibilities from the tcgen05 logits
+    kernel sum to one, the weighted statistics summed over components reproduce the plain
+    Gaussian statistics of the same data, and a random subset of logit rows matches float64."""
+    import torch
+    n, d, k = 1 << 21, 64, 256
+    g = torch.Generator(device='cuda').manual_seed(5)
+    centers = torch.randn(k, d, device='cuda', generator=g) * 2
+    X = centers[torch.randint(k, (n,), device='cuda', generator=g)] + torch.randn(n, d, device='cuda', generator=g)
+    U = (torch.eye(d, device='cuda') + 0.05 * torch.randn(k, d, d, device='cuda', generator=g).triu()).contiguous()
+    t = torch.einsum('kji,ki->kj', U, centers).contiguous()
+    c = torch.randn(k, device='cuda', generator=g)
+    logits, lse, total = S.mixture_logits(X, U, t, c)
+    rows = torch.randint(n, (4096,), device='cuda', generator=g)
+    z = torch.einsum('kji,ni->nkj', U.double(), X[rows].double()) - t.double()[None]
+    want = c.double()[None] - 0.5 * (z * z).sum(-1)
+    # logits are O(-300) here: rtol 1e-4 (north-star) plus a small absolute term
+    assert bool(((logits[rows].double() - want).abs() <= 1e-4 * want.abs() + 1e-3).all())
+    want_lse = torch.logsumexp(want, 1)
+    assert bool(((lse[rows].double() - want_lse).abs() <= 1e-4 * want_lse.abs() + 1e-3).all())
+    assert abs(float(total) - float(lse.double().sum())) <= 1e-6 * abs(float(total))
+    R = torch.exp(logits - lse[:, None])
+    assert float((R.sum(1) - 1).abs().max()) <= 1e-4
+    nk, rx, rxx = S.weighted_suffstats(X, R)
+    _, s1, s2 = S.gaussian_suffstats(X)
+    rowsum = R.double().sum(1)
+    assert abs(float(nk.sum()) - float(rowsum.sum())) <= 1e-6 * n
+    Xw = X.double() * rowsum[:, None]
+    ref2 = torch.zeros(d, d, dtype=torch.float64, device='cuda')
+    for lo in range(0, n, 1 << 19):
+        ref2 += Xw[lo:lo + (1 << 19)].T @ X[lo:lo + (1 << 19)].double()
+    np.testing.assert_allclose(rxx.sum(0).cpu().numpy(), ref2.cpu().numpy(), rtol=5e-5,
+                               atol=3e-5 * float(s2.abs().max()))
+    np.testing.assert_allclose(rx.sum(0).cpu().numpy(), Xw.sum(0).cpu().numpy(), rtol=5e-5,
+                               atol=3e-5 * float(s1.abs().max()))
