@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -324,8 +325,11 @@ BB_API int bb_colproj(const float* X, const float* R, int64_t n, int32_t d, int3
 }
 
 BB_API int64_t bb_logistic_reparam_workspace(int64_t n, int32_t d, int32_t s) {
-  return align_up(n * static_cast<int64_t>(s) * 4, 256) +
-         std::max(rowproj_tc_workspace(n, d, s), colproj_tc_workspace(n, d, s)) + 512;
+  int64_t need = align_up(n * static_cast<int64_t>(s) * 4, 256) +
+                 std::max(rowproj_tc_workspace(n, d, s), colproj_tc_workspace(n, d, s)) + 512;
+  if (s == 64 && d >= 128 && d % 128 == 0 && d <= 512 && n > 0)
+    need = std::max(need, logistic_fused_workspace(n, d, s) + 512);
+  return need;
 }
 
 BB_API int bb_logistic_reparam_pass(const float* X, const float* y, const float* W, int64_t n, int32_t d, int32_t s,
@@ -349,6 +353,10 @@ BB_API int bb_logistic_reparam_pass(const float* X, const float* y, const float*
               static_cast<long long>(bb_logistic_reparam_workspace(n, d, s)));
     return BB_ERR_WORKSPACE;
   }
+  // single-kernel path (X read from HBM once); BB_LOGISTIC_UNFUSED=1 keeps the two-kernel path
+  static const bool unfused = getenv("BB_LOGISTIC_UNFUSED") != nullptr;
+  if (!unfused && logistic_fused_supported(n, d, s, X))
+    return launch_logistic_fused(X, y, W, n, d, s, loglik, G, workspace, workspace_bytes, st);
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
   float* resid = reinterpret_cast<float*>(ws);
   ws += align_up(n * static_cast<int64_t>(s) * 4, 256);

@@ -47,6 +47,12 @@ int64_t colproj_tc_workspace(int64_t n, int d, int q);
 int launch_colproj_tc(const float* x, const float* r, int64_t n, int d, int q, double* out, void* workspace,
                       int64_t workspace_bytes, cudaStream_t stream);
 
+// logistic_fused_sm100.cu: the whole reparameterised logistic pass in one kernel (X read once)
+bool logistic_fused_supported(int64_t n, int d, int s, const void* x);
+int64_t logistic_fused_workspace(int64_t n, int d, int s);
+int launch_logistic_fused(const float* x, const float* y, const float* w, int64_t n, int d, int s, double* loglik,
+                          double* g, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+
 // mixture_logits_sm100.cu: logit[n,k] = c_k - 1/2 |U_k x_n - t_k|^2 (+ row log-sum-exp) on tcgen05
 bool mixture_logits_supported(int64_t n, int d, int k, const void* x);
 int64_t mixture_logits_workspace(int64_t n, int d, int k);

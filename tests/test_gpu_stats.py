@@ -428,3 +428,23 @@ def test_large_cfg3_properties():
                                atol=3e-5 * float(s2.abs().max()))
     np.testing.assert_allclose(rx.sum(0).cpu().numpy(), Xw.sum(0).cpu().numpy(), rtol=5e-5,
                                atol=3e-5 * float(s1.abs().max()))
+
+
+@pytest.mark.parametrize('n,d,s', [(1, 128, 64), (100, 128, 64), (129, 256, 64), (2049, 384, 64), (6000, 512, 64),
+                                   (40000, 512, 64), (3000, 128, 128)])
+def test_logistic_reparam_stats(n, d, s):
+    """Fused logistic pass (single-kernel path when S = 64, D % 128 == 0, D <= 512; the two-kernel
+    path otherwise) vs float64: loglik[s] and G[d, s]."""
+    import torch
+    rng = np.random.RandomState(n + d + s)
+    X = rng.randn(n, d).astype(np.float32)
+    W = (rng.randn(s, d) / np.sqrt(d)).astype(np.float32)
+    y = (rng.rand(n) < 1 / (1 + np.exp(-X @ W[0]))).astype(np.float32)
+    ll, G = S.logistic_reparam_stats(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(W).cuda())
+    Z = X.astype(np.float64) @ W.astype(np.float64).T
+    want_ll = (y[:, None] * Z - np.logaddexp(0.0, Z)).sum(0)
+    resid = y[:, None] - 1.0 / (1.0 + np.exp(-Z))
+    want_G = X.astype(np.float64).T @ resid
+    np.testing.assert_allclose(ll.cpu().numpy(), want_ll, rtol=1e-4, atol=1e-5)
+    scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(resid, axis=0)[None, :]
+    assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 3e-5 * scale + 1e-12)
