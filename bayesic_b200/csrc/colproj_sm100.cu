@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -104,7 +105,7 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
 // [k group (row >> 3) 1 KB][row & 7 -> 128 B][16-byte chunk ^ (row & 7)].
 template <int kNSeg, int kNQ>
 __global__ void __launch_bounds__(kThreads, 1)
-colproj_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t n, int n_stages,
+colproj_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t n, int n_stages, int prefetch_iters,
                float* __restrict__ partial) {         // [cta][kNSeg][Q cols][128 rows] fp32
   constexpr int kD = kNSeg * 128, kQ = kNQ * 64;
   constexpr int kXPart = kD * 32, kRPart = kQ * 32;             // bytes per bf16 part per stage
@@ -181,6 +182,23 @@ colproj_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t
 #pragma unroll
         for (int qs = 0; qs < kNQ; ++qs)
           rr[qs] = (row0 + (lane >> 4) < n) ? ldg_f4(pr + qs * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // L2 prefetch hints a few stages ahead: the register-resident loads above can keep only
+      // ~64 KB per SM in flight, which covers the L2 latency but not the HBM latency
+      if (prefetch_iters > 0) {
+        const int64_t prow = row0 + static_cast<int64_t>(prefetch_iters) * kConvGroups * kStageRows;   // this warp's 2 rows, later
+        constexpr int kXLines = kD * 4 / 128;                  // 128-byte lines per row of X
+        const int64_t row_limit = (it_end < total_iters ? it_end * kStageRows : n);
+        if (lane < 2 * kXLines) {
+          const int64_t pr_row = prow + lane / kXLines;
+          if (pr_row < row_limit) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + pr_row * kD + (lane % kXLines) * 32));
+        }
+        constexpr int kRLines = kQ * 4 / 128;
+        if (lane >= 32 - 2 * kRLines) {
+          const int l2 = lane - (32 - 2 * kRLines);
+          const int64_t pr_row = prow + l2 / kRLines;
+          if (pr_row < row_limit) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + pr_row * kQ + (l2 % kRLines) * 32));
+        }
       }
       row0 += kConvGroups * kStageRows;
       px += static_cast<int64_t>(kConvGroups) * kStageRows * kD;
@@ -320,7 +338,9 @@ int launch_instance(const float* x, const float* r, int64_t n, const ColProjPlan
     BB_CUDA_OK(cudaFuncSetAttribute(colproj_kernel<kNSeg, kNQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 4096));
     attr_set = true;
   }
-  colproj_kernel<kNSeg, kNQ><<<p.grid, kThreads, p.smem_bytes, stream>>>(x, r, n, p.n_stages, partial);
+  // measured on B200 (cfg5): 0 -> 1.674 ms, 2 -> 1.575 ms, 4 -> 1.595 ms, 8 -> 2.08 ms
+  static const int prefetch_iters = getenv("BB_COLPROJ_PREFETCH") ? atoi(getenv("BB_COLPROJ_PREFETCH")) : 2;
+  colproj_kernel<kNSeg, kNQ><<<p.grid, kThreads, p.smem_bytes, stream>>>(x, r, n, p.n_stages, prefetch_iters, partial);
   BB_CHECK_LAUNCH("colproj_kernel");
   return BB_OK;
 }

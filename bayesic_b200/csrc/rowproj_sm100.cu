@@ -32,6 +32,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -141,6 +142,7 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&e)[32], int lane) 
 }
 
 struct RowProjParams {
+  int prefetch_iters;               // L2 prefetch distance in converter iterations (0 = off)
   const float* x;
   const __nv_bfloat16* wsplit;      // [2][q][d]
   const float* y;                   // logistic epilogue: labels [n]
@@ -230,9 +232,20 @@ __global__ void __launch_bounds__(kThreads, 1) rowproj_kernel(const RowProjParam
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // L2 prefetch hint for the chunk this group converts `prefetch_iters` iterations from now: the
+    // register-resident loads keep only ~64 KB per SM in flight, which covers the L2 latency but
+    // not the HBM latency.  16 rows x 2 lines of 128 B per warp = one line per lane.
+    auto prefetch = [&](int64_t it) {
+      if (it >= n_iters) return;
+      const int64_t tile = blockIdx.x + (it / kc_count) * gridDim.x;
+      const int kc = static_cast<int>(it % kc_count);
+      const int64_t row = tile * kTileRows + wi * 16 + (lane >> 1);
+      if (row < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + row * d + kc * kChunk + (lane & 1) * 32));
+    };
     if (group < n_iters) load(group);
     for (int64_t it = group; it < n_iters; it += kConvGroups) {
       const int s = static_cast<int>(it % kStages);
+      if (p.prefetch_iters > 0) prefetch(it + static_cast<int64_t>(p.prefetch_iters + 1) * kConvGroups);
       ptx::mbar_wait(&sm.empty[s], (static_cast<uint32_t>(it / kStages) & 1) ^ 1);
       const uint32_t stage_addr = stage0 + s * kStageBytes;
 #pragma unroll
@@ -400,7 +413,9 @@ int launch_rowproj_tc(const float* x, const float* w, const float* y, int64_t n,
   const int64_t count = static_cast<int64_t>(q) * d;
   split_w_kernel<<<static_cast<int>((count + 255) / 256), 256, 0, stream>>>(w, count, wsplit);
   BB_CHECK_LAUNCH("split_w_kernel");
+  static const int prefetch_iters = getenv("BB_ROWPROJ_PREFETCH") ? atoi(getenv("BB_ROWPROJ_PREFETCH")) : 2;
   RowProjParams p;
+  p.prefetch_iters = prefetch_iters;
   p.x = x; p.wsplit = wsplit; p.y = y; p.out = out; p.partial_colsum = partial; p.n = n; p.d = d; p.q = q;
   const int grid = rowproj_grid(n);
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
