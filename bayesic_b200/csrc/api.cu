@@ -411,4 +411,18 @@ BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int3
                                     static_cast<cudaStream_t>(stream));
 }
 
+BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits, const float* lse, int64_t n,
+                                      int32_t d, int32_t k, double* Nk, double* sum_rx, double* sum_rxx,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n < 0 || !sum_rxx || (n > 0 && (!X || !logits || !lse))) { set_error("suffstats_weighted_from_logits: bad arguments"); return BB_ERR_INVALID; }
+  if (n == 0) {
+    BB_CUDA_OK(cudaMemsetAsync(sum_rxx, 0, sizeof(double) * k * d * d, st));
+    if (sum_rx) BB_CUDA_OK(cudaMemsetAsync(sum_rx, 0, sizeof(double) * k * d, st));
+    if (Nk) BB_CUDA_OK(cudaMemsetAsync(Nk, 0, sizeof(double) * k, st));
+    return BB_OK;
+  }
+  return launch_weighted_pairs(X, logits, lse, n, d, k, Nk, sum_rx, sum_rxx, workspace, workspace_bytes, st);
+}
+
 }  // extern "C"

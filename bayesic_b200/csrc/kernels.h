@@ -77,8 +77,9 @@ int launch_weighted_stats_tc(const float* x, const float* r, int64_t n, int d, i
 // weighted_pairs_sm100.cu: the same statistics as R^T . (X (x) X) on BF16 tcgen05 (d % 8 == 0, k <= 256)
 bool weighted_pairs_supported(int64_t n, int d, int k, const void* x, const void* r);
 int64_t weighted_pairs_workspace(int64_t n, int d, int k);
-int launch_weighted_pairs(const float* x, const float* r, int64_t n, int d, int k, double* nk, double* sum_rx,
-                          double* sum_rxx, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int launch_weighted_pairs(const float* x, const float* r, const float* lse, int64_t n, int d, int k, double* nk,
+                          double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t stream);
 // tcgen05 kernel when the shape allows it (and BB_WEIGHTED_SIMT is unset), SIMT kernel otherwise
 int64_t weighted_stats_auto_workspace(int64_t n, int d, int k);
 int launch_weighted_stats_auto(const float* x, const float* r, int64_t n, int d, int k, double* nk,

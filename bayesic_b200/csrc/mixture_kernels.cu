@@ -344,7 +344,7 @@ int launch_weighted_stats_auto(const float* x, const float* r, int64_t n, int d,
   // R^T . (X (x) X) grouping on BF16 tcgen05 (weighted_pairs_sm100.cu): tensor-pipe bound
   if (!force_simt && !no_pairs && n >= 1024 && weighted_pairs_supported(n, d, k, x, r) && workspace != nullptr &&
       workspace_bytes >= weighted_pairs_workspace(n, d, k))
-    return launch_weighted_pairs(x, r, n, d, k, nk, sum_rx, sum_rxx, workspace, workspace_bytes, stream);
+    return launch_weighted_pairs(x, r, nullptr, n, d, k, nk, sum_rx, sum_rxx, workspace, workspace_bytes, stream);
   // the tensor-core kernel pays off once there are enough rows to amortise its per-CTA setup
   if (!force_simt && n >= 1024 && weighted_tc_supported(n, d, k, x, r) && workspace != nullptr &&
       workspace_bytes >= weighted_tc_workspace(n, k))

@@ -142,8 +142,8 @@ __device__ __forceinline__ void pair_of(int b, int n_groups, int* ga, int* gb) {
 // The blocks are spread evenly over the tiles (3 or 4 each at D = 64): every CTA converts the same
 // R rows whatever its column count, so equal row ranges keep the CTAs in step.
 __global__ void __launch_bounds__(kThreads, 1)
-weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t n, Geometry g,
-                      int n_splits, int prefetch_iters,
+weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ lse,
+                      int64_t n, Geometry g, int n_splits, int prefetch_iters,
                       float* __restrict__ partial,        // [cta][2 m-blocks][256 cols][128 lanes]
                       double* __restrict__ partial_nk) {  // [split of tile 0][k]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -243,6 +243,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     const int64_t r_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.k;
     const int64_t x_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.d;
     float4 rr[2][2];
+    float row_lse[2] = {0.f, 0.f};   // logits mode (lse != nullptr): r = exp(logit - lse[row])
     float xa[2][2];          // [row][block slot]: the left factor of the pair product
     float4 xb[2][2];         // the four right factors
     float nk_f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -257,6 +258,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
         for (int j = 0; j < 2; ++j) {
           rr[j][0] = ldg_f4(rp + j * g.k + kc0);
           rr[j][1] = ldg_f4(rp + j * g.k + kc1);
+          if (lse != nullptr) row_lse[j] = __ldg(lse + row0 + j);
 #pragma unroll
           for (int t2 = 0; t2 < 2; ++t2) {
             xa[j][t2] = __ldg(xp + j * g.d + src_a[t2]);
@@ -270,6 +272,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
           const int64_t back = ok ? 0 : (row0 + j) - (n - 1);     // rows to step back to stay in range
           rr[j][0] = ldg_f4(rp + (j - back) * g.k + kc0);
           rr[j][1] = ldg_f4(rp + (j - back) * g.k + kc1);
+          if (lse != nullptr) row_lse[j] = __ldg(lse + row0 + j - back);
 #pragma unroll
           for (int t2 = 0; t2 < 2; ++t2) {
             xa[j][t2] = __ldg(xp + (j - back) * g.d + src_a[t2]);
@@ -295,6 +298,17 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       const int s = it % kStages;
       ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
       const uint32_t stage_addr = stage0 + s * kStageBytes;
+      if (lse != nullptr) {                               // responsibilities from logits, on the fly
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            rr[j][h].x = __expf(rr[j][h].x - row_lse[j]);
+            rr[j][h].y = __expf(rr[j][h].y - row_lse[j]);
+            rr[j][h].z = __expf(rr[j][h].z - row_lse[j]);
+            rr[j][h].w = __expf(rr[j][h].w - row_lse[j]);
+          }
+      }
       if (!rows_ok || k_partial) {                        // rare: zero what lies past n or past k
         const int64_t first = row0 - kConvGroups * kStageRows;   // row0 was advanced by load_all
 #pragma unroll
@@ -510,8 +524,10 @@ int64_t weighted_pairs_workspace(int64_t n, int d, int k) {
          static_cast<int64_t>(p.n_splits) * k * static_cast<int64_t>(sizeof(double)) + 1024;
 }
 
-int launch_weighted_pairs(const float* x, const float* r, int64_t n, int d, int k, double* nk, double* sum_rx,
-                          double* sum_rxx, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+// r: responsibilities [n, k]; or, with lse != nullptr, logits [n, k] and r = exp(logit - lse[row])
+int launch_weighted_pairs(const float* x, const float* r, const float* lse, int64_t n, int d, int k, double* nk,
+                          double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t stream) {
   if (!weighted_pairs_supported(n, d, k, x, r)) {
     set_error("weighted_pairs: unsupported shape n=%lld d=%d k=%d", static_cast<long long>(n), d, k);
     return BB_ERR_UNSUPPORTED;
@@ -533,7 +549,7 @@ int launch_weighted_pairs(const float* x, const float* r, int64_t n, int d, int 
     attr_set = true;
   }
   static const int prefetch_iters = getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) : 0;
-  weighted_pairs_kernel<<<p.grid, kThreads, smem_bytes, stream>>>(x, r, n, p.g, p.n_splits, prefetch_iters, partial,
+  weighted_pairs_kernel<<<p.grid, kThreads, smem_bytes, stream>>>(x, r, lse, n, p.g, p.n_splits, prefetch_iters, partial,
                                                                   partial_nk);
   BB_CHECK_LAUNCH("weighted_pairs_kernel");
   const int64_t total = static_cast<int64_t>(k) * d * d + static_cast<int64_t>(k) * d + k;

@@ -76,8 +76,16 @@ class GmmStep(object):
         c = ck.double() + 0.5 * (t * t).sum(1)
         return U.float().contiguous(), t.float().contiguous(), c.float().contiguous()
 
-    def __call__(self, X, Ak, bk, ck, fused=True):
+    def __call__(self, X, Ak, bk, ck, fused=True, want_log_resp=True):
         import torch
+        d, k = X.shape[1], Ak.shape[0]
+        if (fused and not want_log_resp and stats.mixture_logits_supported(d, k) and d % 8 == 0 and k <= 256
+                and X.shape[0] >= 1024):
+            # whole local step in two kernels: logits + row log-sum-exp, then the statistics with
+            # r = exp(logit - lse) formed inside the operand conversion (R is never written)
+            logits, lse, sum_lse = stats.mixture_logits(X, *self.whiten(Ak, bk, ck))
+            nk, rx, rxx = stats.weighted_suffstats_from_logits(X, logits, lse)
+            return {'logits': logits, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
         if fused and stats.mixture_logits_supported(X.shape[1], Ak.shape[0]):
             # same value as the einsum plan, as one tcgen05 projection with the quadratic form
             # consumed on chip (the plan route materialises N x K x D and cannot run at cfg3 size)

@@ -20,7 +20,7 @@ from .backend import library as L
 __all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'log_responsibilities',
            'weighted_suffstats', 'regression_suffstats', 'row_projection', 'column_projection',
            'logistic_reparam_stats', 'logistic_reparam_supported', 'mixture_logits',
-           'mixture_logits_supported', 'launch_count']
+           'mixture_logits_supported', 'weighted_suffstats_from_logits', 'launch_count']
 
 _scratch = {}
 
@@ -298,3 +298,28 @@ def mixture_logits(X, U, t, c, want_lse=True, want_sum=True):
                                       total.data_ptr() if want_sum else None, ws.data_ptr(), ws.numel(),
                                       _stream(dev)), 'bb_mixture_logits')
     return logits, lse, total
+
+
+def weighted_suffstats_from_logits(X, logits, lse):
+    """``(N_k, sum_rx, sum_rxx)`` with ``r[n, k] = exp(logits[n, k] - lse[n])`` formed on the fly
+    inside the statistics kernel (the responsibility matrix is never written)."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    logits = _as_device_f32(logits, 2, 'logits')
+    lse = _as_device_f32(lse, 1, 'lse')
+    n, d = X.shape
+    k = logits.shape[1]
+    if logits.shape[0] != n or lse.shape[0] != n:
+        raise ValueError("X, logits and lse disagree on the data axis")
+    dev = X.device
+    with torch.cuda.device(dev):
+        nk = torch.empty(k, dtype=torch.float64, device=dev)
+        rx = torch.empty((k, d), dtype=torch.float64, device=dev)
+        rxx = torch.empty((k, d, d), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.bb_suffstats_weighted_workspace(n, d, k), dev)
+        L.check(lib.bb_suffstats_weighted_from_logits(X.data_ptr(), logits.data_ptr(), lse.data_ptr(), n, d, k,
+                                                      nk.data_ptr(), rx.data_ptr(), rxx.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), _stream(dev)),
+                'bb_suffstats_weighted_from_logits')
+    return nk, rx, rxx

@@ -248,6 +248,16 @@ BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int3
                           double* Nk, double* sum_rx, double* sum_rxx,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Same statistics with the responsibilities formed on the fly from the logits and their row
+ * log-sum-exp (as bb_mixture_logits returns them): r[n,k] = exp(logits[n,k] - lse[n]) -- the
+ * N x K responsibility matrix is never written.  tcgen05 path only: d % 8 == 0, d <= 64,
+ * k % 4 == 0, k <= 256 (BB_ERR_UNSUPPORTED otherwise; normalise with bb_logsoftmax_rows and use
+ * bb_suffstats_weighted instead). */
+BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits, const float* lse,
+                                      int64_t n, int32_t d, int32_t k,
+                                      double* Nk, double* sum_rx, double* sum_rxx,
+                                      void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,3 +176,30 @@ def test_cfg3_gmm_vmp_step_on_the_tensor_core_kernels():
         _close(got['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
         _close(got['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
         assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
+
+
+def test_cfg3_gmm_vmp_step_without_materialising_responsibilities():
+    """want_log_resp=False: logits + lse from the tcgen05 logits kernel, responsibilities formed
+    inside the statistics kernel; same statistics as the oracle's full step."""
+    import torch
+    rng = np.random.RandomState(8)
+    n, d, k = 5000, 64, 12
+    centers = rng.randn(k, d) * 1.5
+    X = (centers[rng.randint(k, size=n)] + rng.randn(n, d)).astype(np.float32)
+    log_pi = np.log(rng.dirichlet(np.ones(k)))
+    m = centers + rng.randn(k, d) * 0.05
+    beta = rng.rand(k) * 5 + 1
+    nu = d + 2 + rng.rand(k) * 5
+    W = np.stack([np.linalg.inv(_spd(rng, d)) / nu[j] for j in range(k)])
+    want = O.gmm_vmp_step(X, log_pi, m, beta, W, nu)
+    step = P.GmmStep()
+    Ak, bk, ck = step.expectations(log_pi, m, beta, W, nu)
+    got = step(torch.from_numpy(X).cuda(), torch.from_numpy(Ak).cuda(), torch.from_numpy(bk).cuda(),
+               torch.from_numpy(ck).cuda(), want_log_resp=False)
+    assert 'log_resp' not in got
+    log_resp = (got['logits'] - got['lse'][:, None]).cpu().numpy()
+    np.testing.assert_allclose(log_resp, want['log_resp'], rtol=1e-4, atol=3e-3)
+    _close(got['nk'], want['nk'], rtol=1e-4, scale_atol=2e-5)
+    _close(got['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
+    _close(got['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
+    assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
