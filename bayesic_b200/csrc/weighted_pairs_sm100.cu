@@ -141,6 +141,7 @@ __device__ __forceinline__ void pair_of(int b, int n_groups, int* ga, int* gb) {
 // grid = n_tiles * n_splits: CTA -> (tile = blockIdx / n_splits, row range = blockIdx % n_splits).
 // The blocks are spread evenly over the tiles (3 or 4 each at D = 64): every CTA converts the same
 // R rows whatever its column count, so equal row ranges keep the CTAs in step.
+template <bool kFromLogits>      // r holds logits and the weights are exp(logit - lse[row])
 __global__ void __launch_bounds__(kThreads, 1)
 weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ lse,
                       int64_t n, Geometry g, int n_splits, int prefetch_iters,
@@ -258,7 +259,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
         for (int j = 0; j < 2; ++j) {
           rr[j][0] = ldg_f4(rp + j * g.k + kc0);
           rr[j][1] = ldg_f4(rp + j * g.k + kc1);
-          if (lse != nullptr) row_lse[j] = __ldg(lse + row0 + j);
+          if (kFromLogits) row_lse[j] = __ldg(lse + row0 + j);
 #pragma unroll
           for (int t2 = 0; t2 < 2; ++t2) {
             xa[j][t2] = __ldg(xp + j * g.d + src_a[t2]);
@@ -272,7 +273,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
           const int64_t back = ok ? 0 : (row0 + j) - (n - 1);     // rows to step back to stay in range
           rr[j][0] = ldg_f4(rp + (j - back) * g.k + kc0);
           rr[j][1] = ldg_f4(rp + (j - back) * g.k + kc1);
-          if (lse != nullptr) row_lse[j] = __ldg(lse + row0 + j - back);
+          if (kFromLogits) row_lse[j] = __ldg(lse + row0 + j - back);
 #pragma unroll
           for (int t2 = 0; t2 < 2; ++t2) {
             xa[j][t2] = __ldg(xp + (j - back) * g.d + src_a[t2]);
@@ -298,7 +299,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       const int s = it % kStages;
       ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
       const uint32_t stage_addr = stage0 + s * kStageBytes;
-      if (lse != nullptr) {                               // responsibilities from logits, on the fly
+      if (kFromLogits) {                                  // responsibilities from logits, on the fly
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -545,12 +546,17 @@ int launch_weighted_pairs(const float* x, const float* r, const float* lse, int6
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
   static bool attr_set = false;
   if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(weighted_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    BB_CUDA_OK(cudaFuncSetAttribute(weighted_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    BB_CUDA_OK(cudaFuncSetAttribute(weighted_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   static const int prefetch_iters = getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) : 0;
-  weighted_pairs_kernel<<<p.grid, kThreads, smem_bytes, stream>>>(x, r, lse, n, p.g, p.n_splits, prefetch_iters, partial,
-                                                                  partial_nk);
+  if (lse != nullptr)
+    weighted_pairs_kernel<true><<<p.grid, kThreads, smem_bytes, stream>>>(x, r, lse, n, p.g, p.n_splits, prefetch_iters,
+                                                                          partial, partial_nk);
+  else
+    weighted_pairs_kernel<false><<<p.grid, kThreads, smem_bytes, stream>>>(x, r, lse, n, p.g, p.n_splits, prefetch_iters,
+                                                                           partial, partial_nk);
   BB_CHECK_LAUNCH("weighted_pairs_kernel");
   const int64_t total = static_cast<int64_t>(k) * d * d + static_cast<int64_t>(k) * d + k;
   weighted_pairs_finalize_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
