@@ -188,9 +188,10 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
 
 
 struct ConvArgs {
+  int prefetch_iters;      // L2 prefetch distance in converter iterations (0 = off)
   const float* x;
   const float* y;
-  int64_t n, row_begin;
+  int64_t n, row_begin, row_end;
   int d, feat_a, feat_b, n_iters, warp, lane;
   bool want_yty;
 };
@@ -247,6 +248,15 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
         ra[j] = ok ? ldg_f4(pa + j * d) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (!kAlias) rb[j] = ok ? ldg_f4(pb + j * d) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (kXty) ry[j] = ok ? __ldg(py + j) : 0.f;
+      }
+    }
+    // L2 prefetch hint for the rows this warp converts `prefetch_iters` iterations from now:
+    // 4 rows x (4 lines of A + 4 lines of B) = one 128-byte line per lane
+    if (ca.prefetch_iters > 0) {
+      const int64_t prow = row0 + static_cast<int64_t>(ca.prefetch_iters) * kConvGroups * kStageRows + (lane >> 3);
+      if (prow < ca.row_end && (!kAlias || (lane & 4) == 0)) {
+        const float* base = (lane & 4) ? ca.x + prow * d + ca.feat_b : ca.x + prow * d + ca.feat_a;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (lane & 3) * 32));
       }
     }
     row0 += kConvGroups * kStageRows;
@@ -373,6 +383,8 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
   if (warp < kConvWarps) {
     // ---------------- converter warps: global fp32 -> registers -> bf16 b1/b2 tiles ----------------
     ConvArgs ca;
+    ca.prefetch_iters = ablate >> 8;
+    ca.row_end = it_end * kStageRows < n ? it_end * kStageRows : n;
     ca.x = x; ca.y = y; ca.n = n; ca.d = d; ca.feat_a = feat_a; ca.feat_b = feat_b;
     ca.row_begin = row_begin; ca.n_iters = n_iters; ca.warp = warp; ca.lane = lane;
     ca.want_yty = blk == 0 && rank == 0;
@@ -557,7 +569,8 @@ int launch_gram_tc(const float* x, const float* y, int64_t n, int d, double* xtx
   }
   const int grid = static_cast<int>(2 * pairs);
   // developer ablation switches (timing experiments only; results are wrong when set)
-  static const int ablate = getenv("BB_GRAM_ABLATE") ? atoi(getenv("BB_GRAM_ABLATE")) : 0;
+  static const int ablate = (getenv("BB_GRAM_ABLATE") ? atoi(getenv("BB_GRAM_ABLATE")) : 0) |
+                            ((getenv("BB_GRAM_PREFETCH") ? atoi(getenv("BB_GRAM_PREFETCH")) : 0) << 8);
   gram_pair_kernel<<<grid, kThreads, smem_bytes, stream>>>(x, y, n, d, g.n_blocks, g.n_splits, ablate, partial,
                                                            partial_xty, partial_yty);
   BB_CHECK_LAUNCH("gram_pair_kernel");
