@@ -206,12 +206,32 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
     const int q = warp & 3, h = warp >> 2;
     double sum_lse = 0.0;
     int64_t gi = 0;
+    float tl_next[4], c_next[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(p.tprep + static_cast<int64_t>(h * 2 + (i >> 1)) * 64 + (i & 1) * 32 + lane);
+    c_next[0] = __ldg(p.c + h * 2);
+    c_next[1] = __ldg(p.c + h * 2 + 1);
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int64_t tile = blockIdx.x + t * gridDim.x;
       const int64_t row = tile * kTileRows + q * 32 + lane;
       const bool valid = row < p.n;
       float run_m = -INFINITY, run_s = 0.f;
       for (int g = 0; g < n_groups; ++g, ++gi) {
+        // this group's t and c values were fetched one group ahead (a load issued right before its
+        // use stalled the epilogue on the L2 latency four times per group -- the top stall in ncu)
+        float tl[4], cc[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tl[i] = tl_next[i];
+        cc[0] = c_next[0];
+        cc[1] = c_next[1];
+        {
+          const int gn = (g + 1 == n_groups) ? 0 : g + 1;
+          const int comp0 = gn * kGroupComps + h * 2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(p.tprep + static_cast<int64_t>(comp0 + (i >> 1)) * 64 + (i & 1) * 32 + lane);
+          c_next[0] = __ldg(p.c + comp0);
+          c_next[1] = __ldg(p.c + comp0 + 1);
+        }
         const int ab = static_cast<int>(gi & 1);
         ptx::mbar_wait(&sm.acc_full[ab], static_cast<uint32_t>(gi >> 1) & 1);
         ptx::tc_fence_after_sync();
@@ -219,21 +239,20 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
         float logit[2];
 #pragma unroll
         for (int cidx = 0; cidx < 2; ++cidx) {
-          const int comp = g * kGroupComps + h * 2 + cidx;
           float acc = 0.f;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(t_addr + cidx * 64 + half * 32, v);
-            const float tl = __ldg(p.tprep + static_cast<int64_t>(comp) * 64 + half * 32 + lane);
+            const float tv = tl[cidx * 2 + half];
             ptx::tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float dz = __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, tl, j);
+              const float dz = __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, tv, j);
               acc = fmaf(dz, dz, acc);
             }
           }
-          logit[cidx] = fmaf(-0.5f, acc, __ldg(p.c + comp));
+          logit[cidx] = fmaf(-0.5f, acc, cc[cidx]);
         }
         ptx::tc_fence_before_sync();
         __syncwarp();

@@ -1,1 +1,3 @@
-for h in 0 1 2 4 8; do echo "gram prefetch $h"; BB_GRAM_PREFETCH=$h timeout 100 python tests/gpu_profile_driver.py gram; done
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_stats.py -q -x -m gpu -k "mixture_logits or large_cfg3" > gpurun_out/pytest_w.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_w.log
+timeout 100 python tests/gpu_profile_driver.py logits
