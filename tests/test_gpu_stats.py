@@ -448,3 +448,56 @@ def test_logistic_reparam_stats(n, d, s):
     np.testing.assert_allclose(ll.cpu().numpy(), want_ll, rtol=1e-4, atol=1e-5)
     scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(resid, axis=0)[None, :]
     assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 3e-5 * scale + 1e-12)
+
+
+# ---- error behaviour of the C-ABI entry points (status codes -> exceptions) ----
+
+def test_entry_points_reject_bad_arguments_and_small_workspaces():
+    import ctypes
+    import torch
+    from bayesic_b200.backend import library as L
+    lib = L.load()
+    X = torch.randn(2048, 256, device='cuda')
+    y = torch.randn(2048, device='cuda')
+    out = torch.empty(256 * 256 + 256 + 1, dtype=torch.float64, device='cuda')
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device='cuda')
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # y without xty / yty
+    st = lib.bb_suffstats_regression(X.data_ptr(), y.data_ptr(), 2048, 256, out.data_ptr(), None, None,
+                                     ws.data_ptr(), ws.numel(), stream)
+    assert st == 1 and b'go together' in lib.bb_last_error()               # BB_ERR_INVALID
+    with pytest.raises(ValueError):
+        L.check(st, 'bb_suffstats_regression')
+    # workspace too small
+    st = lib.bb_suffstats_regression(X.data_ptr(), None, 2048, 256, out.data_ptr(), None, None, ws.data_ptr(), 16, stream)
+    assert st == 5                                                         # BB_ERR_WORKSPACE
+    with pytest.raises(L.BackendError):
+        L.check(st, 'bb_suffstats_regression')
+    # shapes the tensor-core kernels do not serve are refused loudly, never computed elsewhere
+    W = torch.randn(64, 250, device='cuda')
+    Z = torch.empty(2048, 64, device='cuda')
+    st = lib.bb_rowproj(X.data_ptr(), W.data_ptr(), 2048, 250, 64, Z.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+    assert st == 3                                                         # BB_ERR_UNSUPPORTED
+    st = lib.bb_mixture_logits(X.data_ptr(), X.data_ptr(), X.data_ptr(), X.data_ptr(), 2048, 40, 8, Z.data_ptr(), None,
+                               None, ws.data_ptr(), ws.numel(), stream)
+    assert st == 3
+    st = lib.bb_logistic_reparam_pass(X.data_ptr(), y.data_ptr(), W.data_ptr(), 2048, 250, 64, out.data_ptr(),
+                                      out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+    assert st == 3
+    torch.cuda.synchronize()
+
+
+def test_mismatched_shapes_raise_before_any_launch():
+    import torch
+    X = torch.randn(100, 128, device='cuda')
+    with pytest.raises(ValueError):
+        S.regression_suffstats(X, torch.randn(99, device='cuda'))
+    with pytest.raises(ValueError):
+        S.row_projection(X, torch.randn(64, 64, device='cuda'))
+    with pytest.raises(ValueError):
+        S.column_projection(X, torch.randn(99, 64, device='cuda'))
+    with pytest.raises(ValueError):
+        S.mixture_logits(torch.randn(10, 64, device='cuda'), torch.randn(4, 64, 64, device='cuda'),
+                         torch.randn(4, 32, device='cuda'), torch.randn(4, device='cuda'))
+    with pytest.raises(TypeError):
+        S.regression_suffstats(np.zeros((4, 4), dtype=np.float32))         # host array: device passes only
