@@ -57,7 +57,6 @@ constexpr int kTmemCols = 512;
 
 struct __align__(1024) SmemLayout {
   uint8_t stage[kStages][kStageBytes];
-  double nk[kMaxK];
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t acc_full;
@@ -117,7 +116,9 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
 
 // Column blocks of 64: block b < n_pair is the feature-group pair (ga, gb), ga <= gb, enumerated
 // row-major over the upper triangle; column (i, j) -> x[8 ga + i] * x[8 gb + j].  Block n_pair is
-// the linear block: column c -> x[c] (c < d).
+// the linear block: column c -> x[c] (c < d).  Block n_pair + 1 is the ones block: column 0 -> 1
+// (its contraction with R is Nk; at D = 64 the 38 blocks fill 10 tiles of N = 256 that are
+// issued in full anyway, so Nk costs no extra MMA).
 struct Geometry {
   int d, k, n_groups, n_pair, n_blocks, n_tiles;
   int base, rem;      // tile t holds base + (t < rem) blocks, starting at block t * base + min(t, rem)
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ lse,
                       int64_t n, Geometry g, int n_splits, int prefetch_iters,
                       float* __restrict__ partial,        // [cta][2 m-blocks][256 cols][128 lanes]
-                      double* __restrict__ partial_nk) {  // [split of tile 0][k]
+                      double* __restrict__ /*unused*/) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -176,7 +177,6 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     __syncwarp();
     ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
   }
-  for (int i = threadIdx.x; i < kMaxK; i += kThreads) sm.nk[i] = 0.0;
   // Every tile issues N = 256 MMAs so that all CTAs of a row range run at the same pace and share
   // the R rows through L2; the unused blocks of a 3-block tile are never written and stay zero.
   for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads)
@@ -191,44 +191,51 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     // ---------------- converter warps ----------------
     // group = warp & 1 takes every 2nd stage; warp wi of the group owns rows 2 wi, 2 wi + 1.
     // R: lane l holds components [4 l + 128 h, +4), h = 0, 1, of both rows.
-    // Phi: item (row j, block bl, lane) -> 4 columns: 16 lanes per 64-column block row
-    //      (i = (lane & 15) >> 1, j0 = 4 (lane & 1)); lanes >= 16 take the odd block of a pair of blocks.
+    // Phi: item (row j, block slot t2, lane) -> 4 columns: 16 lanes per 64-column block row
+    //      (i = (lane & 15) >> 1, j0 = 4 (lane & 1)); lanes >= 16 take the odd block of a pair.
+    // The SM's issue slots are the budget here (the first version spent ~2 300 warp instructions
+    // per stage against ~3 000 slots in the stage's MMA time), so: every per-lane quantity is
+    // hoisted, the products are formed as (x_a m_a + c_a) * x_b so that pair / linear / ones /
+    // padding columns share one code path, and the ragged tail is a separate (cold) path.
     const int group = warp & (kConvGroups - 1);
     const int wi = warp / kConvGroups;
-    const bool do_nk = tile == 0;
     uint32_t off[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int kk = 2 * wi + j;      // row within the stage = MMA k index
       off[j] = (kk >> 3) * 1024 + (kk & 7) * 128 + ((((lane & 15) >> 1) ^ (kk & 7)) << 4) + (lane & 1) * 8;
     }
-    // per-lane Phi sources for the (up to) two blocks this lane serves: blocks 2 t2 + (lane >> 4).
-    // Every load is unconditional (clamped addresses, masked values) so the compiler can batch
-    // them: the branchy first version serialised on divergent-branch reconvergence.
-    int src_a[2], src_b[2];        // element offsets into the row of X
-    float lin[2], mask_b[2];       // lin = 1: linear block (left factor is 1); mask_b = 0: padding columns
+    // left factor a = x[src_a] * ma + ca; right factors x[src_b .. +3] * mb + (cb, 0, 0, 0):
+    //   pair block   ma = 1, ca = 0, mb = 1, cb = 0        (x_d x_e)
+    //   linear block ma = 0, ca = 1, mb = 1 (0 past d)     (x_e)
+    //   ones block   ma = 0, ca = 1, mb = 0, cb = 1 on column 0  (1: gives Nk)
+    //   unused slot  all zero
+    int src_a[2], src_b[2];
+    float ma[2], ca[2], mb[2], cb[2];
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2) {
       const int bl = 2 * t2 + (lane >> 4);
       const int b = block0 + bl;
       const int i = (lane & 15) >> 1, j0 = (lane & 1) * 4;
-      src_a[t2] = 0;
-      src_b[t2] = 0;
-      lin[t2] = 0.f;
-      mask_b[t2] = 0.f;
+      src_a[t2] = 0; src_b[t2] = 0;
+      ma[t2] = 0.f; ca[t2] = 0.f; mb[t2] = 0.f; cb[t2] = 0.f;
       if (bl < tile_blocks) {
         if (b < g.n_pair) {
           int ga, gb;
           pair_of(b, g.n_groups, &ga, &gb);
           src_a[t2] = 8 * ga + i;
           src_b[t2] = 8 * gb + j0;
-          mask_b[t2] = 1.f;
-        } else {
-          lin[t2] = 1.f;
+          ma[t2] = 1.f;
+          mb[t2] = 1.f;
+        } else if (b == g.n_pair) {
+          ca[t2] = 1.f;
           if (8 * i + j0 < g.d) {        // linear block: column c = 8 i + j0 .. +3
             src_b[t2] = 8 * i + j0;
-            mask_b[t2] = 1.f;
+            mb[t2] = 1.f;
           }
+        } else {                         // ones block: column 0 = 1
+          ca[t2] = 1.f;
+          cb[t2] = (lane & 15) == 0 ? 1.f : 0.f;
         }
       }
     }
@@ -237,62 +244,44 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     const int kc0 = min(4 * lane, g.k - 4), kc1 = min(4 * lane + 128, g.k - 4);
     const float km0 = 4 * lane < g.k ? 1.f : 0.f, km1 = 4 * lane + 128 < g.k ? 1.f : 0.f;
     const bool k_partial = g.k < kMaxK;                  // some lanes hold components past k
-    // walking pointers (row0, this lane's columns); the loop is issue-bound, so no per-iteration
-    // address arithmetic beyond one add each
+    // walking pointers to this warp's first row of the next stage it converts
     const float* rp = r + row0 * g.k;
     const float* xp = x + row0 * g.d;
+    const float* lp = kFromLogits ? lse + row0 : nullptr;
     const int64_t r_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.k;
     const int64_t x_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.d;
     float4 rr[2][2];
-    float row_lse[2] = {0.f, 0.f};   // logits mode (lse != nullptr): r = exp(logit - lse[row])
-    float xa[2][2];          // [row][block slot]: the left factor of the pair product
-    float4 xb[2][2];         // the four right factors
-    float nk_f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    int since_flush = 0;
-    bool rows_ok = true;     // both rows of the prefetched stage are inside [0, n)
+    float row_lse[2] = {0.f, 0.f};   // logits mode: r = exp(logit - lse[row])
+    float xa[2][2];                  // [row][block slot]
+    float4 xb[2][2];
+    bool rows_ok = true;             // both rows of the prefetched stage are inside [0, n)
     // everything a stage needs is loaded one iteration ahead (nothing is fetched between the
     // barrier wait and the stores: dependent loads there serialise on the L2 latency)
     auto load_all = [&]() {
       rows_ok = row0 + 2 <= n;
-      if (rows_ok) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          rr[j][0] = ldg_f4(rp + j * g.k + kc0);
-          rr[j][1] = ldg_f4(rp + j * g.k + kc1);
-          if (kFromLogits) row_lse[j] = __ldg(lse + row0 + j);
-#pragma unroll
-          for (int t2 = 0; t2 < 2; ++t2) {
-            xa[j][t2] = __ldg(xp + j * g.d + src_a[t2]);
-            xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xp + j * g.d + src_b[t2]));
-          }
-        }
-      } else {                                            // ragged last stage: clamp, zero the weights
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const bool ok = row0 + j < n;
-          const int64_t back = ok ? 0 : (row0 + j) - (n - 1);     // rows to step back to stay in range
-          rr[j][0] = ldg_f4(rp + (j - back) * g.k + kc0);
-          rr[j][1] = ldg_f4(rp + (j - back) * g.k + kc1);
-          if (kFromLogits) row_lse[j] = __ldg(lse + row0 + j - back);
-#pragma unroll
-          for (int t2 = 0; t2 < 2; ++t2) {
-            xa[j][t2] = __ldg(xp + (j - back) * g.d + src_a[t2]);
-            xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xp + (j - back) * g.d + src_b[t2]));
-          }
-        }
+      // ragged last stage: a row past the end re-reads row n - 1 (its weights are zeroed later)
+      int jj[2] = {0, 1};
+      if (!rows_ok) {
+        jj[0] = row0 < n ? 0 : static_cast<int>((n - 1) - row0);
+        jj[1] = row0 + 1 < n ? 1 : static_cast<int>((n - 1) - row0);
       }
-      if (prefetch_iters > 0 && lane < 20) {             // L2 prefetch hints a few stages ahead
-        const bool is_r = lane < 16;
-        const int prow = is_r ? (lane >> 3) : ((lane - 16) >> 1);
-        const int64_t ahead = row0 + static_cast<int64_t>(prefetch_iters) * kConvGroups * kStageRows + prow;
-        if (ahead < row_end) {
-          const float* pp = is_r ? r + ahead * g.k + (lane & 7) * 32 : x + ahead * g.d + (lane & 1) * 32;
-          if ((is_r ? (lane & 7) * 32 : (lane & 1) * 32) < (is_r ? g.k : g.d)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float* rrow = rp + jj[j] * g.k;
+        const float* xrow = xp + jj[j] * g.d;
+        rr[j][0] = ldg_f4(rrow + kc0);
+        rr[j][1] = ldg_f4(rrow + kc1);
+        if (kFromLogits) row_lse[j] = __ldg(lp + jj[j]);
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+          xa[j][t2] = __ldg(xrow + src_a[t2]);
+          xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xrow + src_b[t2]));
         }
       }
       row0 += kConvGroups * kStageRows;
       rp += r_step;
       xp += x_step;
+      if (kFromLogits) lp += kConvGroups * kStageRows;
     };
     if (group < n_iters) load_all();
     for (int it = group; it < n_iters; it += kConvGroups) {
@@ -310,7 +299,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
             rr[j][h].w = __expf(rr[j][h].w - row_lse[j]);
           }
       }
-      if (!rows_ok || k_partial) {                        // rare: zero what lies past n or past k
+      if (!rows_ok || k_partial) {                        // cold: zero what lies past n or past k
         const int64_t first = row0 - kConvGroups * kStageRows;   // row0 was advanced by load_all
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -331,22 +320,15 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
           sts_u2(addr, b1[0], b1[1]);
           sts_u2(addr + kRPart, b2[0], b2[1]);
         }
-      if (do_nk) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          nk_f[h][0] += rr[0][h].x + rr[1][h].x;
-          nk_f[h][1] += rr[0][h].y + rr[1][h].y;
-          nk_f[h][2] += rr[0][h].z + rr[1][h].z;
-          nk_f[h][3] += rr[0][h].w + rr[1][h].w;
-        }
-      }
       // ---- Phi tile: [block (64 columns) 2 KB][k group][8][128 B] ----
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int t2 = 0; t2 < 2; ++t2) {
-          const float a = (lin[t2] != 0.f ? 1.f : xa[j][t2]) * mask_b[t2];
-          const float4 p = make_float4(a * xb[j][t2].x, a * xb[j][t2].y, a * xb[j][t2].z, a * xb[j][t2].w);
+          const float a = fmaf(xa[j][t2], ma[t2], ca[t2]);
+          const float am = a * mb[t2];
+          const float4 p = make_float4(fmaf(am, xb[j][t2].x, a * cb[t2]), am * xb[j][t2].y, am * xb[j][t2].z,
+                                       am * xb[j][t2].w);
           uint32_t b1[2], b2[2];
           split_bf16(p, b1, b2);
           const uint32_t addr = stage_addr + 2 * kRPart + (2 * t2 + (lane >> 4)) * 2048 + off[j];
@@ -357,26 +339,6 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&sm.full[s]);
       if (it + kConvGroups < n_iters) load_all();
-      if (do_nk && ++since_flush == 16) {      // fp32 over 32 rows, then float64 in shared memory
-        since_flush = 0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int kc = 4 * lane + 128 * h + c;
-            if (kc < g.k) atomicAdd(&sm.nk[kc], static_cast<double>(nk_f[h][c]));
-            nk_f[h][c] = 0.f;
-          }
-      }
-    }
-    if (do_nk) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int kc = 4 * lane + 128 * h + c;
-          if (kc < g.k) atomicAdd(&sm.nk[kc], static_cast<double>(nk_f[h][c]));
-        }
     }
   } else if (warp < kMmaWarp) {
     // ---------------- epilogue warps: TMEM fp32 -> fp32 partial (coalesced RMW), single-buffered ----------------
@@ -444,8 +406,6 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (tile == 0 && partial_nk != nullptr)
-    for (int i = threadIdx.x; i < g.k; i += kThreads) partial_nk[static_cast<int64_t>(split) * g.k + i] = sm.nk[i];
   if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -481,11 +441,7 @@ weighted_pairs_finalize_kernel(const float* __restrict__ partial, const double* 
     if (srx != nullptr) srx[j] = column_sum(static_cast<int>(j / g.d), g.n_pair, static_cast<int>(j % g.d));
   } else if (idx < n_xx + static_cast<int64_t>(g.k) * g.d + g.k) {
     const int k = static_cast<int>(idx - n_xx - static_cast<int64_t>(g.k) * g.d);
-    if (nk != nullptr) {
-      double acc = 0.0;
-      for (int s = 0; s < n_splits; ++s) acc += partial_nk[static_cast<int64_t>(s) * g.k + k];
-      nk[k] = acc;
-    }
+    if (nk != nullptr) nk[k] = column_sum(k, g.n_pair + 1, 0);
   }
 }
 
@@ -500,7 +456,7 @@ PairsPlan plan_pairs(int64_t n, int d, int k) {
   p.g.k = k;
   p.g.n_groups = d / 8;
   p.g.n_pair = p.g.n_groups * (p.g.n_groups + 1) / 2;
-  p.g.n_blocks = p.g.n_pair + 1;
+  p.g.n_blocks = p.g.n_pair + 2;      // pair blocks, the linear block, the ones block (Nk)
   p.g.n_tiles = (p.g.n_blocks + 3) / 4;
   p.g.base = p.g.n_blocks / p.g.n_tiles;
   p.g.rem = p.g.n_blocks % p.g.n_tiles;

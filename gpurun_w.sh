@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_stats.py -q -x -m gpu -k "reject or mismatched" 2>&1 | tail -8
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_passes.py tests/test_gpu_stats.py -q -m gpu -k "cfg3 or weighted or mixture" > gpurun_out/pytest_w.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_w.log

@@ -179,7 +179,8 @@ def test_weighted_suffstats_sum_over_components_is_the_plain_statistic():
     np.testing.assert_allclose(rxx.sum(0).cpu().numpy(), (Xw.T @ X.double()).cpu().numpy(), rtol=2e-5,
                                atol=1e-6 * float(s2.abs().max()))
     np.testing.assert_allclose(rx.sum(0).cpu().numpy(), Xw.sum(0).cpu().numpy(), rtol=1e-5)
-    assert abs(float(nk.sum()) - float(rowsum.sum())) <= 1e-6 * n
+    # Nk comes out of the same tensor-core contraction (a constant-1 column): same 1e-5 class
+    assert abs(float(nk.sum()) - float(rowsum.sum())) <= 2e-5 * n
 
 
 # ---- regression / Gram statistics (cfg4): X^T X, X^T y, y^T y in one pass -------------------
@@ -419,7 +420,7 @@ def test_large_cfg3_properties():
     nk, rx, rxx = S.weighted_suffstats(X, R)
     _, s1, s2 = S.gaussian_suffstats(X)
     rowsum = R.double().sum(1)
-    assert abs(float(nk.sum()) - float(rowsum.sum())) <= 1e-6 * n
+    assert abs(float(nk.sum()) - float(rowsum.sum())) <= 2e-5 * n
     Xw = X.double() * rowsum[:, None]
     ref2 = torch.zeros(d, d, dtype=torch.float64, device='cuda')
     for lo in range(0, n, 1 << 19):
