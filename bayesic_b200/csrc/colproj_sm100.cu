@@ -242,7 +242,7 @@ colproj_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t
     }
     for (int interval = 0; interval < n_intervals; ++interval) {
       const int buf = interval & 1;
-      ptx::mbar_wait(&bar.acc_full[buf], (interval >> 1) & 1);
+      ptx::mbar_wait_sleep(&bar.acc_full[buf], (interval >> 1) & 1);
       ptx::tc_fence_after_sync();
       const uint32_t t_addr = tmem + (static_cast<uint32_t>(qd * 32) << 16) + buf * kAccCols;
 #pragma unroll 1

@@ -403,7 +403,7 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
     }
     for (int interval = 0; interval < n_intervals; ++interval) {
       const int buf = interval & 1;
-      ptx::mbar_wait(&sm.acc_full[buf], (interval >> 1) & 1);
+      ptx::mbar_wait_sleep(&sm.acc_full[buf], (interval >> 1) & 1);
       ptx::tc_fence_after_sync();
       const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * kBlock;
 #pragma unroll 1

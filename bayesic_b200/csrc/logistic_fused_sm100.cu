@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused_kernel(const Fused
       }
       // drain G every kFlushTiles tiles (and after the last tile)
       if ((t % kFlushTiles) == kFlushTiles - 1 || t == T - 1) {
-        ptx::mbar_wait(&sm.g_full, static_cast<uint32_t>(flushes) & 1);
+        ptx::mbar_wait_sleep(&sm.g_full, static_cast<uint32_t>(flushes) & 1);
         ptx::tc_fence_after_sync();
         const uint32_t g_addr = tmem + (static_cast<uint32_t>(qd * 32) << 16) + kTmemG;
 #pragma unroll 1

@@ -54,6 +54,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait that backs off between polls: for warps that wait a long time (epilogue warps waiting for a
+// 2048-row accumulation interval).  A bare try_wait loop returns every few tens of cycles and,
+// with the scheduler favouring high warp ids, takes issue slots from the converter warps.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 256) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---- TMA ----------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

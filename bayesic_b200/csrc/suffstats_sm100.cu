@@ -43,6 +43,14 @@ namespace bb {
 
 namespace {
 
+// epilogue warps wait ~5 000 cycles per 512-row chunk; a backing-off wait (mbar_wait_sleep) was
+// measured here and made no difference (0.772 ms either way), so they spin
+#ifdef BB_SUFFSTATS_EPI_SLEEP
+#define BB_SUFFSTATS_EPI_WAIT(bar, parity) ptx::mbar_wait_sleep(bar, parity, 64)
+#else
+#define BB_SUFFSTATS_EPI_WAIT(bar, parity) ptx::mbar_wait(bar, parity)
+#endif
+
 constexpr int kFeat = 64;          // padded feature extent (= MMA N, = half of MMA M)
 constexpr int kTileRows = 128;     // data rows per pipeline stage
 constexpr int kStages = 6;
@@ -245,7 +253,7 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
     const int n_chunks = (my_tiles + kFlushTiles - 1) / kFlushTiles;
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int ab = chunk & 1;
-      ptx::mbar_wait(&sm.acc_full[ab], (chunk >> 1) & 1);
+      BB_SUFFSTATS_EPI_WAIT(&sm.acc_full[ab], (chunk >> 1) & 1);
       ptx::tc_fence_after_sync();
       const uint32_t d_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemAcc + ab * kFeat +
                               chalf * kCols;

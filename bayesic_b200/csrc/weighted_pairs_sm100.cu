@@ -350,7 +350,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       for (int c = 0; c < 2 * kTileCols; ++c) my_partial[c * 128] = 0.f;
     }
     for (int interval = 0; interval < n_intervals; ++interval) {
-      ptx::mbar_wait(&sm.acc_full, interval & 1);
+      ptx::mbar_wait_sleep(&sm.acc_full, interval & 1);
       ptx::tc_fence_after_sync();
       for (int mb = 0; mb < m_blocks; ++mb) {
         const uint32_t t_addr = tmem + (static_cast<uint32_t>(qd * 32) << 16) + mb * kTileCols;

@@ -1,2 +1,2 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_passes.py tests/test_gpu_stats.py -q -m gpu -k "cfg3 or weighted or mixture" > gpurun_out/pytest_w.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_w.log
+for i in 1 2; do timeout 100 python tests/gpu_profile_driver.py suffstats; done
+timeout 300 python bench.py --steps 50 --warmup 3 --no-e2e --no-cpu-baseline --no-other-configs | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms'])"
