@@ -388,15 +388,15 @@ BB_API int64_t bb_mixture_logits_workspace(int64_t n, int32_t d, int32_t k) {
 }
 
 BB_API int bb_mixture_logits(const float* X, const float* U, const float* t, const float* c, int64_t n, int32_t d,
-                      int32_t k, float* logits, float* lse, double* sum_lse, void* workspace,
-                      int64_t workspace_bytes, void* stream) {
+                      int32_t k, int32_t upper_triangular, float* logits, float* lse, double* sum_lse,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n < 0 || !U || !t || !c || (n > 0 && (!X || !logits))) { set_error("mixture_logits: bad arguments"); return BB_ERR_INVALID; }
   if (n == 0) {
     if (sum_lse) BB_CUDA_OK(cudaMemsetAsync(sum_lse, 0, sizeof(double), st));
     return BB_OK;
   }
-  return launch_mixture_logits(X, U, t, c, n, d, k, logits, lse, sum_lse, workspace, workspace_bytes, st);
+  return launch_mixture_logits(X, U, t, c, n, d, k, upper_triangular, logits, lse, sum_lse, workspace, workspace_bytes, st);
 }
 
 BB_API int64_t bb_suffstats_weighted_workspace(int64_t n, int32_t d, int32_t k) {

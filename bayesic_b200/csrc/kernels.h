@@ -57,8 +57,8 @@ int launch_logistic_fused(const float* x, const float* y, const float* w, int64_
 bool mixture_logits_supported(int64_t n, int d, int k, const void* x);
 int64_t mixture_logits_workspace(int64_t n, int d, int k);
 int launch_mixture_logits(const float* x, const float* u, const float* t, const float* c, int64_t n, int d, int k,
-                          float* logits, float* lse, double* sum_lse, void* workspace, int64_t workspace_bytes,
-                          cudaStream_t stream);
+                          int upper_triangular, float* logits, float* lse, double* sum_lse, void* workspace,
+                          int64_t workspace_bytes, cudaStream_t stream);
 
 // mixture_kernels.cu
 int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_resp, float* lse,

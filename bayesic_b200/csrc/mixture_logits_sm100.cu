@@ -123,43 +123,47 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
   b2[1] = *reinterpret_cast<uint32_t*>(&q1);
 }
 
-// U[k, j, i] float32 (row j of factor k) -> wprep[group][part][256 rows x 128 B] bf16 in the K-major
-// SWIZZLE_128B layout (row r = 64 (k % 4) + j; features i >= d and rows j >= d are zero);
-// t[k, j] -> tprep[k][64] zero-padded.
-__global__ void prep_factors_kernel(const float* __restrict__ u, const float* __restrict__ t, int k_total, int d,
-                                    uint8_t* __restrict__ wprep, float* __restrict__ tprep) {
+// Column order of the projection: MMA tile (cg, jr) holds, for the 16 components 16 cg .. 16 cg + 15,
+// rows j in [16 jr, 16 jr + 16) of their factors: column c * 16 + jj <-> (component 16 cg + c,
+// row j = 16 jr + jj).  For upper-triangular factors (Cholesky) row j is zero left of feature j, so
+// tile jr only needs the K steps ks >= jr: 10 of 16 MMA K-steps at D = 64.
+// U[k, j, i] float32 -> wprep[tile = 4 cg + jr][part][256 rows x 128 B] bf16, K-major SWIZZLE_128B
+// (components >= k, rows j >= d and features i >= d are zero); t[k, j] -> tprep[tile][256].
+__global__ void prep_factors_kernel(const float* __restrict__ u, const float* __restrict__ t, int k_total, int k16,
+                                    int d, uint8_t* __restrict__ wprep, float* __restrict__ tprep) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // (k, j, chunk of 8 features)
-  const int64_t total = static_cast<int64_t>(k_total) * 64 * 8;
+  const int64_t total = static_cast<int64_t>(k16) * 64 * 8;
   if (idx >= total) return;
-  const int c = static_cast<int>(idx % 8);
+  const int c8 = static_cast<int>(idx % 8);
   const int j = static_cast<int>((idx / 8) % 64);
   const int k = static_cast<int>(idx / (8 * 64));
   __align__(16) __nv_bfloat16 b1[8], b2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int i = c * 8 + e;
-    const float x = (j < d && i < d) ? u[(static_cast<int64_t>(k) * d + j) * d + i] : 0.f;
+    const int i = c8 * 8 + e;
+    const float x = (k < k_total && j < d && i < d) ? u[(static_cast<int64_t>(k) * d + j) * d + i] : 0.f;
     b1[e] = __float2bfloat16_rn(x);
     b2[e] = __float2bfloat16_rn(x - __bfloat162float(b1[e]));
   }
-  const int group = k / kGroupComps, r = (k % kGroupComps) * 64 + j;
-  const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
-  uint8_t* base = wprep + static_cast<int64_t>(group) * kWBytes;
+  const int tile = (k / 16) * 4 + j / 16, r = (k % 16) * 16 + j % 16;
+  const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4);
+  uint8_t* base = wprep + static_cast<int64_t>(tile) * kWBytes;
   *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(b1);
   *reinterpret_cast<uint4*>(base + kWPart + off) = *reinterpret_cast<const uint4*>(b2);
-  if (c == 0) tprep[static_cast<int64_t>(k) * 64 + j] = j < d ? t[static_cast<int64_t>(k) * d + j] : 0.f;
+  if (c8 == 0) tprep[static_cast<int64_t>(tile) * 256 + r] = (k < k_total && j < d) ? t[static_cast<int64_t>(k) * d + j] : 0.f;
 }
 
 struct LogitParams {
   const float* x;
   const uint8_t* wprep;
-  const float* tprep;       // [k][64]
+  const float* tprep;       // [tile][256]
   const float* c;           // [k]
   float* logits;            // [n, k]
   float* lse;               // [n] or nullptr
   double* partial_sum_lse;  // [grid] or nullptr
   int64_t n;
   int d, k;
+  int triangular;           // factors are upper triangular: tile jr skips the K steps below jr
 };
 
 __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const LogitParams p) {
@@ -167,8 +171,9 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_groups = p.k / kGroupComps;
-  const int k_steps = p.d / 16;
+  const int n_cg = (p.k + 15) / 16;          // component groups of 16
+  const int k_steps = p.d / 16;              // = number of j ranges with data
+  const int n_seq = n_cg * k_steps;          // MMA tiles per row tile, in order (cg, jr)
   const int64_t n_tiles = (p.n + kTileRows - 1) / kTileRows;
   const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -206,63 +211,81 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
     const int q = warp & 3, h = warp >> 2;
     double sum_lse = 0.0;
     int64_t gi = 0;
-    float tl_next[4], c_next[2];
+    // t values of a tile are fetched one tile ahead (a load issued right before its use stalled the
+    // epilogue on the L2 latency four times per tile -- the top stall in the first ncu profile)
+    float tl_next[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(p.tprep + static_cast<int64_t>(h * 2 + (i >> 1)) * 64 + (i & 1) * 32 + lane);
-    c_next[0] = __ldg(p.c + h * 2);
-    c_next[1] = __ldg(p.c + h * 2 + 1);
+    for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(p.tprep + h * 128 + i * 32 + lane);      // tile (0, 0)
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int64_t tile = blockIdx.x + t * gridDim.x;
       const int64_t row = tile * kTileRows + q * 32 + lane;
       const bool valid = row < p.n;
       float run_m = -INFINITY, run_s = 0.f;
-      for (int g = 0; g < n_groups; ++g, ++gi) {
-        // this group's t and c values were fetched one group ahead (a load issued right before its
-        // use stalled the epilogue on the L2 latency four times per group -- the top stall in ncu)
-        float tl[4], cc[2];
+      for (int cg = 0; cg < n_cg; ++cg) {
+        // this warp's 8 components of the group: 16 cg + 8 h + (0 .. 7)
+        const int comp0 = cg * 16 + h * 8;
+        float cc[8], acc[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tl[i] = tl_next[i];
-        cc[0] = c_next[0];
-        cc[1] = c_next[1];
-        {
-          const int gn = (g + 1 == n_groups) ? 0 : g + 1;
-          const int comp0 = gn * kGroupComps + h * 2;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(p.tprep + static_cast<int64_t>(comp0 + (i >> 1)) * 64 + (i & 1) * 32 + lane);
-          c_next[0] = __ldg(p.c + comp0);
-          c_next[1] = __ldg(p.c + comp0 + 1);
+        for (int c = 0; c < 8; ++c) {
+          cc[c] = comp0 + c < p.k ? __ldg(p.c + comp0 + c) : 0.f;
+          acc[c] = 0.f;
         }
-        const int ab = static_cast<int>(gi & 1);
-        ptx::mbar_wait(&sm.acc_full[ab], static_cast<uint32_t>(gi >> 1) & 1);
-        ptx::tc_fence_after_sync();
-        const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + ab * kGroupCols + h * 128;
-        float logit[2];
+        for (int jr = 0; jr < k_steps; ++jr, ++gi) {
+          float tl[4];
 #pragma unroll
-        for (int cidx = 0; cidx < 2; ++cidx) {
-          float acc = 0.f;
+          for (int i = 0; i < 4; ++i) tl[i] = tl_next[i];
+          {
+            int ncg = cg, njr = jr + 1;
+            if (njr == k_steps) { njr = 0; ncg = (cg + 1 == n_cg) ? 0 : cg + 1; }
+            const float* src = p.tprep + static_cast<int64_t>(ncg * 4 + njr) * 256 + h * 128 + lane;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+            for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(src + i * 32);
+          }
+          const int ab = static_cast<int>(gi & 1);
+          ptx::mbar_wait(&sm.acc_full[ab], static_cast<uint32_t>(gi >> 1) & 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + ab * kGroupCols + h * 128;
+#pragma unroll
+          for (int quarter = 0; quarter < 4; ++quarter) {        // 32 columns = 2 components x 16 rows j
             uint32_t v[32];
-            tmem_ld_32x32b_x32(t_addr + cidx * 64 + half * 32, v);
-            const float tv = tl[cidx * 2 + half];
+            tmem_ld_32x32b_x32(t_addr + quarter * 32, v);
+            const float tv = tl[quarter];
             ptx::tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float dz = __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, tv, j);
-              acc = fmaf(dz, dz, acc);
+              acc[quarter * 2 + (j >> 4)] = fmaf(dz, dz, acc[quarter * 2 + (j >> 4)]);
             }
           }
-          logit[cidx] = fmaf(-0.5f, acc, cc[cidx]);
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&sm.acc_empty[ab]);
         }
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&sm.acc_empty[ab]);
-        if (valid)
-          *reinterpret_cast<float2*>(p.logits + row * p.k + g * kGroupComps + h * 2) = make_float2(logit[0], logit[1]);
-        // online log-sum-exp over this warp's components
-        const float m_new = fmaxf(run_m, fmaxf(logit[0], logit[1]));
-        run_s = run_s * __expf(run_m - m_new) + __expf(logit[0] - m_new) + __expf(logit[1] - m_new);
-        run_m = m_new;
+        // the 8 logits of this row are complete: store, fold into the online log-sum-exp
+        if (comp0 < p.k) {
+          float lg[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) lg[c] = comp0 + c < p.k ? fmaf(-0.5f, acc[c], cc[c]) : -INFINITY;
+          if (valid) {
+            float* dst = p.logits + row * p.k + comp0;
+            if (comp0 + 8 <= p.k) {
+              *reinterpret_cast<float4*>(dst) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(lg[4], lg[5], lg[6], lg[7]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                if (comp0 + c < p.k) dst[c] = lg[c];
+            }
+          }
+          float m_new = run_m;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) m_new = fmaxf(m_new, lg[c]);
+          float sum = run_s * __expf(run_m - m_new);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sum += __expf(lg[c] - m_new);      // exp(-inf) = 0 for padding
+          run_s = sum;
+          run_m = m_new;
+        }
       }
       // combine the two column halves of each row: h = 1 hands (m, s) to h = 0 through shared memory
       const int tb = static_cast<int>(t & 1);
@@ -293,11 +316,12 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
     if (ptx::elect_one()) {
       int64_t gi = 0;
       for (int64_t t = 0; t < my_tiles; ++t)
-        for (int g = 0; g < n_groups; ++g, ++gi) {
+        for (int g = 0; g < n_seq; ++g, ++gi) {
           const int s = static_cast<int>(gi % kWStages);
           ptx::mbar_wait(&sm.w_empty[s], (static_cast<uint32_t>(gi / kWStages) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&sm.w_full[s], kWBytes);
-          const uint8_t* src = p.wprep + static_cast<int64_t>(g) * kWBytes;
+          const int wtile = (g / k_steps) * 4 + g % k_steps;
+          const uint8_t* src = p.wprep + static_cast<int64_t>(wtile) * kWBytes;
           bulk_load(sm.w[s], src, kWPart, &sm.w_full[s]);
           bulk_load(sm.w[s] + kWPart, src + kWPart, kWPart, &sm.w_full[s]);
         }
@@ -311,20 +335,21 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
         const int tb = static_cast<int>(t & 1);
         ptx::mbar_wait(&sm.a_full[tb], static_cast<uint32_t>(t >> 1) & 1);
         const uint32_t a_base = ptx::smem_u32(sm.a[tb]);
-        for (int g = 0; g < n_groups; ++g, ++gi) {
+        for (int g = 0; g < n_seq; ++g, ++gi) {
           const int s = static_cast<int>(gi % kWStages);
           const int ab = static_cast<int>(gi & 1);
+          const int ks_begin = p.triangular ? g % k_steps : 0;     // tile jr: rows j >= 16 jr are zero left of feature 16 jr
           ptx::mbar_wait(&sm.w_full[s], static_cast<uint32_t>(gi / kWStages) & 1);
           ptx::mbar_wait(&sm.acc_empty[ab], (static_cast<uint32_t>(gi >> 1) & 1) ^ 1);
           ptx::tc_fence_after_sync();
           const uint32_t w_base = ptx::smem_u32(sm.w[s]);
           const uint32_t d_tmem = tmem + ab * kGroupCols;
-          for (int ks = 0; ks < k_steps; ++ks) {
+          for (int ks = ks_begin; ks < k_steps; ++ks) {
             const uint64_t a1 = ptx::make_smem_desc(a_base + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
             const uint64_t a2 = ptx::make_smem_desc(a_base + kAPart + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
             const uint64_t b1 = ptx::make_smem_desc(w_base + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
             const uint64_t b2 = ptx::make_smem_desc(w_base + kWPart + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
-            mma_bf16_ss(d_tmem, a1, b1, idesc, ks == 0 ? 0u : 1u);
+            mma_bf16_ss(d_tmem, a1, b1, idesc, ks == ks_begin ? 0u : 1u);
             mma_bf16_ss(d_tmem, a1, b2, idesc, 1u);
             mma_bf16_ss(d_tmem, a2, b1, idesc, 1u);
           }
@@ -397,15 +422,15 @@ bool mixture_logits_supported(int64_t n, int d, int k, const void* x) {
 
 int64_t mixture_logits_workspace(int64_t n, int d, int k) {
   (void)d;
-  return static_cast<int64_t>(k / kGroupComps) * kWBytes + static_cast<int64_t>(k) * 64 * 4 +
-         static_cast<int64_t>(logits_grid(n)) * 8 + 1024;
+  const int64_t n_cg = (k + 15) / 16;
+  return n_cg * 4 * kWBytes + n_cg * 4 * 256 * 4 + static_cast<int64_t>(logits_grid(n)) * 8 + 1024;
 }
 
 // u [k, d, d] (upper Cholesky factors, row-major), t [k, d], c [k]: device float32.
 // logits [n, k] float32 (required), lse [n] float32 and sum_lse (float64) optional.
 int launch_mixture_logits(const float* x, const float* u, const float* t, const float* c, int64_t n, int d, int k,
-                          float* logits, float* lse, double* sum_lse, void* workspace, int64_t workspace_bytes,
-                          cudaStream_t stream) {
+                          int upper_triangular, float* logits, float* lse, double* sum_lse, void* workspace,
+                          int64_t workspace_bytes, cudaStream_t stream) {
   if (!mixture_logits_supported(n, d, k, x) || reinterpret_cast<uintptr_t>(logits) % 8 != 0) {
     set_error("mixture_logits: unsupported shape n=%lld d=%d k=%d", static_cast<long long>(n), d, k);
     return BB_ERR_UNSUPPORTED;
@@ -416,18 +441,19 @@ int launch_mixture_logits(const float* x, const float* u, const float* t, const 
     return BB_ERR_WORKSPACE;
   }
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  const int n_cg = (k + 15) / 16;
   uint8_t* wprep = ws;
-  ws += static_cast<int64_t>(k / kGroupComps) * kWBytes;
+  ws += static_cast<int64_t>(n_cg) * 4 * kWBytes;
   float* tprep = reinterpret_cast<float*>(ws);
-  ws += static_cast<int64_t>(k) * 64 * 4;
+  ws += static_cast<int64_t>(n_cg) * 4 * 256 * 4;
   double* partial = reinterpret_cast<double*>(ws);
-  const int64_t prep_items = static_cast<int64_t>(k) * 64 * 8;
-  prep_factors_kernel<<<static_cast<int>((prep_items + 255) / 256), 256, 0, stream>>>(u, t, k, d, wprep, tprep);
+  const int64_t prep_items = static_cast<int64_t>(n_cg) * 16 * 64 * 8;
+  prep_factors_kernel<<<static_cast<int>((prep_items + 255) / 256), 256, 0, stream>>>(u, t, k, n_cg * 16, d, wprep, tprep);
   BB_CHECK_LAUNCH("prep_factors_kernel");
   LogitParams p;
   p.x = x; p.wprep = wprep; p.tprep = tprep; p.c = c; p.logits = logits; p.lse = lse;
   p.partial_sum_lse = sum_lse != nullptr ? partial : nullptr;
-  p.n = n; p.d = d; p.k = k;
+  p.n = n; p.d = d; p.k = k; p.triangular = upper_triangular ? 1 : 0;
   const int grid = logits_grid(n);
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
   static bool attr_set = false;

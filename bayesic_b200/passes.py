@@ -83,13 +83,14 @@ class GmmStep(object):
                 and X.shape[0] >= 1024):
             # whole local step in two kernels: logits + row log-sum-exp, then the statistics with
             # r = exp(logit - lse) formed inside the operand conversion (R is never written)
-            logits, lse, sum_lse = stats.mixture_logits(X, *self.whiten(Ak, bk, ck))
+            logits, lse, sum_lse = stats.mixture_logits(X, *self.whiten(Ak, bk, ck), upper_triangular=True)
             nk, rx, rxx = stats.weighted_suffstats_from_logits(X, logits, lse)
             return {'logits': logits, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
         if fused and stats.mixture_logits_supported(X.shape[1], Ak.shape[0]):
             # same value as the einsum plan, as one tcgen05 projection with the quadratic form
             # consumed on chip (the plan route materialises N x K x D and cannot run at cfg3 size)
-            logits, _, _ = stats.mixture_logits(X, *self.whiten(Ak, bk, ck), want_lse=False, want_sum=False)
+            logits, _, _ = stats.mixture_logits(X, *self.whiten(Ak, bk, ck), want_lse=False, want_sum=False,
+                                               upper_triangular=True)
         else:
             logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
         log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place

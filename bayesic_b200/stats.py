@@ -274,9 +274,11 @@ def mixture_logits_supported(d, k):
     return d in (16, 32, 48, 64) and k % 4 == 0 and k >= 4
 
 
-def mixture_logits(X, U, t, c, want_lse=True, want_sum=True):
+def mixture_logits(X, U, t, c, want_lse=True, want_sum=True, upper_triangular=False):
     """``logits[n, k] = c[k] - 0.5 * ||U[k] @ x_n - t[k]||**2`` (float32 CUDA tensor) and,
-    optionally, the row log-sum-exp ``lse[n]`` and its sum (float64[1])."""
+    optionally, the row log-sum-exp ``lse[n]`` and its sum (float64[1]).
+    ``upper_triangular=True`` promises ``U[k, j, i] == 0`` for ``i < j`` (Cholesky factors) and
+    lets the kernel skip the tensor-core steps that would only multiply zeros."""
     torch = _torch()
     lib = L.load()
     X = _as_device_f32(X, 2, 'X')
@@ -294,7 +296,7 @@ def mixture_logits(X, U, t, c, want_lse=True, want_sum=True):
         total = torch.empty(1, dtype=torch.float64, device=dev) if want_sum else None
         ws = _workspace(lib.bb_mixture_logits_workspace(n, d, k), dev)
         L.check(lib.bb_mixture_logits(X.data_ptr(), U.data_ptr(), t.data_ptr(), c.data_ptr(), n, d, k,
-                                      logits.data_ptr(), lse.data_ptr() if want_lse else None,
+                                      1 if upper_triangular else 0, logits.data_ptr(), lse.data_ptr() if want_lse else None,
                                       total.data_ptr() if want_sum else None, ws.data_ptr(), ws.numel(),
                                       _stream(dev)), 'bb_mixture_logits')
     return logits, lse, total

@@ -34,7 +34,7 @@ def main(which):
             U = torch.eye(d, device='cuda').repeat(k, 1, 1).contiguous() + 0.01 * torch.randn(k, d, d, device='cuda').triu()
             t = torch.randn(k, d, device='cuda')
             c = torch.randn(k, device='cuda')
-            fn = lambda: S.mixture_logits(X, U, t, c)
+            fn = lambda: S.mixture_logits(X, U, t, c, upper_triangular=True)
     elif which == 'suffstats':               # cfg2: N = 16 Mi, D = 64
         X = torch.randn(1 << 24, 64, device='cuda')
         fn = lambda: S.gaussian_suffstats(X)

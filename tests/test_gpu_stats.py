@@ -335,9 +335,10 @@ def test_projection_unsupported_shapes_fail_loudly():
 
 # ---- mixture logits (cfg3): c_k - 1/2 |U_k x - t_k|^2 on tcgen05 --------------------------------
 
+@pytest.mark.parametrize('triangular', [False, True], ids=['general', 'triangular'])
 @pytest.mark.parametrize('n,d,k', [(1, 64, 4), (127, 64, 8), (128, 64, 4), (129, 16, 12), (1000, 32, 8),
-                                   (5000, 48, 20), (20000, 64, 256), (4097, 64, 64)])
-def test_mixture_logits(n, d, k):
+                                   (5000, 48, 20), (20000, 64, 256), (4097, 64, 64), (3000, 64, 36)])
+def test_mixture_logits(n, d, k, triangular):
     """Whitened Gaussian-mixture logits + row log-sum-exp vs float64.  The logits are O(1e2) in
     magnitude and come out of a float32 epilogue, hence the absolute term."""
     import torch
@@ -346,13 +347,17 @@ def test_mixture_logits(n, d, k):
     centers = rng.randn(k, d) * 2
     X = (centers[rng.randint(k, size=n)] + rng.randn(n, d)).astype(np.float32)
     A = np.stack([_spd_np(rng, d) for _ in range(k)])
-    U = np.stack([np.linalg.cholesky(a).T for a in A])                  # A = U^T U
+    U = np.stack([np.linalg.cholesky(a).T for a in A])                  # A = U^T U, upper triangular
+    if not triangular:                                                  # any factor with A = U^T U will do
+        Q = np.linalg.qr(rng.randn(d, d))[0]
+        U = np.einsum('ij,kjl->kil', Q, U)
     t = np.einsum('kji,ki->kj', U, centers)
     c = rng.randn(k)
     before = S.launch_count()
     logits, lse, total = S.mixture_logits(torch.from_numpy(X).cuda(), torch.from_numpy(U.astype(np.float32)).cuda(),
                                           torch.from_numpy(t.astype(np.float32)).cuda(),
-                                          torch.from_numpy(c.astype(np.float32)).cuda())
+                                          torch.from_numpy(c.astype(np.float32)).cuda(),
+                                          upper_triangular=triangular)
     assert S.launch_count() > before
     U32, t32, c32 = U.astype(np.float32).astype(np.float64), t.astype(np.float32).astype(np.float64), c.astype(np.float32).astype(np.float64)
     z = np.einsum('kji,ni->nkj', U32, X.astype(np.float64)) - t32[None]
@@ -406,7 +411,7 @@ def test_large_cfg3_properties():
     U = (torch.eye(d, device='cuda') + 0.05 * torch.randn(k, d, d, device='cuda', generator=g).triu()).contiguous()
     t = torch.einsum('kji,ki->kj', U, centers).contiguous()
     c = torch.randn(k, device='cuda', generator=g)
-    logits, lse, total = S.mixture_logits(X, U, t, c)
+    logits, lse, total = S.mixture_logits(X, U, t, c, upper_triangular=True)
     rows = torch.randint(n, (4096,), device='cuda', generator=g)
     z = torch.einsum('kji,ni->nkj', U.double(), X[rows].double()) - t.double()[None]
     want = c.double()[None] - 0.5 * (z * z).sum(-1)
