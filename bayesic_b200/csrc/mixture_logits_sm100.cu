@@ -42,9 +42,11 @@ constexpr int kGroupComps = 4;                     // components per MMA group
 constexpr int kGroupCols = 256;                    // = 4 x 64 padded factor rows
 constexpr int kAPart = kTileRows * 128;            // 16 KB: one bf16 part of the X tile (128-byte rows)
 constexpr int kABytes = 2 * kAPart;                // 32 KB
-constexpr int kWPart = kGroupCols * 128;           // 32 KB
-constexpr int kWBytes = 2 * kWPart;                // 64 KB per group
-constexpr int kWStages = 2;
+constexpr int kWPart = kGroupCols * 128;           // 32 KB: one bf16 part of a 256-column factor tile
+constexpr int kWBytes = 2 * kWPart;                // 64 KB per tile: [half 0: b1 | b2][half 1: b1 | b2]
+constexpr int kWHalfPart = kWPart / 2;             // 16 KB: 128 columns of one part
+constexpr int kWHalfBytes = kWBytes / 2;           // 32 KB: what one CTA of the pair loads per tile
+constexpr int kWStages = 4;
 constexpr int kEpiWarps = 8;                       // warps 0-7
 constexpr int kProdWarp = 8;
 constexpr int kMmaWarp = 9;
@@ -55,12 +57,13 @@ constexpr int kTmemCols = 512;
 
 struct __align__(1024) SmemLayout {
   uint8_t a[2][kABytes];
-  uint8_t w[kWStages][kWBytes];
+  uint8_t w[kWStages][kWHalfBytes];
   float lse_m[2][kTileRows];       // partial (max, sum) of the upper column half, per row
   float lse_s[2][kTileRows];
   double sum_lse;
   uint64_t a_full[2], a_empty[2];
   uint64_t w_full[kWStages], w_empty[kWStages];
+  uint64_t w_peer[kWStages];       // leader: the peer CTA's half of the factor tile has landed
   uint64_t acc_full[2], acc_empty[2];
   uint64_t lse_ready[2], lse_taken[2];
   uint32_t tmem_base;
@@ -77,6 +80,50 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` (no release fence: the
+// caller has made its writes visible with fence.proxy.async / tcgen05 fences + __syncwarp)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(ptx::smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t n_cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_slot)),
+               "r"(n_cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t n_cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(n_cols) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all MMAs issued so far completed
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(ptx::smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
 }
 // plain (non-tensor) bulk copy global -> shared, completion counted on an mbarrier
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -127,7 +174,7 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
 // rows j in [16 jr, 16 jr + 16) of their factors: column c * 16 + jj <-> (component 16 cg + c,
 // row j = 16 jr + jj).  For upper-triangular factors (Cholesky) row j is zero left of feature j, so
 // tile jr only needs the K steps ks >= jr: 10 of 16 MMA K-steps at D = 64.
-// U[k, j, i] float32 -> wprep[tile = 4 cg + jr][part][256 rows x 128 B] bf16, K-major SWIZZLE_128B
+// U[k, j, i] float32 -> wprep[tile = 4 cg + jr][half][part][128 rows x 128 B] bf16, K-major SWIZZLE_128B
 // (components >= k, rows j >= d and features i >= d are zero); t[k, j] -> tprep[tile][256].
 __global__ void prep_factors_kernel(const float* __restrict__ u, const float* __restrict__ t, int k_total, int k16,
                                     int d, uint8_t* __restrict__ wprep, float* __restrict__ tprep) {
@@ -146,10 +193,12 @@ __global__ void prep_factors_kernel(const float* __restrict__ u, const float* __
     b2[e] = __float2bfloat16_rn(x - __bfloat162float(b1[e]));
   }
   const int tile = (k / 16) * 4 + j / 16, r = (k % 16) * 16 + j % 16;
-  const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4);
-  uint8_t* base = wprep + static_cast<int64_t>(tile) * kWBytes;
+  // the tile's 256 columns are split between the two CTAs of a pair: half = r / 128
+  const int rh = r & 127;
+  const uint32_t off = (rh >> 3) * 1024 + (rh & 7) * 128 + ((c8 ^ (rh & 7)) << 4);
+  uint8_t* base = wprep + static_cast<int64_t>(tile) * kWBytes + (r >> 7) * kWHalfBytes;
   *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(b1);
-  *reinterpret_cast<uint4*>(base + kWPart + off) = *reinterpret_cast<const uint4*>(b2);
+  *reinterpret_cast<uint4*>(base + kWHalfPart + off) = *reinterpret_cast<const uint4*>(b2);
   if (c8 == 0) tprep[static_cast<int64_t>(tile) * 256 + r] = (k < k_total && j < d) ? t[static_cast<int64_t>(k) * d + j] : 0.f;
 }
 
@@ -166,35 +215,42 @@ struct LogitParams {
   int triangular;           // factors are upper triangular: tile jr skips the K steps below jr
 };
 
-__global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const LogitParams p) {
+// One CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 256, N = 256) per 256-row tile: CTA r owns
+// rows [128 r, +128) (A operand, accumulator, epilogue) and loads half of every factor tile, so
+// the L2 -> SM traffic of the factor stream -- what bounded the single-CTA version at 8.4 TB/s --
+// is halved.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mixture_logits_kernel(const LogitParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_cg = (p.k + 15) / 16;          // component groups of 16
   const int k_steps = p.d / 16;              // = number of j ranges with data
   const int n_seq = n_cg * k_steps;          // MMA tiles per row tile, in order (cg, jr)
-  const int64_t n_tiles = (p.n + kTileRows - 1) / kTileRows;
-  const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_ptiles = (p.n + 2 * kTileRows - 1) / (2 * kTileRows);      // 256-row pair tiles
+  const int64_t my_tiles = n_ptiles > pair ? (n_ptiles - pair + n_pairs - 1) / n_pairs : 0;
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int b = 0; b < 2; ++b) {
-        ptx::mbar_init(&sm.a_full[b], kConvWarps);
+        ptx::mbar_init(&sm.a_full[b], 2 * kConvWarps);        // leader: both CTAs' converter warps
         ptx::mbar_init(&sm.a_empty[b], 1);
         ptx::mbar_init(&sm.acc_full[b], 1);
-        ptx::mbar_init(&sm.acc_empty[b], kEpiWarps);
+        ptx::mbar_init(&sm.acc_empty[b], 2 * kEpiWarps);      // leader: both CTAs' epilogue warps
         ptx::mbar_init(&sm.lse_ready[b], 4);
         ptx::mbar_init(&sm.lse_taken[b], 4);
       }
       for (int s = 0; s < kWStages; ++s) {
         ptx::mbar_init(&sm.w_full[s], 1);
         ptx::mbar_init(&sm.w_empty[s], 1);
+        ptx::mbar_init(&sm.w_peer[s], 1);
       }
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
+    tmem_alloc_pair(&sm.tmem_base, kTmemCols);
   }
   if (threadIdx.x == 0) sm.sum_lse = 0.0;
   // zero the padding features of both X tile buffers once (d < 64: chunks beyond d stay zero)
@@ -203,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
   fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers initialised before any remote arrive
   ptx::tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
 
@@ -217,8 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
 #pragma unroll
     for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(p.tprep + h * 128 + i * 32 + lane);      // tile (0, 0)
     for (int64_t t = 0; t < my_tiles; ++t) {
-      const int64_t tile = blockIdx.x + t * gridDim.x;
-      const int64_t row = tile * kTileRows + q * 32 + lane;
+      const int64_t ptile = pair + t * n_pairs;
+      const int64_t row = (ptile * 2 + rank) * kTileRows + q * 32 + lane;
       const bool valid = row < p.n;
       float run_m = -INFINITY, run_s = 0.f;
       for (int cg = 0; cg < n_cg; ++cg) {
@@ -259,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
           }
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&sm.acc_empty[ab]);
+          if (lane == 0) mbar_arrive_cluster_relaxed(&sm.acc_empty[ab], 0);      // TMEM reads done (wait::ld above)
         }
         // the 8 logits of this row are complete: store, fold into the online log-sum-exp
         if (comp0 < p.k) {
@@ -319,17 +376,28 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
         for (int g = 0; g < n_seq; ++g, ++gi) {
           const int s = static_cast<int>(gi % kWStages);
           ptx::mbar_wait(&sm.w_empty[s], (static_cast<uint32_t>(gi / kWStages) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&sm.w_full[s], kWBytes);
+          ptx::mbar_arrive_expect_tx(&sm.w_full[s], kWHalfBytes);
           const int wtile = (g / k_steps) * 4 + g % k_steps;
-          const uint8_t* src = p.wprep + static_cast<int64_t>(wtile) * kWBytes;
-          bulk_load(sm.w[s], src, kWPart, &sm.w_full[s]);
-          bulk_load(sm.w[s] + kWPart, src + kWPart, kWPart, &sm.w_full[s]);
+          const uint8_t* src = p.wprep + static_cast<int64_t>(wtile) * kWBytes + rank * kWHalfBytes;
+          bulk_load(sm.w[s], src, kWHalfPart, &sm.w_full[s]);
+          bulk_load(sm.w[s] + kWHalfPart, src + kWHalfPart, kWHalfPart, &sm.w_full[s]);
         }
     }
-  } else if (warp == kMmaWarp) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == kMmaWarp && rank == 1) {
+    // ---------------- peer relay: tell the leader when this CTA's half of a factor tile has landed ----------------
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc(128, kGroupCols, /*bf16*/ 1, /*A K-major*/ 0, /*B K-major*/ 0);
+      int64_t gi = 0;
+      for (int64_t t = 0; t < my_tiles; ++t)
+        for (int g = 0; g < n_seq; ++g, ++gi) {
+          const int s = static_cast<int>(gi % kWStages);
+          ptx::mbar_wait(&sm.w_full[s], static_cast<uint32_t>(gi / kWStages) & 1);
+          mbar_arrive_cluster_relaxed(&sm.w_peer[s], 0);
+        }
+    }
+  } else if (warp == kMmaWarp) {          // rank == 0 (the peer's MMA warp took the relay branch above)
+    // ---------------- MMA issuer (leader CTA, one elected thread) ----------------
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc(256, kGroupCols, /*bf16*/ 1, /*A K-major*/ 0, /*B K-major*/ 0);
       int64_t gi = 0;
       for (int64_t t = 0; t < my_tiles; ++t) {
         const int tb = static_cast<int>(t & 1);
@@ -340,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
           const int ab = static_cast<int>(gi & 1);
           const int ks_begin = p.triangular ? g % k_steps : 0;     // tile jr: rows j >= 16 jr are zero left of feature 16 jr
           ptx::mbar_wait(&sm.w_full[s], static_cast<uint32_t>(gi / kWStages) & 1);
+          ptx::mbar_wait(&sm.w_peer[s], static_cast<uint32_t>(gi / kWStages) & 1);
           ptx::mbar_wait(&sm.acc_empty[ab], (static_cast<uint32_t>(gi >> 1) & 1) ^ 1);
           ptx::tc_fence_after_sync();
           const uint32_t w_base = ptx::smem_u32(sm.w[s]);
@@ -348,15 +417,15 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
             const uint64_t a1 = ptx::make_smem_desc(a_base + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
             const uint64_t a2 = ptx::make_smem_desc(a_base + kAPart + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
             const uint64_t b1 = ptx::make_smem_desc(w_base + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
-            const uint64_t b2 = ptx::make_smem_desc(w_base + kWPart + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
-            mma_bf16_ss(d_tmem, a1, b1, idesc, ks == ks_begin ? 0u : 1u);
-            mma_bf16_ss(d_tmem, a1, b2, idesc, 1u);
-            mma_bf16_ss(d_tmem, a2, b1, idesc, 1u);
+            const uint64_t b2 = ptx::make_smem_desc(w_base + kWHalfPart + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
+            mma_bf16_pair(d_tmem, a1, b1, idesc, ks == ks_begin ? 0u : 1u);
+            mma_bf16_pair(d_tmem, a1, b2, idesc, 1u);
+            mma_bf16_pair(d_tmem, a2, b1, idesc, 1u);
           }
-          ptx::mma_commit(&sm.w_empty[s]);
-          ptx::mma_commit(&sm.acc_full[ab]);
+          mma_commit_pair(&sm.w_empty[s]);
+          mma_commit_pair(&sm.acc_full[ab]);
         }
-        ptx::mma_commit(&sm.a_empty[tb]);
+        mma_commit_pair(&sm.a_empty[tb]);
       }
     }
   } else {
@@ -366,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
     const bool col_ok = c4 * 4 < p.d;
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int tb = static_cast<int>(t & 1);
-      const int64_t tile = blockIdx.x + t * gridDim.x;
+      const int64_t tile = (pair + t * n_pairs) * 2 + rank;
       float4 rx[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -388,14 +457,15 @@ __global__ void __launch_bounds__(kThreads, 1) mixture_logits_kernel(const Logit
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&sm.a_full[tb]);
+      if (lane == 0) mbar_arrive_cluster_relaxed(&sm.a_full[tb], 0);
     }
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (threadIdx.x == 0 && p.partial_sum_lse != nullptr) p.partial_sum_lse[blockIdx.x] = sm.sum_lse;
-  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
+  cluster_sync_all();          // the peer's shared memory / barriers stay alive until both are done
+  if (warp == kMmaWarp) tmem_dealloc_pair(tmem, kTmemCols);
 }
 
 __global__ void sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
@@ -406,11 +476,11 @@ __global__ void sum_partials_kernel(const double* __restrict__ partial, int n, d
   }
 }
 
-int logits_grid(int64_t n) {
+int logits_grid(int64_t n) {           // CTAs (two per pair)
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
-  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sms, tiles)));
+  const int64_t ptiles = (n + 2 * kTileRows - 1) / (2 * kTileRows);
+  return 2 * static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sms / 2, ptiles)));
 }
 
 }  // namespace
