@@ -47,19 +47,20 @@ constexpr int kWBytes = 2 * kWPart;                // 64 KB per tile: [half 0: b
 constexpr int kWHalfPart = kWPart / 2;             // 16 KB: 128 columns of one part
 constexpr int kWHalfBytes = kWBytes / 2;           // 32 KB: what one CTA of the pair loads per tile
 constexpr int kWStages = 4;
-constexpr int kEpiWarps = 8;                       // warps 0-7
-constexpr int kProdWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kConvWarp0 = 10;                     // warps 10-13
+constexpr int kEpiWarps = 16;                      // warps 0-15: (TMEM lane quadrant, 64-column slice)
+constexpr int kProdWarp = 16;
+constexpr int kMmaWarp = 17;
+constexpr int kConvWarp0 = 18;                     // warps 18-21
 constexpr int kConvWarps = 4;
-constexpr int kThreads = (kConvWarp0 + kConvWarps) * 32;   // 448
+constexpr int kThreads = (kConvWarp0 + kConvWarps) * 32;   // 704
 constexpr int kTmemCols = 512;
 
 struct __align__(1024) SmemLayout {
   uint8_t a[2][kABytes];
   uint8_t w[kWStages][kWHalfBytes];
-  float lse_m[2][kTileRows];       // partial (max, sum) of the upper column half, per row
-  float lse_s[2][kTileRows];
+  float lse_m[2][3][kTileRows];    // partial (max, sum) of column slices 1-3, per row
+  float lse_s[2][3][kTileRows];
+  float tscratch[kEpiWarps][32];   // per-warp staging of 32 t values (read back as broadcast pairs)
   double sum_lse;
   uint64_t a_full[2], a_empty[2];
   uint64_t w_full[kWStages], w_empty[kWStages];
@@ -239,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mixture
         ptx::mbar_init(&sm.a_empty[b], 1);
         ptx::mbar_init(&sm.acc_full[b], 1);
         ptx::mbar_init(&sm.acc_empty[b], 2 * kEpiWarps);      // leader: both CTAs' epilogue warps
-        ptx::mbar_init(&sm.lse_ready[b], 4);
+        ptx::mbar_init(&sm.lse_ready[b], 12);
         ptx::mbar_init(&sm.lse_taken[b], 4);
       }
       for (int s = 0; s < kWStages; ++s) {
@@ -264,103 +265,115 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mixture
   const uint32_t tmem = sm.tmem_base;
 
   if (warp < kEpiWarps) {
-    // ---------------- epilogue: lane = data row; warp = (quadrant q, column half h) ----------------
+    // ---------------- epilogue: lane = data row; warp = (quadrant q, 64-column slice h) ----------------
+    // Per value one packed FADD2 / FFMA2 half-instruction: t is staged per warp in shared memory and
+    // read back as broadcast 64-bit pairs (instead of one shuffle per value), (z - t)^2 is
+    // accumulated in f32x2 pairs.  16 warps (4 per scheduler) hide the TMEM-load and ALU latencies.
     const int q = warp & 3, h = warp >> 2;
+    float* scratch = sm.tscratch[warp];
+    const uint32_t scratch_addr = ptx::smem_u32(scratch);
     double sum_lse = 0.0;
     int64_t gi = 0;
     // t values of a tile are fetched one tile ahead (a load issued right before its use stalled the
-    // epilogue on the L2 latency four times per tile -- the top stall in the first ncu profile)
-    float tl_next[4];
+    // epilogue on the L2 latency -- the top stall in the first ncu profile)
+    float tl_next[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(p.tprep + h * 128 + i * 32 + lane);      // tile (0, 0)
+    for (int i = 0; i < 2; ++i) tl_next[i] = __ldg(p.tprep + h * 64 + i * 32 + lane);       // tile (0, 0)
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int64_t ptile = pair + t * n_pairs;
       const int64_t row = (ptile * 2 + rank) * kTileRows + q * 32 + lane;
       const bool valid = row < p.n;
       float run_m = -INFINITY, run_s = 0.f;
       for (int cg = 0; cg < n_cg; ++cg) {
-        // this warp's 8 components of the group: 16 cg + 8 h + (0 .. 7)
-        const int comp0 = cg * 16 + h * 8;
-        float cc[8], acc[8];
+        // this warp's 4 components of the group: 16 cg + 4 h + (0 .. 3)
+        const int comp0 = cg * 16 + h * 4;
+        float cc[4];
+        uint64_t acc2[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           cc[c] = comp0 + c < p.k ? __ldg(p.c + comp0 + c) : 0.f;
-          acc[c] = 0.f;
+          acc2[c] = 0ull;
         }
         for (int jr = 0; jr < k_steps; ++jr, ++gi) {
-          float tl[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) tl[i] = tl_next[i];
+          float tl[2];
+          tl[0] = tl_next[0];
+          tl[1] = tl_next[1];
           {
             int ncg = cg, njr = jr + 1;
             if (njr == k_steps) { njr = 0; ncg = (cg + 1 == n_cg) ? 0 : cg + 1; }
-            const float* src = p.tprep + static_cast<int64_t>(ncg * 4 + njr) * 256 + h * 128 + lane;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tl_next[i] = __ldg(src + i * 32);
+            const float* src = p.tprep + static_cast<int64_t>(ncg * 4 + njr) * 256 + h * 64 + lane;
+            tl_next[0] = __ldg(src);
+            tl_next[1] = __ldg(src + 32);
           }
           const int ab = static_cast<int>(gi & 1);
           ptx::mbar_wait(&sm.acc_full[ab], static_cast<uint32_t>(gi >> 1) & 1);
           ptx::tc_fence_after_sync();
-          const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + ab * kGroupCols + h * 128;
+          const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + ab * kGroupCols + h * 64;
 #pragma unroll
-          for (int quarter = 0; quarter < 4; ++quarter) {        // 32 columns = 2 components x 16 rows j
+          for (int quarter = 0; quarter < 2; ++quarter) {        // 32 columns = 2 components x 16 rows j
             uint32_t v[32];
             tmem_ld_32x32b_x32(t_addr + quarter * 32, v);
-            const float tv = tl[quarter];
+            scratch[lane] = tl[quarter];
+            __syncwarp();
             ptx::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float dz = __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, tv, j);
-              acc[quarter * 2 + (j >> 4)] = fmaf(dz, dz, acc[quarter * 2 + (j >> 4)]);
+            for (int m = 0; m < 16; m += 2) {                    // two pairs per 128-bit broadcast read
+              uint64_t t01, t23;
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(t01), "=l"(t23) : "r"(scratch_addr + m * 8));
+              uint64_t z01, z23, d01, d23;
+              asm("mov.b64 %0, {%1, %2};" : "=l"(z01) : "r"(v[2 * m]), "r"(v[2 * m + 1]));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(z23) : "r"(v[2 * m + 2]), "r"(v[2 * m + 3]));
+              asm("sub.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(z01), "l"(t01));
+              asm("sub.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(z23), "l"(t23));
+              uint64_t& acc = acc2[quarter * 2 + (m >> 3)];
+              asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(d01));
+              asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(d23));
             }
+            __syncwarp();                                        // scratch is rewritten by the next quarter
           }
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_relaxed(&sm.acc_empty[ab], 0);      // TMEM reads done (wait::ld above)
         }
-        // the 8 logits of this row are complete: store, fold into the online log-sum-exp
+        // the 4 logits of this row are complete: store, fold into the online log-sum-exp
         if (comp0 < p.k) {
-          float lg[8];
+          float lg[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) lg[c] = comp0 + c < p.k ? fmaf(-0.5f, acc[c], cc[c]) : -INFINITY;
-          if (valid) {
-            float* dst = p.logits + row * p.k + comp0;
-            if (comp0 + 8 <= p.k) {
-              *reinterpret_cast<float4*>(dst) = make_float4(lg[0], lg[1], lg[2], lg[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(lg[4], lg[5], lg[6], lg[7]);
-            } else {
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
-                if (comp0 + c < p.k) dst[c] = lg[c];
-            }
+          for (int c = 0; c < 4; ++c) {
+            const float sq = __uint_as_float(static_cast<uint32_t>(acc2[c])) + __uint_as_float(static_cast<uint32_t>(acc2[c] >> 32));
+            lg[c] = comp0 + c < p.k ? fmaf(-0.5f, sq, cc[c]) : -INFINITY;
           }
+          if (valid) *reinterpret_cast<float4*>(p.logits + row * p.k + comp0) = make_float4(lg[0], lg[1], lg[2], lg[3]);
           float m_new = run_m;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) m_new = fmaxf(m_new, lg[c]);
+          for (int c = 0; c < 4; ++c) m_new = fmaxf(m_new, lg[c]);
           float sum = run_s * __expf(run_m - m_new);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) sum += __expf(lg[c] - m_new);      // exp(-inf) = 0 for padding
+          for (int c = 0; c < 4; ++c) sum += __expf(lg[c] - m_new);      // exp(-inf) = 0 for padding
           run_s = sum;
           run_m = m_new;
         }
       }
-      // combine the two column halves of each row: h = 1 hands (m, s) to h = 0 through shared memory
+      // combine the four column slices of each row: h = 1..3 hand (m, s) to h = 0 through shared memory
       const int tb = static_cast<int>(t & 1);
       const uint32_t ph = static_cast<uint32_t>(t >> 1) & 1;
-      if (h == 1) {
+      if (h != 0) {
         ptx::mbar_wait(&sm.lse_taken[tb], ph ^ 1);
-        sm.lse_m[tb][q * 32 + lane] = run_m;
-        sm.lse_s[tb][q * 32 + lane] = run_s;
+        sm.lse_m[tb][h - 1][q * 32 + lane] = run_m;
+        sm.lse_s[tb][h - 1][q * 32 + lane] = run_s;
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&sm.lse_ready[tb]);
       } else {
         ptx::mbar_wait(&sm.lse_ready[tb], ph);
-        const float om = sm.lse_m[tb][q * 32 + lane], os = sm.lse_s[tb][q * 32 + lane];
+        float m = run_m;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) m = fmaxf(m, sm.lse_m[tb][o][q * 32 + lane]);
+        float ssum = run_s * __expf(run_m - m);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) ssum += sm.lse_s[tb][o][q * 32 + lane] * __expf(sm.lse_m[tb][o][q * 32 + lane] - m);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&sm.lse_taken[tb]);
-        const float m = fmaxf(run_m, om);
-        const float s = run_s * __expf(run_m - m) + os * __expf(om - m);
-        const float lse = m + __logf(s);
+        const float lse = m + __logf(ssum);
         if (valid) {
           if (p.lse != nullptr) p.lse[row] = lse;
           sum_lse += static_cast<double>(lse);
@@ -430,29 +443,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mixture
     }
   } else {
     // ---------------- X tile converter: 4 warps x 32 rows, lane covers float4 (lane & 15) of 2 rows ----------------
+    // (two halves of 16 rows per tile: the kernel runs 704 threads, so 80 registers per thread)
     const int wi = warp - kConvWarp0;
     const int sub = lane >> 4, c4 = lane & 15;
     const bool col_ok = c4 * 4 < p.d;
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int tb = static_cast<int>(t & 1);
       const int64_t tile = (pair + t * n_pairs) * 2 + rank;
-      float4 rx[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int64_t row = tile * kTileRows + wi * 32 + 2 * i + sub;
-        rx[i] = (col_ok && row < p.n) ? ldg_f4(p.x + row * p.d + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      ptx::mbar_wait(&sm.a_empty[tb], (static_cast<uint32_t>(t >> 1) & 1) ^ 1);
       const uint32_t a_base = ptx::smem_u32(sm.a[tb]);
-      if (col_ok) {
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        float4 rx[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int r = wi * 32 + 2 * i + sub;
-          const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
-          uint32_t b1[2], b2[2];
-          split_bf16(rx[i], b1, b2);
-          sts_u2(a_base + off, b1[0], b1[1]);
-          sts_u2(a_base + kAPart + off, b2[0], b2[1]);
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = tile * kTileRows + wi * 32 + hf * 16 + 2 * i + sub;
+          rx[i] = (col_ok && row < p.n) ? ldg_f4(p.x + row * p.d + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // a tile lasts ~100k cycles: back off between polls instead of spinning over the epilogue warps
+        if (hf == 0) ptx::mbar_wait_sleep(&sm.a_empty[tb], (static_cast<uint32_t>(t >> 1) & 1) ^ 1, 512);
+        if (col_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = wi * 32 + hf * 16 + 2 * i + sub;
+            const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
+            uint32_t b1[2], b2[2];
+            split_bf16(rx[i], b1, b2);
+            sts_u2(a_base + off, b1[0], b1[1]);
+            sts_u2(a_base + kAPart + off, b2[0], b2[1]);
+          }
         }
       }
       fence_proxy_async_smem();
