@@ -333,11 +333,8 @@ ColProjPlan plan_colproj(int64_t n, int d, int q) {
 
 template <int kNSeg, int kNQ>
 int launch_instance(const float* x, const float* r, int64_t n, const ColProjPlan& p, float* partial, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(colproj_kernel<kNSeg, kNQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 4096));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in;
+  BB_CUDA_OK(smem_opt_in.ensure(colproj_kernel<kNSeg, kNQ>, kSmemBudget + 4096));
   // measured on B200 (cfg5): 0 -> 1.674 ms, 2 -> 1.575 ms, 4 -> 1.595 ms, 8 -> 2.08 ms
   static const int prefetch_iters = getenv("BB_COLPROJ_PREFETCH") ? atoi(getenv("BB_COLPROJ_PREFETCH")) : 2;
   colproj_kernel<kNSeg, kNQ><<<p.grid, kThreads, p.smem_bytes, stream>>>(x, r, n, p.n_stages, prefetch_iters, partial);

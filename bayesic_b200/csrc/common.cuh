@@ -81,6 +81,22 @@ struct View {
 
 int device_sm_count();
 
+// Function attributes are per device: remember, per kernel, on which devices the opt-in to large
+// dynamic shared memory has been made (one process may drive several GPUs).
+struct SmemOptIn {
+  bool done[64] = {false};
+  template <typename Kernel>
+  cudaError_t ensure(Kernel kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+  }
+};
+
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace bb

@@ -562,11 +562,8 @@ int launch_gram_tc(const float* x, const float* y, int64_t n, int d, double* xtx
   ws += static_cast<int64_t>(g.n_splits) * d * sizeof(double);
   double* partial_yty = reinterpret_cast<double*>(ws);
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in_0;
+  BB_CUDA_OK(smem_opt_in_0.ensure(gram_pair_kernel, smem_bytes));
   const int grid = static_cast<int>(2 * pairs);
   // developer ablation switches (timing experiments only; results are wrong when set)
   static const int ablate = (getenv("BB_GRAM_ABLATE") ? atoi(getenv("BB_GRAM_ABLATE")) : 0) |

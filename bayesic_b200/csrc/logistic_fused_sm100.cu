@@ -544,11 +544,8 @@ int fused_grid(int64_t n) {
 template <int kNSeg>
 int launch_fused_instance(const FusedParams& p, int grid, cudaStream_t stream) {
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(logistic_fused_kernel<kNSeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in_0;
+  BB_CUDA_OK(smem_opt_in_0.ensure(logistic_fused_kernel<kNSeg>, smem_bytes));
   logistic_fused_kernel<kNSeg><<<grid, kThreads, smem_bytes, stream>>>(p);
   BB_CHECK_LAUNCH("logistic_fused_kernel");
   return BB_OK;

@@ -544,11 +544,8 @@ int launch_mixture_logits(const float* x, const float* u, const float* t, const 
   p.n = n; p.d = d; p.k = k; p.triangular = upper_triangular ? 1 : 0;
   const int grid = logits_grid(n);
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(mixture_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in_0;
+  BB_CUDA_OK(smem_opt_in_0.ensure(mixture_logits_kernel, smem_bytes));
   mixture_logits_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
   BB_CHECK_LAUNCH("mixture_logits_kernel");
   if (sum_lse != nullptr) {

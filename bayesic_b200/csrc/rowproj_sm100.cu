@@ -419,12 +419,10 @@ int launch_rowproj_tc(const float* x, const float* w, const float* y, int64_t n,
   p.x = x; p.wsplit = wsplit; p.y = y; p.out = out; p.partial_colsum = partial; p.n = n; p.d = d; p.q = q;
   const int grid = rowproj_grid(n);
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(rowproj_kernel<kEpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    BB_CUDA_OK(cudaFuncSetAttribute(rowproj_kernel<kEpiLogistic>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in_0;
+  BB_CUDA_OK(smem_opt_in_0.ensure(rowproj_kernel<kEpiStore>, smem_bytes));
+  static SmemOptIn smem_opt_in_1;
+  BB_CUDA_OK(smem_opt_in_1.ensure(rowproj_kernel<kEpiLogistic>, smem_bytes));
   if (y == nullptr) {
     rowproj_kernel<kEpiStore><<<grid, kThreads, smem_bytes, stream>>>(p);
     BB_CHECK_LAUNCH("rowproj_kernel<store>");

@@ -399,12 +399,8 @@ int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double
   double* partial_s1 = partial_s2 + static_cast<int64_t>(grid) * 128 * kFeat;
 
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout)) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(suffstats_tc_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in_0;
+  BB_CUDA_OK(smem_opt_in_0.ensure(suffstats_tc_kernel, smem_bytes));
   suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial_s2, partial_s1);
   BB_CHECK_LAUNCH("suffstats_tc_kernel");
   const int fin_blocks = (d * d + 31) / 32 + 1;

@@ -500,12 +500,10 @@ int launch_weighted_pairs(const float* x, const float* r, const float* lse, int6
   ws += static_cast<int64_t>(p.grid) * 2 * kTileCols * 128 * sizeof(float);
   double* partial_nk = reinterpret_cast<double*>(ws);
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(weighted_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    BB_CUDA_OK(cudaFuncSetAttribute(weighted_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in_0;
+  BB_CUDA_OK(smem_opt_in_0.ensure(weighted_pairs_kernel<false>, smem_bytes));
+  static SmemOptIn smem_opt_in_1;
+  BB_CUDA_OK(smem_opt_in_1.ensure(weighted_pairs_kernel<true>, smem_bytes));
   static const int prefetch_iters = getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) : 0;
   if (lse != nullptr)
     weighted_pairs_kernel<true><<<p.grid, kThreads, smem_bytes, stream>>>(x, r, lse, n, p.g, p.n_splits, prefetch_iters,

@@ -405,11 +405,8 @@ int launch_weighted_stats_tc(const float* x, const float* r, int64_t n, int d, i
   double* partial_rx = partial_g + static_cast<int64_t>(grid) * kGroup * 128 * kFeat;
   double* partial_nk = partial_rx + static_cast<int64_t>(grid) * kRowParts * kGroup * kFeat;
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
-  static bool attr_set = false;
-  if (!attr_set) {
-    BB_CUDA_OK(cudaFuncSetAttribute(weighted_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static SmemOptIn smem_opt_in_0;
+  BB_CUDA_OK(smem_opt_in_0.ensure(weighted_stats_tc_kernel, smem_bytes));
   weighted_stats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(x_map, r_map, tiles, n_groups, n_splits,
                                                                    partial_g, partial_rx, partial_nk);
   BB_CHECK_LAUNCH("weighted_stats_tc_kernel");
