@@ -80,6 +80,12 @@ SIGNATURES = {
                                                          _vp]),
     'bb_suffstats_weighted': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
                                              _vp]),
+    'bb_gmm_global_update': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'bb_svi_natural_blend': (ctypes.c_int, [_vp, _vp, _vp, _dbl, _dbl, _i64, _vp]),
+    'bb_reparam_draws': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    'bb_reparam_gradient': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    'bb_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _i64, _i32, _vp]),
 }
 
 _lib = None

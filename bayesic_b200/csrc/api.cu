@@ -425,4 +425,56 @@ BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits
   return launch_weighted_pairs(X, logits, lse, n, d, k, Nk, sum_rx, sum_rxx, workspace, workspace_bytes, st);
 }
 
+BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const double* sum_rxx, int32_t k, int32_t d,
+                         double alpha0, double beta0, double nu0, const double* m0, const double* W0_inv,
+                         double* alpha, double* beta, double* nu, double* m, double* W_inv, float* U, float* t,
+                         float* c, double* kl, int32_t* status, void* stream) {
+  if (!Nk || !sum_rx || !sum_rxx || !m0 || !W0_inv || !alpha || !beta || !nu || !m || !W_inv || !U || !t || !c ||
+      !kl || !status) {
+    set_error("gmm_global_update: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  return launch_gmm_global_update(Nk, sum_rx, sum_rxx, k, d, alpha0, beta0, nu0, m0, W0_inv, alpha, beta, nu, m,
+                                  W_inv, U, t, c, kl, status, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_svi_natural_blend(double* eta, const double* eta_prior, const double* stat, double scale, double rho,
+                         int64_t count, void* stream) {
+  if (count < 0 || (count > 0 && (!eta || !eta_prior || !stat)) || !(rho >= 0.0 && rho <= 1.0)) {
+    set_error("svi_natural_blend: bad arguments (need 0 <= rho <= 1)");
+    return BB_ERR_INVALID;
+  }
+  return launch_svi_blend(eta, eta_prior, stat, scale, rho, count, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_reparam_draws(const double* mu, const double* log_sigma, const double* eps, int32_t d, int32_t s,
+                     float* W, void* stream) {
+  if (d < 0 || s < 0 || (d > 0 && s > 0 && (!mu || !log_sigma || !eps || !W))) {
+    set_error("reparam_draws: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  return launch_reparam_draws(mu, log_sigma, eps, d, s, W, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_reparam_gradient(const double* G, const double* loglik, const double* eps, const double* mu,
+                        const double* log_sigma, int32_t d, int32_t s, double* grad_mu, double* grad_log_sigma,
+                        double* elbo, void* stream) {
+  if (d < 1 || s < 1 || !G || !loglik || !eps || !mu || !log_sigma || !grad_mu || !grad_log_sigma || !elbo) {
+    set_error("reparam_gradient: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  return launch_reparam_gradient(G, loglik, eps, mu, log_sigma, d, s, grad_mu, grad_log_sigma, elbo,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_adam_step(double* param, const double* grad, double* m, double* v, int64_t count, double lr,
+                 double beta1, double beta2, double eps, int64_t step, int32_t maximize, void* stream) {
+  if (count < 0 || step < 1 || (count > 0 && (!param || !grad || !m || !v))) {
+    set_error("adam_step: bad arguments (step counts from 1)");
+    return BB_ERR_INVALID;
+  }
+  return launch_adam_step(param, grad, m, v, count, lr, beta1, beta2, eps, step, maximize,
+                          static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -86,6 +86,21 @@ int launch_weighted_stats_auto(const float* x, const float* r, int64_t n, int d,
                                double* sum_rx, double* sum_rxx, void* workspace,
                                int64_t workspace_bytes, cudaStream_t stream);
 
+// update_kernels.cu: parameter-space steps (VMP global update, SVI blend, reparameterised gradient, Adam)
+int launch_gmm_global_update(const double* nk, const double* sum_rx, const double* sum_rxx, int k, int d,
+                             double alpha0, double beta0, double nu0, const double* m0, const double* w0_inv,
+                             double* alpha, double* beta, double* nu, double* m, double* w_inv, float* u, float* t,
+                             float* c, double* kl, int* status, cudaStream_t stream);
+int launch_svi_blend(double* eta, const double* eta_prior, const double* stat, double scale, double rho,
+                     int64_t count, cudaStream_t stream);
+int launch_reparam_draws(const double* mu, const double* log_sigma, const double* eps, int d, int s, float* w,
+                         cudaStream_t stream);
+int launch_reparam_gradient(const double* g, const double* loglik, const double* eps, const double* mu,
+                            const double* log_sigma, int d, int s, double* grad_mu, double* grad_ls, double* elbo,
+                            cudaStream_t stream);
+int launch_adam_step(double* param, const double* grad, double* m, double* v, int64_t count, double lr, double b1,
+                     double b2, double eps, int64_t step, int maximize, cudaStream_t stream);
+
 // stats_kernels.cu
 int launch_f32_to_f64(const float* in, double* out, int64_t n, cudaStream_t stream);
 int launch_gaussian_expected_loglik(const double* s1, const double* s2, double n,

@@ -22,6 +22,7 @@ import numpy as np
 
 from . import algebra as A
 from . import stats
+from . import updates
 from .backend.compiled import compile_many
 
 __all__ = ['gaussian_pass', 'GmmStep', 'LinRegSviStep', 'LogisticReparamGrad']
@@ -122,8 +123,8 @@ class LinRegSviStep(object):
         b = X.shape[0]
         xtx, xty, yty = xtx.double(), xty.double(), yty.double()
         scale = float(n_total) / float(b)
-        new1 = (1 - rho) * eta1 + rho * (eta1_prior + scale * tau * xty)
-        new2 = (1 - rho) * eta2 + rho * (eta2_prior - 0.5 * scale * tau * xtx)
+        new1 = updates.svi_natural_blend(eta1.clone(), eta1_prior, xty, scale * tau, rho)
+        new2 = updates.svi_natural_blend(eta2.clone(), eta2_prior, xtx, -0.5 * scale * tau, rho)
         chol = torch.linalg.cholesky(-2.0 * new2)                 # precision of q(w) is SPD
         cov = torch.cholesky_inverse(chol)
         mean = cov @ new1
@@ -148,13 +149,15 @@ class LogisticReparamGrad(object):
 
     def __call__(self, X, y, mu, log_sigma, eps, fused=True):
         import torch
+        if fused and stats.logistic_reparam_supported(X.shape[1], eps.shape[0]):
+            # the same two plans on the tcgen05 projection kernels, elementwise chain fused; draws
+            # and gradient assembly are device kernels too (nothing syncs with the host)
+            loglik, G = stats.logistic_reparam_stats(X, y, updates.reparam_draws(mu, log_sigma, eps))
+            elbo, grad_mu, grad_ls = updates.reparam_gradient(G, loglik, eps, mu, log_sigma)
+            return {'elbo': elbo.reshape(()), 'G': G, 'grad_mu': grad_mu, 'grad_log_sigma': grad_ls}
         sigma = torch.exp(log_sigma)
         Wm = (mu[None, :] + sigma[None, :] * eps).to(torch.float32)
-        if fused and stats.logistic_reparam_supported(X.shape[1], Wm.shape[0]):
-            # the same two plans on the tcgen05 projection kernels, elementwise chain fused
-            loglik, G = stats.logistic_reparam_stats(X, y, Wm)
-        else:
-            loglik, G = self.fn(X=X, y=y, Wm=Wm)
+        loglik, G = self.fn(X=X, y=y, Wm=Wm)
         G = G.double()
         kl = 0.5 * torch.sum(sigma ** 2 + mu ** 2 - 1.0 - 2.0 * log_sigma)
         grad_mu = G.mean(dim=1) - mu

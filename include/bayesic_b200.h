@@ -261,6 +261,51 @@ BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits
                                       double* Nk, double* sum_rx, double* sum_rxx,
                                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- parameter-space update steps either side of the data pass ----
+ * The reference names these algorithms in prose only (README.md:30-37 VMP, :47-51
+ * reparameterised gradients, :69-80 SVI).  All pointers are device pointers; nothing here
+ * synchronises with the host, so a whole iteration can be enqueued on one stream. */
+
+/* VMP global step of a K-component Gaussian mixture with a Dirichlet(alpha0) prior on the
+ * weights and Gaussian-Wishart(m0, beta0, W0, nu0) priors on the components (Bishop PRML
+ * 10.58-10.63), from the (all-reduced) statistics of the local step:
+ *   alpha_k = alpha0 + N_k, beta_k = beta0 + N_k, nu_k = nu0 + N_k,
+ *   m_k = (beta0 m0 + sum r x) / beta_k,
+ *   W_k^-1 = W0^-1 + sum r x x^T + beta0 m0 m0^T - beta_k m_k m_k^T.
+ * Also emits what the next local step consumes (bb_mixture_logits, upper_triangular = 1):
+ *   U_k upper triangular with nu_k W_k = U_k^T U_k, t_k = U_k m_k,
+ *   c_k = E[log pi_k] + 1/2 E[log|Lambda_k|] - D/2 log 2 pi - D / (2 beta_k),
+ * and kl[0..k-1] = KL(q(mu_k, Lambda_k) || p), kl[k] = KL(q(pi) || p(pi)); kl has k + 2 slots
+ * (the last one is scratch: log|W0^-1|).  status (device int32) is 0, or 1 + the index of a
+ * component whose W_k^-1 is not positive definite (its outputs are NaN).  1 <= d <= 96. */
+BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const double* sum_rxx,
+                         int32_t k, int32_t d, double alpha0, double beta0, double nu0,
+                         const double* m0, const double* W0_inv,
+                         double* alpha, double* beta, double* nu, double* m, double* W_inv,
+                         float* U, float* t, float* c, double* kl, int32_t* status, void* stream);
+
+/* SVI natural-parameter blend (Hoffman et al. 2013; README.md:69-80), in place:
+ *   eta[i] <- (1 - rho) eta[i] + rho (eta_prior[i] + scale * stat[i]),  i < count. */
+BB_API int bb_svi_natural_blend(double* eta, const double* eta_prior, const double* stat,
+                         double scale, double rho, int64_t count, void* stream);
+
+/* Reparameterised draws W[s, j] = mu[j] + exp(log_sigma[j]) * eps[s, j]  (float32 out, [S, D]). */
+BB_API int bb_reparam_draws(const double* mu, const double* log_sigma, const double* eps,
+                     int32_t d, int32_t s, float* W, void* stream);
+
+/* ELBO and its reparameterised gradient for q(w) = N(mu, diag sigma^2), prior N(0, I), from the
+ * outputs of bb_logistic_reparam_pass (G[D, S], loglik[S]):
+ *   elbo = mean_s loglik_s - KL,  grad_mu = mean_s G_s - mu,
+ *   grad_log_sigma = mean_s (G_s * eps_s) * sigma - sigma^2 + 1. */
+BB_API int bb_reparam_gradient(const double* G, const double* loglik, const double* eps,
+                        const double* mu, const double* log_sigma, int32_t d, int32_t s,
+                        double* grad_mu, double* grad_log_sigma, double* elbo, void* stream);
+
+/* One Adam step on count float64 parameters (step counts from 1); maximize != 0 ascends. */
+BB_API int bb_adam_step(double* param, const double* grad, double* m, double* v, int64_t count,
+                 double lr, double beta1, double beta2, double eps, int64_t step,
+                 int32_t maximize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,3 +155,52 @@ def logistic_reparam_gradient(X, y, mu, log_sigma, eps):
     grad_mu = G.mean(axis=1) - mu
     grad_ls = (G * eps.T).mean(axis=1) * sigma - sigma ** 2 + 1.0
     return {'Z': Z, 'elbo': ll.mean() - kl, 'G': G, 'grad_mu': grad_mu, 'grad_log_sigma': grad_ls}
+
+
+def _log_wishart_b(W, nu):
+    """log B(W, nu), the Wishart normaliser (Bishop PRML B.79)."""
+    d = W.shape[0]
+    _, logdet = np.linalg.slogdet(W)
+    return (-0.5 * nu * logdet - (0.5 * nu * d * np.log(2.0) + 0.25 * d * (d - 1) * np.log(np.pi)
+                                  + gammaln(0.5 * (nu - np.arange(d))).sum()))
+
+
+def gmm_global_update(nk, rx, rxx, alpha0, beta0, nu0, m0, W0_inv):
+    """VMP global step of a Gaussian mixture with Dirichlet(alpha0) weights and Gaussian-Wishart
+    (m0, beta0, W0, nu0) components, from the local step's statistics (Bishop PRML 10.58-10.63;
+    the reference names the algorithm at README.md:30-37 and has no code for it):
+      alpha_k = alpha0 + N_k; beta_k = beta0 + N_k; nu_k = nu0 + N_k; m_k = (beta0 m0 + sum r x) / beta_k
+      W_k^-1 = W0^-1 + N_k S_k + beta0 N_k / (beta0 + N_k) (xbar_k - m0)(xbar_k - m0)^T
+    written with sums so that N_k = 0 is fine, plus the quantities the next local step needs
+    (E[log pi_k], W_k) and the KL terms of the ELBO (10.74-10.77 regrouped as KL(q || p))."""
+    nk = np.asarray(nk, dtype=np.float64)
+    k, d = rx.shape
+    alpha, beta, nu = alpha0 + nk, beta0 + nk, nu0 + nk
+    m = (beta0 * m0[None, :] + rx) / beta[:, None]
+    W0 = np.linalg.inv(W0_inv)
+    W_inv = np.empty((k, d, d))
+    W = np.empty((k, d, d))
+    kl = np.empty(k + 1)
+    for j in range(k):
+        W_inv[j] = (W0_inv + rxx[j] + beta0 * np.outer(m0, m0) - beta[j] * np.outer(m[j], m[j]))
+        W_inv[j] = 0.5 * (W_inv[j] + W_inv[j].T)
+        W[j] = np.linalg.inv(W_inv[j])
+        _, logdet_w = np.linalg.slogdet(W[j])
+        e_logdet = digamma(0.5 * (nu[j] - np.arange(d))).sum() + d * np.log(2.0) + logdet_w
+        dm = m[j] - m0
+        kl_wishart = (_log_wishart_b(W[j], nu[j]) - _log_wishart_b(W0, nu0) + 0.5 * (nu[j] - nu0) * e_logdet
+                      - 0.5 * nu[j] * d + 0.5 * nu[j] * np.trace(W0_inv @ W[j]))
+        kl_gauss = 0.5 * (d * beta0 / beta[j] + beta0 * nu[j] * dm @ W[j] @ dm - d + d * np.log(beta[j] / beta0))
+        kl[j] = kl_wishart + kl_gauss
+    e_log_pi = digamma(alpha) - digamma(alpha.sum())
+    kl[k] = (gammaln(alpha.sum()) - gammaln(alpha).sum() - gammaln(k * alpha0) + k * gammaln(alpha0)
+             + ((alpha - alpha0) * e_log_pi).sum())
+    return {'alpha': alpha, 'beta': beta, 'nu': nu, 'm': m, 'W_inv': W_inv, 'W': W, 'e_log_pi': e_log_pi, 'kl': kl}
+
+
+def adam_step(param, grad, m, v, lr, b1, b2, eps, step, maximize=False):
+    """One Adam step (Kingma & Ba 2015), float64; returns (param, m, v)."""
+    m = b1 * m + (1 - b1) * grad
+    v = b2 * v + (1 - b2) * grad * grad
+    update = lr * (m / (1 - b1 ** step)) / (np.sqrt(v / (1 - b2 ** step)) + eps)
+    return (param + update if maximize else param - update), m, v

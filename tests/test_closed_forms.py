@@ -63,3 +63,48 @@ def test_log_responsibilities_and_weighted_stats():
     np.testing.assert_allclose(nk.sum(), 50.0, rtol=1e-12)
     np.testing.assert_allclose(rx.sum(0), X.sum(0), rtol=1e-12)
     np.testing.assert_allclose(rxx.sum(0), X.T @ X, rtol=1e-12)
+
+
+def test_gmm_global_update_matches_bishop_and_scipy():
+    """The VMP global step: W_k^-1 in Bishop's (10.62) grouping, KL = 0 at the prior, the
+    Gaussian-Wishart / Dirichlet KL terms against scipy densities by Monte Carlo, and the
+    logit constants against gmm_expected_logits."""
+    from scipy.stats import dirichlet
+    rng = np.random.RandomState(7)
+    d, k, n = 3, 2, 60
+    m0, W0_inv, alpha0, beta0, nu0 = rng.randn(d), _spd(rng, d) * d, 1.5, 2.0, d + 2.0
+    zero = O.gmm_global_update(np.zeros(k), np.zeros((k, d)), np.zeros((k, d, d)), alpha0, beta0, nu0, m0, W0_inv)
+    np.testing.assert_allclose(zero['kl'], 0.0, atol=1e-10)
+    X, R = rng.randn(n, d) + 1.0, rng.dirichlet(np.ones(k), size=n)
+    nk, rx, rxx = O.weighted_suffstats(X, R)
+    out = O.gmm_global_update(nk, rx, rxx, alpha0, beta0, nu0, m0, W0_inv)
+    xbar = rx / nk[:, None]
+    for j in range(k):
+        S = rxx[j] / nk[j] - np.outer(xbar[j], xbar[j])
+        want = W0_inv + nk[j] * S + beta0 * nk[j] / (beta0 + nk[j]) * np.outer(xbar[j] - m0, xbar[j] - m0)
+        np.testing.assert_allclose(out['W_inv'][j], want, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(out['m'], (beta0 * m0 + nk[:, None] * xbar) / (beta0 + nk)[:, None], rtol=1e-12)
+    # Monte Carlo KL of component 0 (Wishart part by densities, Gaussian part in closed form given Lambda)
+    W, nu, beta, m = out['W'][0], out['nu'][0], out['beta'][0], out['m'][0]
+    lam = wishart(df=nu, scale=W).rvs(size=60000, random_state=1)
+    lam_t = np.moveaxis(lam, 0, -1)
+    log_ratio = wishart(df=nu, scale=W).logpdf(lam_t) - wishart(df=nu0, scale=np.linalg.inv(W0_inv)).logpdf(lam_t)
+    dm = m - m0
+    gauss = 0.5 * (d * beta0 / beta + beta0 * np.einsum('i,nij,j->n', dm, lam, dm) - d + d * np.log(beta / beta0))
+    mc = log_ratio + gauss
+    assert abs(mc.mean() - out['kl'][0]) < 5 * mc.std() / np.sqrt(len(mc))
+    draws = dirichlet(out['alpha']).rvs(60000, random_state=2)
+    mc = dirichlet(out['alpha']).logpdf(draws.T) - dirichlet(np.full(k, alpha0)).logpdf(draws.T)
+    assert abs(mc.mean() - out['kl'][k]) < 5 * mc.std() / np.sqrt(len(mc))
+    # E[log pi] sums consistently and feeds the logits
+    np.testing.assert_allclose(np.exp(out['e_log_pi']).sum() < 1.0, True)
+    logits = O.gmm_expected_logits(X, out['e_log_pi'], out['m'], out['beta'], out['W'], out['nu'])
+    assert np.isfinite(logits).all()
+
+
+def test_adam_step_first_step_moves_by_lr():
+    p, g = np.array([1.0, -2.0]), np.array([0.5, -3.0])
+    new, m, v = O.adam_step(p, g, np.zeros(2), np.zeros(2), 0.1, 0.9, 0.999, 1e-12, 1)
+    np.testing.assert_allclose(new, p - 0.1 * np.sign(g), rtol=1e-9)
+    new, _, _ = O.adam_step(p, g, np.zeros(2), np.zeros(2), 0.1, 0.9, 0.999, 1e-12, 1, maximize=True)
+    np.testing.assert_allclose(new, p + 0.1 * np.sign(g), rtol=1e-9)
