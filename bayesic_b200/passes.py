@@ -10,6 +10,7 @@ data-axis contraction lands on a device kernel:
   cfg1/2  Gaussian(-Wishart) statistics + expected log-likelihood   ``gaussian_pass``
   cfg3    GMM VMP local step: logits -> responsibilities -> weighted stats ``GmmStep``
   cfg4    conjugate natural-gradient SVI step for linear regression  ``LinRegSviStep``
+  cfg4b   factor-analysis local step from the same Gram pass           ``FactorAnalysisStep``
   cfg5    reparameterised ELBO gradient, logistic regression          ``LogisticReparamGrad``
 
 Global parameters are tiny and replicated; data stays sharded/resident (CUDA tensors in, CUDA
@@ -25,7 +26,7 @@ from . import stats
 from . import updates
 from .backend.compiled import compile_many
 
-__all__ = ['gaussian_pass', 'GmmStep', 'LinRegSviStep', 'LogisticReparamGrad']
+__all__ = ['gaussian_pass', 'GmmStep', 'LinRegSviStep', 'FactorAnalysisStep', 'LogisticReparamGrad']
 
 _LOG_2PI = math.log(2.0 * math.pi)
 
@@ -131,6 +132,48 @@ class LinRegSviStep(object):
         e_wwT = cov + torch.outer(mean, mean)
         ell = 0.5 * b * (math.log(tau) - _LOG_2PI) - 0.5 * tau * (yty - 2 * mean @ xty + (e_wwT * xtx).sum())
         return {'xtx': xtx, 'xty': xty, 'yty': yty, 'eta1': new1, 'eta2': new2, 'ell': ell}
+
+
+class FactorAnalysisStep(object):
+    """cfg4, second variant (BASELINE.json: "factor-analysis local step"): the
+    local step of x = Lam z + mu + eps, z ~ N(0, I_L), eps ~ N(0, diag psi).  Because
+    E[z_n] = G (x_n - mu) is linear in x_n with a shared G = Sigma_z Lam^T Psi^-1, every statistic
+    the global step needs -- sum E[z], sum x E[z]^T, sum E[z z^T] -- is a small product with
+    {sum x, X^T X}, so the minibatch is read ONCE by the Gram kernel of ``LinRegSviStep``
+    (``dot(X.T, X)`` and ``dot(X.T, ones)``); the per-row latent means, when asked for, are the
+    plan of ``dot(X, G.T)`` (tcgen05 row projection when the shape fits)."""
+
+    def __init__(self):
+        X, G = A.var('X', 2), A.var('G', 2)
+        self.latent_fn = A.dot(X, G.T).compile()
+        self._ones = None
+
+    def __call__(self, X, Lam, psi, mu, want_latent_means=False):
+        import torch
+        n, d = X.shape
+        if self._ones is None or self._ones.shape[0] != n or self._ones.device != X.device:
+            self._ones = torch.ones(n, dtype=torch.float32, device=X.device)
+        xtx, sum_x, _ = stats.regression_suffstats(X, self._ones)
+        xtx, sum_x = xtx.double(), sum_x.double()
+        l = Lam.shape[1]
+        lam_p = Lam / psi[:, None]
+        sigma_z = torch.cholesky_inverse(torch.linalg.cholesky(
+            torch.eye(l, dtype=torch.float64, device=X.device) + Lam.T @ lam_p))
+        G = sigma_z @ lam_p.T                                          # [L, D]
+        sum_z = G @ (sum_x - n * mu)
+        sum_xz = (xtx - torch.outer(sum_x, mu)) @ G.T
+        centred = xtx - torch.outer(sum_x, mu) - torch.outer(mu, sum_x) + n * torch.outer(mu, mu)
+        sum_zz = n * sigma_z + G @ centred @ G.T
+        diag_xx = torch.diagonal(xtx)
+        xc_sq = diag_xx - 2 * mu * sum_x + n * mu * mu
+        cross = (Lam * (sum_xz - torch.outer(mu, sum_z))).sum(1)
+        quad = ((Lam @ sum_zz) * Lam).sum(1)
+        ell = -0.5 * n * (d * _LOG_2PI + torch.log(psi).sum()) - 0.5 * ((xc_sq - 2 * cross + quad) / psi).sum()
+        out = {'sum_z': sum_z, 'sum_xz': sum_xz, 'sum_zz': sum_zz, 'sum_x': sum_x, 'diag_xx': diag_xx,
+               'sigma_z': sigma_z, 'ell': ell}
+        if want_latent_means:
+            out['Ez'] = self.latent_fn(X=X, G=G.float().contiguous()) - (G @ mu).float()[None, :]
+        return out
 
 
 class LogisticReparamGrad(object):

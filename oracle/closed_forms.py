@@ -204,3 +204,30 @@ def adam_step(param, grad, m, v, lr, b1, b2, eps, step, maximize=False):
     v = b2 * v + (1 - b2) * grad * grad
     update = lr * (m / (1 - b1 ** step)) / (np.sqrt(v / (1 - b2 ** step)) + eps)
     return (param + update if maximize else param - update), m, v
+
+
+def factor_analysis_local_step(X, Lam, psi, mu):
+    """Local (E) step of factor analysis x = Lam z + mu + eps, z ~ N(0, I_L), eps ~ N(0, diag psi)
+    (the second minibatch-SVI variant BASELINE.json cfg4 names; README.md:69-80), written per row:
+      Sigma_z = (I + Lam^T Psi^-1 Lam)^-1;  E[z_n] = Sigma_z Lam^T Psi^-1 (x_n - mu)
+      sum_n E[z_n], sum_n x_n E[z_n]^T, sum_n E[z_n z_n^T] = N Sigma_z + sum_n E[z_n] E[z_n]^T,
+      sum_n x_n, diag sum_n x_n x_n^T
+    and the expected complete-data log-likelihood of the minibatch given those expectations."""
+    X = np.asarray(X, dtype=np.float64)
+    n, d = X.shape
+    l = Lam.shape[1]
+    sigma_z = np.linalg.inv(np.eye(l) + Lam.T @ (Lam / psi[:, None]))
+    G = sigma_z @ (Lam / psi[:, None]).T                     # [L, D]
+    Ez = (X - mu) @ G.T                                      # [N, L]
+    sum_z = Ez.sum(0)
+    sum_xz = X.T @ Ez
+    sum_zz = n * sigma_z + Ez.T @ Ez
+    sum_x = X.sum(0)
+    diag_xx = (X * X).sum(0)
+    # E log p(x | z) summed over rows, with residual e = x - mu - Lam z
+    xc_sq = diag_xx - 2 * mu * sum_x + n * mu * mu
+    cross = np.einsum('dl,dl->d', Lam, sum_xz - np.outer(mu, sum_z))
+    quad = np.einsum('dl,lm,dm->d', Lam, sum_zz, Lam)
+    ell = -0.5 * n * (d * LOG_2PI + np.log(psi).sum()) - 0.5 * ((xc_sq - 2 * cross + quad) / psi).sum()
+    return {'Ez': Ez, 'sum_z': sum_z, 'sum_xz': sum_xz, 'sum_zz': sum_zz, 'sum_x': sum_x, 'diag_xx': diag_xx,
+            'sigma_z': sigma_z, 'ell': ell}

@@ -108,3 +108,20 @@ def test_adam_step_first_step_moves_by_lr():
     np.testing.assert_allclose(new, p - 0.1 * np.sign(g), rtol=1e-9)
     new, _, _ = O.adam_step(p, g, np.zeros(2), np.zeros(2), 0.1, 0.9, 0.999, 1e-12, 1, maximize=True)
     np.testing.assert_allclose(new, p + 0.1 * np.sign(g), rtol=1e-9)
+
+
+def test_factor_analysis_local_step_by_brute_force():
+    rng = np.random.RandomState(9)
+    n, d, l = 120, 6, 3
+    Lam, psi, mu = rng.randn(d, l), rng.rand(d) + 0.5, rng.randn(d)
+    X = rng.randn(n, l) @ Lam.T + mu + rng.randn(n, d) * np.sqrt(psi)
+    out = O.factor_analysis_local_step(X, Lam, psi, mu)
+    # posterior mean = conditional mean of the joint Gaussian (Woodbury-free form)
+    np.testing.assert_allclose(out['Ez'], (X - mu) @ np.linalg.solve(Lam @ Lam.T + np.diag(psi), Lam), rtol=1e-10)
+    ell = 0.0
+    for i in range(n):
+        e = X[i] - mu - Lam @ out['Ez'][i]
+        ell += (-0.5 * (d * np.log(2 * np.pi) + np.log(psi).sum()) - 0.5 * (e * e / psi).sum()
+                - 0.5 * np.trace((Lam / psi[:, None]).T @ Lam @ out['sigma_z']))
+    np.testing.assert_allclose(out['ell'], ell, rtol=1e-12)
+    np.testing.assert_allclose(out['sum_zz'], n * out['sigma_z'] + out['Ez'].T @ out['Ez'], rtol=1e-12)

@@ -203,3 +203,21 @@ def test_cfg3_gmm_vmp_step_without_materialising_responsibilities():
     _close(got['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
     _close(got['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
     assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
+
+
+@pytest.mark.parametrize('n,d,l', [(20000, 256, 16), (5000, 96, 5), (8192, 1024, 32)])
+def test_cfg4_factor_analysis_local_step(n, d, l):
+    """Second cfg4 variant: all statistics from one Gram pass, latent means from the row projection."""
+    import torch
+    rng = np.random.RandomState(11)
+    Lam, psi, mu = rng.randn(d, l) / np.sqrt(l), rng.rand(d) + 0.5, rng.randn(d) * 0.3
+    X = (rng.randn(n, l) @ Lam.T + mu + rng.randn(n, d) * np.sqrt(psi)).astype(np.float32)
+    want = O.factor_analysis_local_step(X, Lam, psi, mu)
+    t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64)).cuda()
+    got = P.FactorAnalysisStep()(torch.from_numpy(X).cuda(), t(Lam), t(psi), t(mu), want_latent_means=True)
+    for key in ('sum_x', 'diag_xx', 'sum_xz', 'sum_zz', 'sigma_z'):
+        _close(got[key], want[key], scale_atol=2e-5)
+    # sum E[z] is a difference of O(n) terms that cancel to O(sqrt n): tolerance relative to the terms
+    np.testing.assert_allclose(got['sum_z'].cpu().numpy(), want['sum_z'], atol=2e-5 * n)
+    _close(got['Ez'], want['Ez'], rtol=1e-4, scale_atol=5e-5)
+    np.testing.assert_allclose(float(got['ell']), want['ell'], rtol=1e-5)
