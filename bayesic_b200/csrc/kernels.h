@@ -53,6 +53,12 @@ int64_t logistic_fused_workspace(int64_t n, int d, int s);
 int launch_logistic_fused(const float* x, const float* y, const float* w, int64_t n, int d, int s, double* loglik,
                           double* g, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 
+// logistic_fused2_sm100.cu: same pass with the X tile resident (converted once) and W streamed
+bool logistic_fused2_supported(int64_t n, int d, int s, const void* x);
+int64_t logistic_fused2_workspace(int64_t n, int d, int s);
+int launch_logistic_fused2(const float* x, const float* y, const float* w, int64_t n, int d, int s, double* loglik,
+                           double* g, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+
 // mixture_logits_sm100.cu: logit[n,k] = c_k - 1/2 |U_k x_n - t_k|^2 (+ row log-sum-exp) on tcgen05
 bool mixture_logits_supported(int64_t n, int d, int k, const void* x);
 int64_t mixture_logits_workspace(int64_t n, int d, int k);

@@ -61,6 +61,22 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
   while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 
+// Wait that lets the hardware park the thread: try_wait with a suspend-time hint blocks inside the
+// instruction until the phase completes (or the hint expires) instead of returning to a software
+// spin loop, so a waiting warp takes no issue slots from the warps it is waiting for.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } while (!ok);
+}
+
 // ---- TMA ----------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
