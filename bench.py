@@ -172,7 +172,7 @@ def time_other_configs(dev):
         out['cfg5'] = {"workload": "logistic reparameterised gradient: X[4 Mi, 512] f32, S = 64 draws",
                        "ms_per_pass": ms, "points_per_s": n / (ms * 1e-3),
                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                                    "counts": "algorithmic 4 D + 4 bytes/row: X read from HBM once (the single-kernel pass re-reads each 128-row tile from L2)"}}
+                                    "counts": "algorithmic 4 D + 4 bytes/row: X read from HBM once and converted once (resident 64-row tile; W streams from L2)"}}
         del X, W, y
     except Exception as exc:
         out['cfg5'] = "failed: %s" % exc

@@ -456,6 +456,35 @@ def test_logistic_reparam_stats(n, d, s):
     assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 3e-5 * scale + 1e-12)
 
 
+@pytest.mark.parametrize('env', [{'BB_FUSED_V2': '0'}, {'BB_LOGISTIC_UNFUSED': '1'}])
+def test_logistic_reparam_alternative_kernels(env):
+    """The kernels behind the same entry point that are not the default -- the W-resident single-kernel
+    design (BB_FUSED_V2=0) and the two-kernel row/column projection path (BB_LOGISTIC_UNFUSED=1) --
+    stay parity-green.  The switches are read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np, torch\n"
+        "from bayesic_b200 import stats as S\n"
+        "for n, d in [(129, 128), (5000, 256), (2049, 384), (20000, 512)]:\n"
+        "    rng = np.random.RandomState(n + d)\n"
+        "    X = rng.randn(n, d).astype(np.float32); W = (rng.randn(64, d) / np.sqrt(d)).astype(np.float32)\n"
+        "    y = (rng.rand(n) < 0.5).astype(np.float32)\n"
+        "    ll, G = S.logistic_reparam_stats(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(W).cuda())\n"
+        "    Z = X.astype(np.float64) @ W.astype(np.float64).T\n"
+        "    want_ll = (y[:, None] * Z - np.logaddexp(0.0, Z)).sum(0)\n"
+        "    R = y[:, None] - 1.0 / (1.0 + np.exp(-Z)); want_G = X.astype(np.float64).T @ R\n"
+        "    scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(R, axis=0)[None, :]\n"
+        "    np.testing.assert_allclose(ll.cpu().numpy(), want_ll, rtol=1e-4, atol=1e-5)\n"
+        "    assert np.all(np.abs(G.cpu().numpy() - want_G) <= 1e-4 * np.abs(want_G) + 3e-5 * scale + 1e-12)\n"
+        "print('ok')\n")
+    run = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                         text=True, timeout=600)
+    assert run.returncode == 0 and run.stdout.strip().endswith('ok'), run.stdout + run.stderr
+
+
 # ---- error behaviour of the C-ABI entry points (status codes -> exceptions, INTEGRATION.md) ----
 
 def test_entry_points_reject_bad_arguments_and_small_workspaces():
