@@ -443,6 +443,15 @@ BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const do
                                   W_inv, U, t, c, kl, status, static_cast<cudaStream_t>(stream));
 }
 
+BB_API int bb_gather_rows(const float* X, int64_t n, int32_t d, const int64_t* index, int64_t m, float* out,
+                   int32_t* n_out_of_range, void* stream) {
+  if (n < 0 || d < 0 || m < 0 || !n_out_of_range || (m > 0 && d > 0 && (!X || !index || !out))) {
+    set_error("gather_rows: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  return launch_gather_rows(X, n, d, index, m, out, n_out_of_range, static_cast<cudaStream_t>(stream));
+}
+
 BB_API int bb_svi_natural_blend(double* eta, const double* eta_prior, const double* stat, double scale, double rho,
                          int64_t count, void* stream) {
   if (count < 0 || (count > 0 && (!eta || !eta_prior || !stat)) || !(rho >= 0.0 && rho <= 1.0)) {

@@ -97,6 +97,8 @@ int launch_gmm_global_update(const double* nk, const double* sum_rx, const doubl
                              double alpha0, double beta0, double nu0, const double* m0, const double* w0_inv,
                              double* alpha, double* beta, double* nu, double* m, double* w_inv, float* u, float* t,
                              float* c, double* kl, int* status, cudaStream_t stream);
+int launch_gather_rows(const float* x, int64_t n, int d, const int64_t* idx, int64_t m, float* out, int* bad,
+                       cudaStream_t stream);
 int launch_svi_blend(double* eta, const double* eta_prior, const double* stat, double scale, double rho,
                      int64_t count, cudaStream_t stream);
 int launch_reparam_draws(const double* mu, const double* log_sigma, const double* eps, int d, int s, float* w,

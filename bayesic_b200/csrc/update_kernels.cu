@@ -307,6 +307,29 @@ __global__ void adam_step_kernel(double* param, const double* grad, double* m, d
   }
 }
 
+// out[j, :] = x[idx[j], :]; rows with an index outside [0, n) are NaN-filled and counted in *bad
+__global__ void gather_rows_kernel(const float* __restrict__ x, int64_t n, int d, const int64_t* __restrict__ idx,
+                                   int64_t m, float* __restrict__ out, int* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int64_t j = warp; j < m; j += n_warps) {
+    const int64_t src = idx[j];
+    const bool ok = src >= 0 && src < n;
+    if (!ok && lane == 0) atomicAdd(bad, 1);
+    float* dst = out + j * d;
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(x + (ok ? src : 0) * d);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int c = lane; c < d / 4; c += 32)
+        d4[c] = ok ? __ldg(s4 + c) : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+    } else {
+      for (int c = lane; c < d; c += 32) dst[c] = ok ? __ldg(x + src * d + c) : CUDART_NAN_F;
+    }
+  }
+}
+
 SmemOptIn g_optin_update, g_optin_prior;
 
 inline int elementwise_grid(int64_t count) {
@@ -348,6 +371,16 @@ int launch_gmm_global_update(const double* nk, const double* sum_rx, const doubl
   p.status = status;
   gmm_global_update_kernel<<<k, kUpdThreads, smem, stream>>>(p);
   BB_CHECK_LAUNCH("gmm_global_update_kernel");
+  return BB_OK;
+}
+
+int launch_gather_rows(const float* x, int64_t n, int d, const int64_t* idx, int64_t m, float* out, int* bad,
+                       cudaStream_t stream) {
+  BB_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+  if (m == 0 || d == 0) return BB_OK;
+  const int64_t warps = std::min<int64_t>(m, 148 * 32);
+  gather_rows_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, idx, m, out, bad);
+  BB_CHECK_LAUNCH("gather_rows_kernel");
   return BB_OK;
 }
 

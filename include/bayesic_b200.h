@@ -284,6 +284,12 @@ BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const do
                          double* alpha, double* beta, double* nu, double* m, double* W_inv,
                          float* U, float* t, float* c, double* kl, int32_t* status, void* stream);
 
+/* Minibatch selection on the device (README.md:71-73 "subsample the data"): out[j, :] = X[index[j], :]
+ * for j < m.  Indices outside [0, n) are counted in *n_out_of_range (device int32) and their rows
+ * NaN-filled; nothing is read back by the library. */
+BB_API int bb_gather_rows(const float* X, int64_t n, int32_t d, const int64_t* index, int64_t m,
+                   float* out, int32_t* n_out_of_range, void* stream);
+
 /* SVI natural-parameter blend (Hoffman et al. 2013; README.md:69-80), in place:
  *   eta[i] <- (1 - rho) eta[i] + rho (eta_prior[i] + scale * stat[i]),  i < count. */
 BB_API int bb_svi_natural_blend(double* eta, const double* eta_prior, const double* stat,

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_streaming.py -q -x -m gpu > gpurun_out/pytest_stream.log 2>&1; echo "pytest exit $?"; tail -25 gpurun_out/pytest_stream.log
+timeout 300 python tests/gpu_cfg_timing.py loops 2>&1 | tee gpurun_out/loops_timing.log

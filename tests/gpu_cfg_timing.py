@@ -73,7 +73,33 @@ def cfg3():
     print('  log-softmax: %.2f ms' % ms, flush=True)
 
 
+def loops():
+    """Whole iterations built from the update kernels (bayesic_b200/updates.py)."""
+    import bayesic_b200.updates as U
+    n, d, k = 1 << 21, 64, 256
+    g = torch.Generator(device='cuda').manual_seed(0)
+    centres = torch.randn(k, d, device='cuda', generator=g) * 3
+    X = centres[torch.randint(0, k, (n,), device='cuda', generator=g)] + torch.randn(n, d, device='cuda', generator=g)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device='cuda')
+    vmp = U.GmmVmp(k, d, 1.0, 1.0, d + 2.0, t(np.zeros(d)), t(np.eye(d)))
+    R0 = torch.softmax(torch.randn(1 << 16, k, device='cuda', generator=g), 1)
+    vmp.initialise(*S.weighted_suffstats(X[:1 << 16], R0))
+    ms = timeit(lambda: vmp.step(X), reps=3)
+    print('cfg3 GmmVmp.step, local + all-reduce layout + global update (N = %d): %.2f ms/iteration  %.2f M rows/s'
+          % (n, ms, n / ms / 1e3), flush=True)
+    nk, rx, rxx = S.weighted_suffstats(X[:1 << 16], R0)
+    ms = timeit(lambda: U.gmm_global_update(nk, rx, rxx, 1.0, 1.0, d + 2.0, t(np.zeros(d)), t(np.eye(d))), reps=10)
+    print('  gmm_global_update kernel (K = %d, D = %d): %.3f ms' % (k, d, ms), flush=True)
+    n, d, s = 1 << 22, 512, 64
+    X = torch.randn(n, d, device='cuda')
+    y = (torch.rand(n, device='cuda') < 0.5).float()
+    loop = U.LogisticReparamSgd(t(np.zeros(d)), t(np.full(d, -2.0)), t(np.random.RandomState(0).randn(s, d)))
+    ms = timeit(lambda: loop.step(X, y), reps=3)
+    print('cfg5 LogisticReparamSgd.step, draws + pass + gradient + Adam: %.2f ms/iteration  %.1f M rows/s'
+          % (ms, n / ms / 1e3), flush=True)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['cfg4', 'cfg5', 'cfg3']
+    which = sys.argv[1:] or ['cfg4', 'cfg5', 'cfg3', 'loops']
     for name in which:
         globals()[name]()
