@@ -38,7 +38,6 @@ namespace bb {
 namespace {
 
 constexpr int kTileRows = 128;
-constexpr int kGroupComps = 4;                     // components per MMA group
 constexpr int kGroupCols = 256;                    // = 4 x 64 padded factor rows
 constexpr int kAPart = kTileRows * 128;            // 16 KB: one bf16 part of the X tile (128-byte rows)
 constexpr int kABytes = 2 * kAPart;                // 32 KB
@@ -70,15 +69,6 @@ struct __align__(1024) SmemLayout {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
