@@ -82,6 +82,8 @@ SIGNATURES = {
                                              _vp]),
     'bb_gmm_global_update': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'bb_allreduce_sum_p2p': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i64, ctypes.c_uint32, _dbl, _vp, _vp,
+                                            _vp, _vp, _dbl, _dbl, _i32, _vp, _vp]),
     'bb_gather_rows': (ctypes.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
     'bb_svi_natural_blend': (ctypes.c_int, [_vp, _vp, _vp, _dbl, _dbl, _i64, _vp]),
     'bb_reparam_draws': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),

@@ -443,6 +443,20 @@ BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const do
                                   W_inv, U, t, c, kl, status, static_cast<cudaStream_t>(stream));
 }
 
+BB_API int bb_allreduce_sum_p2p(const void* peer_buffers, const void* peer_flags, int32_t rank, int32_t world,
+                         int64_t count, int64_t slot_stride, uint32_t epoch, double spin_limit_ms, double* out,
+                         int32_t* status, const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
+                         double e_logdet, int32_t d, double* elbo, void* stream) {
+  if (!peer_buffers || !peer_flags || !out || !status || (elbo && (!e_lambda || !e_lambda_mu))) {
+    set_error("allreduce_sum_p2p: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  return launch_p2p_allreduce(static_cast<const double* const*>(peer_buffers),
+                              static_cast<uint32_t* const*>(const_cast<void*>(peer_flags)), rank, world, count,
+                              slot_stride, epoch, spin_limit_ms, out, status, e_lambda, e_lambda_mu, e_mu_l_mu,
+                              e_logdet, d, elbo, static_cast<cudaStream_t>(stream));
+}
+
 BB_API int bb_gather_rows(const float* X, int64_t n, int32_t d, const int64_t* index, int64_t m, float* out,
                    int32_t* n_out_of_range, void* stream) {
   if (n < 0 || d < 0 || m < 0 || !n_out_of_range || (m > 0 && d > 0 && (!X || !index || !out))) {

@@ -109,6 +109,12 @@ int launch_reparam_gradient(const double* g, const double* loglik, const double*
 int launch_adam_step(double* param, const double* grad, double* m, double* v, int64_t count, double lr, double b1,
                      double b2, double eps, int64_t step, int maximize, cudaStream_t stream);
 
+// p2p_reduce.cu: one-shot all-reduce over peer memory (+ fused expected log-likelihood)
+int launch_p2p_allreduce(const double* const* bufs, uint32_t* const* flags, int rank, int world, int64_t count,
+                         int64_t slot_stride, uint32_t epoch, double spin_limit_ms, double* out, int* status,
+                         const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu, double e_logdet, int d,
+                         double* elbo, cudaStream_t stream);
+
 // stats_kernels.cu
 int launch_f32_to_f64(const float* in, double* out, int64_t n, cudaStream_t stream);
 int launch_gaussian_expected_loglik(const double* s1, const double* s2, double n,

@@ -13,7 +13,7 @@ packed float64 buffer so the collective is a single latency-bound call.
 """
 import numpy as np
 
-__all__ = ['shard_bounds', 'PackedStats', 'allreduce_packed', 'gaussian_suffstats_sharded',
+__all__ = ['shard_bounds', 'PackedStats', 'allreduce_packed', 'PeerReducer', 'gaussian_suffstats_sharded',
            'regression_suffstats_sharded', 'mixture_suffstats_sharded', 'logistic_reparam_sharded']
 
 
@@ -74,6 +74,75 @@ def allreduce_packed(buffer, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buffer, op=dist.ReduceOp.SUM, group=group)
     return buffer
+
+
+class PeerReducer(object):
+    """One-shot all-reduce over NVLink peer memory fused with the consumer (``bb_allreduce_sum_p2p``,
+    ``csrc/p2p_reduce.cu``) for the small per-minibatch payloads of this path: one single-CTA
+    kernel per rank replaces "NCCL all-reduce, then the ELBO kernel".
+
+    The peer mapping comes from ``torch.distributed._symmetric_memory`` (CUDA IPC plumbing): a
+    double-buffered float64 payload tensor and a uint32 flag tensor per rank, each mapped into every
+    process.  Write this rank's partial statistics into ``slot()`` (views of the payload for the
+    coming epoch), then call ``reduce`` / ``reduce_loglik``; ``reduced`` holds the sum.  Raises at
+    construction if symmetric memory is unavailable -- callers fall back to ``allreduce_packed``."""
+
+    def __init__(self, layout, device, group=None, spin_limit_ms=2000.0):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.layout = layout
+        self.numel = int(layout.numel)
+        self.stride = (self.numel + 31) // 32 * 32
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        self.spin_limit_ms = float(spin_limit_ms)
+        with torch.cuda.device(self.device):
+            self.payload = symm.empty(2 * self.stride, dtype=torch.float64, device=self.device)
+            self.flags = symm.empty(max(64, self.world), dtype=torch.int32, device=self.device)
+            self.payload.zero_()
+            self.flags.zero_()
+            self._payload_handle = symm.rendezvous(self.payload, group)
+            self._flags_handle = symm.rendezvous(self.flags, group)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)                    # every rank's flags are zero before anyone publishes
+            self.reduced = torch.zeros(self.numel, dtype=torch.float64, device=self.device)
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+
+    def slot(self):
+        """Views (by field name) of this rank's payload slot for the NEXT reduction."""
+        lo = ((self.epoch + 1) & 1) * self.stride
+        return self.layout.views(self.payload[lo:lo + self.numel])
+
+    def _call(self, loglik):
+        from . import stats
+        from .backend import library as L
+        lib = L.load()
+        self.epoch += 1
+        if loglik is None:
+            e_lambda = e_lambda_mu = elbo = None
+            e_mu_l_mu = e_logdet = 0.0
+            d = 0
+        else:
+            e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, d, elbo = loglik
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        L.check(lib.bb_allreduce_sum_p2p(self._payload_handle.buffer_ptrs_dev, self._flags_handle.buffer_ptrs_dev,
+                                         self.rank, self.world, self.numel, self.stride, self.epoch & 0xFFFFFFFF,
+                                         self.spin_limit_ms, self.reduced.data_ptr(), self.status.data_ptr(),
+                                         ptr(e_lambda), ptr(e_lambda_mu), float(e_mu_l_mu), float(e_logdet), int(d),
+                                         ptr(elbo), stats._stream(self.device)), 'bb_allreduce_sum_p2p')
+        return self.layout.views(self.reduced)
+
+    def reduce(self):
+        """Sum the ranks' current slots; returns views of the reduced buffer."""
+        return self._call(None)
+
+    def reduce_loglik(self, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, d, out):
+        """Same, and the Gaussian expected log-likelihood of the reduced statistics into ``out``
+        (float64[1]) in the same kernel (layout ``PackedStats.gaussian``)."""
+        return self._call((e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, d, out))
 
 
 def gaussian_suffstats_sharded(X_local, layout=None, buffer=None, group=None):

@@ -292,7 +292,7 @@ def run_ours(args):
     elbo = torch.zeros(1, dtype=torch.float64, device=dev)
     total_rows = float(n * world)
 
-    def step(kernel_events=None):
+    def step_nccl(kernel_events=None):
         if kernel_events is not None:
             kernel_events[0].record()
         S.gaussian_suffstats(X, out=(s1, s2))
@@ -303,6 +303,51 @@ def run_ours(args):
             allreduce_packed(packed)
         S.gaussian_expected_loglik(total_rows, s1, s2, e_lambda_d, e_lambda_mu_d, e_mu_l_mu,
                                    e_logdet, out=elbo)
+
+    # N > 1: the exchange is 33 KB, i.e. pure latency -- one single-CTA kernel per rank sums the peers'
+    # partial statistics over NVLink peer memory and evaluates the ELBO (csrc/p2p_reduce.cu) instead of
+    # "NCCL all-reduce, then the ELBO kernel".  Checked against the NCCL path before it is used;
+    # BB_P2P_ALLREDUCE=0 (or any failure to set up peer memory) keeps NCCL.
+    peer = None
+    collective = "one NCCL all-reduce of %d float64 per step" % packed.numel() if distributed else "none (1 GPU)"
+    if distributed and os.environ.get('BB_P2P_ALLREDUCE', '1') != '0':
+        ok = 1.0
+        try:
+            from bayesic_b200.parallel import PeerReducer
+            peer = PeerReducer(layout, dev)
+        except Exception as exc:                       # noqa: BLE001 -- any setup problem means "use NCCL"
+            sys.stderr.write("bench: peer-memory all-reduce unavailable (%s); using NCCL\n" % exc)
+            ok = 0.0
+        flag = torch.tensor([ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag) == 0.0:
+            peer = None
+
+    def step_peer(kernel_events=None):
+        views_p = peer.slot()
+        if kernel_events is not None:
+            kernel_events[0].record()
+        S.gaussian_suffstats(X, out=(views_p['s1'], views_p['s2']))
+        if kernel_events is not None:
+            kernel_events[1].record()
+        views_p['count'].fill_(float(n))
+        peer.reduce_loglik(e_lambda_d, e_lambda_mu_d, e_mu_l_mu, e_logdet, D, elbo)
+
+    if peer is not None:
+        step_nccl()
+        want = float(elbo)
+        step_peer()
+        got = float(elbo)
+        agree = torch.tensor([1.0 if abs(got - want) <= 1e-9 * abs(want) and int(peer.status.item()) == 0 else 0.0],
+                             dtype=torch.float64, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if float(agree) == 0.0:
+            sys.stderr.write("bench: peer-memory all-reduce disagreed with NCCL (%r vs %r); using NCCL\n" % (got, want))
+            peer = None
+        else:
+            collective = ("one-shot all-reduce of %d float64 over NVLink peer memory fused with the ELBO kernel "
+                          "(1 launch per rank; checked against the NCCL all-reduce at start-up)" % packed.numel())
+    step = step_peer if peer is not None else step_nccl
 
     def barrier():
         if distributed:
@@ -399,8 +444,7 @@ def run_ours(args):
                        "rows_per_gpu": n, "d": D, "arithmetic": "error-compensated TF32 (hi/lo split) on "
                        "tcgen05, fp32 TMEM accumulate drained to f64",
                        "l2": "inputs (%.1f GiB per GPU) larger than the 126 MB L2" % (n * D * 4 / 2 ** 30),
-                       "collective": "one NCCL all-reduce of %d float64 per step" % packed.numel()
-                       if distributed else "none (1 GPU)"},
+                       "collective": collective},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if n == N_PER_GPU else None,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured'

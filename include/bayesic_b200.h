@@ -284,6 +284,27 @@ BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const do
                          double* alpha, double* beta, double* nu, double* m, double* W_inv,
                          float* U, float* t, float* c, double* kl, int32_t* status, void* stream);
 
+/* Multi-GPU combine of the per-rank partial statistics (distribution/base.py:328-332 sums over the
+ * iid axis) as ONE kernel per rank over NVLink peer memory, fused with the consumer:
+ * publish "epoch e complete" into every peer's flag array (system-scope release), wait for all
+ * peers, sum the world's partial buffers by direct peer loads in rank order (bit-identical on all
+ * ranks) into out[count], and -- when elbo != NULL -- evaluate bb_gaussian_expected_loglik from the
+ * reduced packed layout [S2 (d*d) | S1 (d) | row count] in the same kernel.
+ *   peer_buffers  device array of `world` pointers to float64 buffers of 2 * slot_stride elements
+ *                 (slot = epoch & 1), each rank's own buffer and its peers' mapped into this process;
+ *                 this rank's partial statistics for the epoch must already be in its slot
+ *                 (stream order);
+ *   peer_flags    device array of `world` pointers to uint32[>= world] flag arrays, zeroed before
+ *                 the first call; epoch must advance by 1 per call on every rank, starting at 1;
+ *   spin_limit_ms a lost peer sets *status (device int32) to 1 + its rank instead of hanging.
+ * Meant for the small payloads of this path (cfg2 33 KB, cfg5 260 KB); NCCL serves the MB-sized
+ * ones. */
+BB_API int bb_allreduce_sum_p2p(const void* peer_buffers, const void* peer_flags, int32_t rank,
+                         int32_t world, int64_t count, int64_t slot_stride, uint32_t epoch,
+                         double spin_limit_ms, double* out, int32_t* status,
+                         const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
+                         double e_logdet, int32_t d, double* elbo, void* stream);
+
 /* Minibatch selection on the device (README.md:71-73 "subsample the data"): out[j, :] = X[index[j], :]
  * for j < m.  Indices outside [0, n) are counted in *n_out_of_range (device int32) and their rows
  * NaN-filled; nothing is read back by the library. */
