@@ -98,7 +98,7 @@ def streamed_pass(pass_fn, arrays, chunk_rows, device=None):
             if not isinstance(out, (tuple, list)):
                 out, single = (out,), True
             totals = [o.to(torch.float64).clone() for o in out]
-        compute.wait_stream(copy)
+        copy.synchronize()                           # the sources (pinned or staged) are no longer being read
     return totals[0] if single else tuple(totals)
 
 
