@@ -37,6 +37,20 @@ def test_no_cpu_fallback_without_a_gpu():
         fn(X=np.ones((4, 4), dtype='float32'))  # ... but evaluation must refuse to run on CPU
     with pytest.raises(RuntimeError):
         S.gaussian_suffstats(np.ones((4, 4), dtype='float32'))
+    # the layers built on top refuse likewise: update kernels, streaming, the passes
+    import bayesic_b200.passes as P
+    import bayesic_b200.streaming as T
+    import bayesic_b200.updates as U
+    cpu = torch.zeros(2, 3, dtype=torch.float64)
+    with pytest.raises(RuntimeError):
+        U.gmm_global_update(torch.zeros(2, dtype=torch.float64), cpu, torch.zeros(2, 3, 3, dtype=torch.float64),
+                            1.0, 1.0, 4.0, torch.zeros(3, dtype=torch.float64), torch.eye(3, dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        U.svi_natural_blend(cpu, cpu, cpu, 1.0, 0.5)
+    with pytest.raises(RuntimeError):
+        T.streamed_pass(S.regression_suffstats, (np.ones((4, 4), dtype='float32'), np.ones(4, dtype='float32')), 2)
+    with pytest.raises(RuntimeError):
+        P.gaussian_pass(np.ones((4, 4), dtype='float32'), np.eye(4), np.zeros(4), 0.0, 0.0)
 
 
 def test_library_exports_every_declared_symbol():
