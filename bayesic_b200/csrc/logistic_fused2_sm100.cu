@@ -83,10 +83,11 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Same MMA with an A-operand collector hint: consecutive MMAs that share the A descriptor keep A in
-// the tensor core's collector buffer (fill on the first, lastuse on the last) instead of fetching
-// its 4 KB from shared memory again -- these M128 x N64 x K16 MMAs read 6 KB of operands for 32
-// cycles of math, i.e. they are shared-memory-bandwidth bound (192 B/cycle asked of 128).
+// Same MMA with an A-operand collector hint (SASS .A_KEEP / .A_REUSE): consecutive MMAs that share
+// the A descriptor may keep A in the tensor core's collector buffer (fill on the first, lastuse on
+// the last).  These M128 x N64 x K16 MMAs read 6 KB of operands for 32 cycles of math and run at 48
+// cycles (operand fetch at 128 B/cycle); measured, the hint brings that to 45-47 cycles
+// (tests/cuda/mma_ss_rate.cu) and the kernel gains 1-2 %.
 __device__ __forceinline__ void mma_bf16_ss_fill(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                                  uint32_t idesc, uint32_t accumulate) {
   asm volatile(
