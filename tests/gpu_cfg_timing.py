@@ -73,6 +73,24 @@ def cfg3():
     print('  log-softmax: %.2f ms' % ms, flush=True)
 
 
+def cfg3_full():
+    """BASELINE cfg3 at its full extent: N = 64 Mi rows, K = 256, D = 64 (16 GiB of data, 64 GiB of logits)."""
+    n, d, k = 1 << 26, 64, 256
+    X = torch.randn(n, d, device='cuda')
+    Ak = torch.eye(d, device='cuda').repeat(k, 1, 1).contiguous()
+    bk = torch.randn(k, d, device='cuda')
+    ck = torch.randn(k, device='cuda')
+    step = P.GmmStep()
+    U, t, c = step.whiten(Ak, bk, ck)
+
+    def local_step():
+        logits, lse, _ = S.mixture_logits(X, U, t, c, upper_triangular=True)
+        return S.weighted_suffstats_from_logits(X, logits, lse)
+    ms = timeit(local_step, reps=2)
+    print('cfg3 full size, local step without materialising R (N = %d): %.1f ms  %.2f M rows/s'
+          % (n, ms, n / ms / 1e3), flush=True)
+
+
 def loops():
     """Whole iterations built from the update kernels (bayesic_b200/updates.py)."""
     import bayesic_b200.updates as U

@@ -436,6 +436,53 @@ def test_large_cfg3_properties():
                                atol=3e-5 * float(s1.abs().max()))
 
 
+def test_full_size_cfg3_properties():
+    """BASELINE cfg3 at its full extent (N = 64 Mi, D = 64, K = 256: 16 GiB of data, 64 GiB of logits,
+    N * K = 2^34 elements -- past 32-bit indexing): the local step without materialising R, checked
+    through size-independent properties.  Responsibilities sum to one per row, so the weighted
+    statistics summed over components must reproduce the plain Gaussian statistics {N, sum x,
+    sum x x^T} of the same data; sum_n lse must equal the float64 sum of the lse vector; logit rows
+    sampled from the whole range (including the last rows) must match float64; and the in-place
+    log-softmax of the full logit matrix (cfg3b: 64 GiB in place) must agree with the kernel's lse."""
+    import torch
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    n, d, k = 1 << 26, 64, 256
+    if free < 100 * 2 ** 30:
+        pytest.skip('needs ~90 GiB of free device memory')
+    g = torch.Generator(device='cuda').manual_seed(11)
+    centers = torch.randn(k, d, device='cuda', generator=g) * 2
+    X = torch.randn(n, d, device='cuda', generator=g)
+    for lo in range(0, n, 1 << 22):                      # mixture structure, built in slabs
+        idx = torch.randint(k, (min(1 << 22, n - lo),), device='cuda', generator=g)
+        X[lo:lo + idx.shape[0]] += centers[idx]
+    U = (torch.eye(d, device='cuda') + 0.05 * torch.randn(k, d, d, device='cuda', generator=g).triu()).contiguous()
+    t = torch.einsum('kji,ki->kj', U, centers).contiguous()
+    c = torch.randn(k, device='cuda', generator=g)
+    logits, lse, total = S.mixture_logits(X, U, t, c, upper_triangular=True)
+    rows = torch.cat([torch.randint(n, (2048,), device='cuda', generator=g),
+                      torch.arange(n - 64, n, device='cuda'), torch.arange(0, 64, device='cuda')])
+    z = torch.einsum('kji,ni->nkj', U.double(), X[rows].double()) - t.double()[None]
+    want = c.double()[None] - 0.5 * (z * z).sum(-1)
+    assert bool(((logits[rows].double() - want).abs() <= 1e-4 * want.abs() + 1e-3).all())
+    want_lse = torch.logsumexp(want, 1)
+    assert bool(((lse[rows].double() - want_lse).abs() <= 1e-4 * want_lse.abs() + 1e-3).all())
+    assert abs(float(total) - float(lse.double().sum())) <= 1e-6 * abs(float(total))
+    nk, rx, rxx = S.weighted_suffstats_from_logits(X, logits, lse)
+    cnt, s1, s2 = S.gaussian_suffstats(X)
+    assert abs(float(nk.sum()) - n) <= 2e-5 * n
+    np.testing.assert_allclose(rx.sum(0).cpu().numpy(), s1.cpu().numpy(), rtol=5e-5, atol=3e-5 * float(s2.abs().max()) ** 0.5 * n ** 0.5)
+    np.testing.assert_allclose(rxx.sum(0).cpu().numpy(), s2.cpu().numpy(), rtol=5e-5, atol=3e-5 * float(s2.abs().max()))
+    # cfg3b at full size: in-place log-softmax of the 64 GiB logit matrix
+    log_resp, lse2, total2 = S.log_responsibilities(logits, out=logits)
+    assert bool(((lse2[rows].double() - want_lse).abs() <= 1e-4 * want_lse.abs() + 1e-3).all())
+    assert abs(float(total2) - float(total)) <= 1e-6 * abs(float(total))
+    resp_rows = torch.exp(log_resp[rows].double()).sum(1)
+    assert float((resp_rows - 1).abs().max()) <= 1e-4
+    del logits, log_resp, X
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize('n,d,s', [(1, 128, 64), (100, 128, 64), (129, 256, 64), (2049, 384, 64), (6000, 512, 64),
                                    (40000, 512, 64), (3000, 128, 128)])
 def test_logistic_reparam_stats(n, d, s):
