@@ -14,7 +14,7 @@ from .planner import plan_einsum, lower_to_plan_ir  # noqa: F401
 from .matching import (match, find_duplicate, equivalence_classes, submultisets_of_size,  # noqa: F401
                        find_injection, find_injections, find_bijection, find_bijections)
 from .ops import (dot, tensordot, mul, outer, sum, trace, diagonal, transpose, dimshuffle,  # noqa: F401
-                  div, neg, sub, log, exp, pow, abs_)
+                  div, neg, sub, log, exp, pow, abs_, lgamma)
 
 __all__ = [
     'Expression', 'var', 'constant', 'shape', 'elemwise', 'add', 'eye',
@@ -23,6 +23,6 @@ __all__ = [
     'find_duplicate', 'equivalence_classes', 'submultisets_of_size',
     'find_injection', 'find_injections', 'find_bijection', 'find_bijections',
     'dot', 'tensordot', 'mul', 'outer', 'sum', 'trace', 'diagonal', 'transpose', 'dimshuffle',
-    'div', 'neg', 'sub', 'log', 'exp', 'pow', 'abs_',
+    'div', 'neg', 'sub', 'log', 'exp', 'pow', 'abs_', 'lgamma',
     'Counter', 'defaultdict',
 ]

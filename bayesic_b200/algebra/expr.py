@@ -206,6 +206,9 @@ OP_LOG = ElemwiseOp('log', 1)
 OP_EXP = ElemwiseOp('exp', 1)
 OP_POW = ElemwiseOp('pow', 2)
 OP_ABS = ElemwiseOp('abs_', 1)
+# extension beyond the reference's vocabulary (algebra.py:1435-1448 has log/exp/pow/abs only): the
+# log-normalisers of the Gamma / Dirichlet families need log Gamma
+OP_LGAMMA = ElemwiseOp('lgamma', 1)
 
 
 class elemwise(Expression):

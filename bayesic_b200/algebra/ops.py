@@ -8,11 +8,11 @@ same names, argument order and error behaviour (``ValueError`` on bad axes).
 import builtins as _builtins
 
 from .expr import (Expression, wrap_if_literal, with_wrapped_literals, autobroadcast_or_match,
-                   elemwise, add, OP_LOG, OP_EXP, OP_POW, OP_ABS)
+                   elemwise, add, OP_LOG, OP_EXP, OP_POW, OP_ABS, OP_LGAMMA)
 from .einsum import einsum, sum_index, out_index
 
 __all__ = ['dot', 'tensordot', 'mul', 'outer', 'sum', 'trace', 'diagonal', 'transpose',
-           'dimshuffle', 'div', 'neg', 'sub', 'log', 'exp', 'pow', 'abs_']
+           'dimshuffle', 'div', 'neg', 'sub', 'log', 'exp', 'pow', 'abs_', 'lgamma']
 
 
 def _outs(start, stop):
@@ -144,6 +144,12 @@ def pow(X, Y):
 
 def abs_(X):
     return elemwise(OP_ABS, X)
+
+
+def lgamma(X):
+    """log Gamma(X), pointwise -- not in the reference's vocabulary; an extension for the
+    exponential-family log-normalisers."""
+    return elemwise(OP_LGAMMA, X)
 
 
 # ---- operator overloads (algebra.py:1451-1478) -------------------------------

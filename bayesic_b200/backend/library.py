@@ -17,7 +17,7 @@ NODE_INPUT, NODE_SCALAR, NODE_SHAPE, NODE_EYE, NODE_SUM, NODE_MUL = 0, 1, 2, 3, 
 NODE_DIMSHUFFLE, NODE_TENSORDOT, NODE_DIAGONAL, NODE_ELEMWISE = 6, 7, 8, 9
 NODE_LOGSOFTMAX, NODE_SYRK, NODE_WEIGHTED_SCATTER = 20, 21, 22
 # bb_elemwise_op
-OP_CODES = {'add': 0, 'mul': 1, 'log': 2, 'exp': 3, 'pow': 4, 'abs_': 5}
+OP_CODES = {'add': 0, 'mul': 1, 'log': 2, 'exp': 3, 'pow': 4, 'abs_': 5, 'lgamma': 6}
 
 STATUS_NAMES = {0: 'BB_OK', 1: 'BB_ERR_INVALID', 2: 'BB_ERR_CUDA', 3: 'BB_ERR_UNSUPPORTED',
                 4: 'BB_ERR_SHAPE', 5: 'BB_ERR_WORKSPACE'}

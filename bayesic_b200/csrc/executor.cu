@@ -108,6 +108,7 @@ double host_elemwise(int op, const double* v, int n) {
     case BB_OP_EXP: return exp(v[0]);
     case BB_OP_POW: return pow(v[0], v[1]);
     case BB_OP_ABS: return fabs(v[0]);
+    case BB_OP_LGAMMA: return lgamma(v[0]);
   }
   return v[0];
 }

@@ -56,6 +56,7 @@ __device__ __forceinline__ float apply_op(int op, const float* v, int n, float s
     case BB_OP_EXP: return expf(v[0]);
     case BB_OP_POW: return powf(v[0], v[1]);
     case BB_OP_ABS: return fabsf(v[0]);
+    case BB_OP_LGAMMA: return lgammaf(v[0]);
     default: return v[0];
   }
 }

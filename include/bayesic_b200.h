@@ -94,7 +94,8 @@ typedef enum {
 } bb_node_kind;
 
 typedef enum {
-  BB_OP_ADD = 0, BB_OP_MUL = 1, BB_OP_LOG = 2, BB_OP_EXP = 3, BB_OP_POW = 4, BB_OP_ABS = 5
+  BB_OP_ADD = 0, BB_OP_MUL = 1, BB_OP_LOG = 2, BB_OP_EXP = 3, BB_OP_POW = 4, BB_OP_ABS = 5,
+  BB_OP_LGAMMA = 6   /* extension: log Gamma, for exponential-family log-normalisers */
 } bb_elemwise_op;
 
 typedef struct {

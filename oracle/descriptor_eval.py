@@ -15,7 +15,7 @@ from .semantics import tensordot_declared
 KIND = {0: 'input', 1: 'scalar', 2: 'shape', 3: 'eye', 4: 'sum', 5: 'mul', 6: 'dimshuffle',
         7: 'tensordot', 8: 'diagonal', 9: 'elemwise', 20: 'logsoftmax', 21: 'syrk',
         22: 'weighted_scatter'}
-OPS = {0: 'add', 1: 'mul', 2: 'log', 3: 'exp', 4: 'pow', 5: 'abs'}
+OPS = {0: 'add', 1: 'mul', 2: 'log', 3: 'exp', 4: 'pow', 5: 'abs', 6: 'lgamma'}
 
 
 def evaluate_descriptor(nodes, outputs, input_arrays, dtype=np.float64):
@@ -68,6 +68,9 @@ def evaluate_descriptor(nodes, outputs, input_arrays, dtype=np.float64):
                 value = np.exp(par[0])
             elif op == 'pow':
                 value = np.power(par[0], par[1])
+            elif op == 'lgamma':
+                from scipy.special import gammaln
+                value = gammaln(par[0])
             else:
                 value = np.abs(par[0])
         elif kind == 'logsoftmax':

@@ -27,6 +27,7 @@ _POINTWISE = {
     'add': lambda *xs: _fold(np.add, xs),
     'mul': lambda *xs: _fold(np.multiply, xs),
     'log': np.log, 'exp': np.exp, 'pow': np.power, 'abs_': np.abs,
+    'lgamma': lambda x: __import__('scipy.special', fromlist=['gammaln']).gammaln(x),
 }
 
 

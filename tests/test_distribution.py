@@ -107,3 +107,73 @@ def test_gpu_log_likelihood_and_statistics():
     np.testing.assert_allclose(s1, Xd.sum(0), rtol=1e-4, atol=1e-3)
     np.testing.assert_allclose(s2, Xd.T @ Xd, rtol=1e-4, atol=1e-3)
     assert 21 in [n['kind'] for n in fn.plan.lowered.nodes]     # served by the SYRK kernel
+
+
+# ---- the families of distribution/conjugate.py against scipy.stats ----
+
+def _conjugate_cases(seed=3):
+    """(name, log-likelihood expression, inputs, scipy value) for every added family, iid over axis 0."""
+    from scipy import stats as st
+    from bayesic_b200.distribution import BernoulliLogit, Exponential, Gamma, Categorical, Dirichlet
+    rng = np.random.RandomState(seed)
+    x, M = A.var('x', 1), A.var('M', 2)
+    k, n = 6, 400
+    cases = []
+    xv = (rng.rand(n) < 0.3).astype(np.float32)
+    cases.append(('bernoulli', BernoulliLogit().iid().log_likelihood(x, logit=A.var('l', 0)),
+                  {'x': xv, 'l': np.float32(-0.4)}, st.bernoulli(1 / (1 + np.exp(0.4))).logpmf(xv).sum()))
+    xv = rng.exponential(0.5, n).astype(np.float32)
+    cases.append(('exponential', Exponential().iid().log_likelihood(x, rate=A.var('r', 0)),
+                  {'x': xv, 'r': np.float32(2.0)}, st.expon(scale=0.5).logpdf(xv.astype('f8')).sum()))
+    xv = rng.gamma(3.0, 1 / 1.5, n).astype(np.float32)
+    cases.append(('gamma', Gamma().iid().log_likelihood(x, shape=A.var('a', 0), rate=A.var('b', 0)),
+                  {'x': xv, 'a': np.float32(3.0), 'b': np.float32(1.5)},
+                  st.gamma(3.0, scale=1 / 1.5).logpdf(xv.astype('f8')).sum()))
+    idx = rng.randint(k, size=n)
+    lg = rng.randn(k).astype(np.float32)
+    log_p = lg.astype('f8') - np.log(np.exp(lg.astype('f8')).sum())
+    cases.append(('categorical', Categorical().iid().log_likelihood(M, logits=A.var('lg', 1)),
+                  {'M': np.eye(k, dtype=np.float32)[idx], 'lg': lg}, log_p[idx].sum()))
+    alpha = (rng.rand(k) * 3 + 0.5).astype(np.float32)
+    Mv = rng.dirichlet(alpha, size=n).astype(np.float32)
+    want = sum(st.dirichlet(alpha.astype('f8')).logpdf(r.astype('f8') / r.astype('f8').sum()) for r in Mv)
+    cases.append(('dirichlet', Dirichlet().iid().log_likelihood(M, concentration=A.var('al', 1)),
+                  {'M': Mv, 'al': alpha}, want))
+    return cases
+
+
+def test_conjugate_families_match_scipy():
+    for name, ll, inputs, want in _conjugate_cases():
+        got = float(evaluate(ll, inputs))
+        np.testing.assert_allclose(got, want, rtol=1e-6, err_msg=name)
+
+
+def test_conjugate_families_structure():
+    from bayesic_b200.distribution import BernoulliLogit, Gamma, Categorical, Dirichlet
+    x, M = A.var('x', 1), A.var('M', 2)
+    # iid statistics are the data-axis sums the device kernels serve
+    s_log, s_x = Gamma().iid().sufficient_statistics(x)
+    assert s_x._rewrite_as_special_case_ops() == _sum(x, 0)
+    assert 'log' in repr(s_log)
+    (counts,) = Categorical().iid().sufficient_statistics(M)
+    assert counts._rewrite_as_special_case_ops() == _sum(M, 0)          # class counts N_k = sum_n r_nk
+    assert BernoulliLogit().is_discrete() and Categorical().is_discrete() and not Dirichlet().is_discrete()
+    assert Dirichlet().iid().data_type == ('float32', 2) and Gamma().iid().data_type == ('float32', 1)
+    # per-copy parameters: K Gamma copies, each with its own (shape, rate), iid draws along axis 1
+    rng = np.random.RandomState(2)
+    data = rng.gamma(2.0, 1.0, size=(3, 50)).astype(np.float32)
+    a, b = np.array([1.5, 2.0, 3.0], np.float32), np.array([0.5, 1.0, 2.0], np.float32)
+    copies = Gamma().independent_observations(param_copy_ndim=1, iid_draw_ndim=1)
+    ll = copies.log_likelihood(A.var('data', 2), shape=A.var('a', 1), rate=A.var('b', 1))
+    from scipy import stats as st
+    want = sum(st.gamma(a[i], scale=1 / b[i]).logpdf(data[i].astype('f8')).sum() for i in range(3))
+    np.testing.assert_allclose(float(evaluate(ll, {'data': data, 'a': a, 'b': b})), want, rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_conjugate_families():
+    """The same log-likelihoods through compile() -> C-ABI executor (float32 device arithmetic,
+    incl. the lgamma opcode), rtol 1e-4."""
+    for name, ll, inputs, want in _conjugate_cases(seed=5):
+        got = float(ll.compile()(**inputs))
+        assert abs(got - want) <= 1e-4 * abs(want) + 1e-3, (name, got, want)
