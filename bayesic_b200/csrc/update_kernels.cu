@@ -23,7 +23,7 @@ namespace bb {
 namespace {
 
 constexpr int kUpdThreads = 256;
-constexpr int kMaxUpdateDim = 96;      // 2 D^2 float64 in shared memory: 147 KB at D = 96
+constexpr int kMaxUpdateDim = 96;      // 3 D^2 float64 in shared memory: 216 KB at D = 96
 
 __device__ __forceinline__ double digamma_pos(double x) {
   // psi(x) for x > 0: recurrence up to x >= 10, then the asymptotic series (error < 1e-15 there)
@@ -49,11 +49,10 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return total;
 }
 
-// log B(W, nu) of the Wishart normaliser given log|W| (Bishop B.79)
-__device__ __forceinline__ double log_wishart_b(double logdet_w, double nu, int d) {
-  double lg = 0.0;
-  for (int i = 0; i < d; ++i) lg += lgamma(0.5 * (nu - i));
-  return -0.5 * nu * logdet_w - (0.5 * nu * d * 0.6931471805599453 + 0.25 * d * (d - 1) * 1.1447298858494002 + lg);
+// log B(W, nu) of the Wishart normaliser given log|W| and sum_i lgamma((nu - i) / 2)  (Bishop B.79)
+__device__ __forceinline__ double log_wishart_b(double logdet_w, double nu, int d, double lgamma_sum) {
+  return -0.5 * nu * logdet_w -
+         (0.5 * nu * d * 0.6931471805599453 + 0.25 * d * (d - 1) * 1.1447298858494002 + lgamma_sum);
 }
 
 struct GmmUpdateParams {
@@ -140,8 +139,9 @@ __global__ void __launch_bounds__(kUpdThreads) gmm_prior_logdet_kernel(const dou
 __global__ void __launch_bounds__(kUpdThreads) gmm_global_update_kernel(const GmmUpdateParams p) {
   extern __shared__ double smem_upd[];
   const int d = p.d, comp = blockIdx.x, tid = threadIdx.x;
-  double* a = smem_upd;                 // W_k^-1, then its factor R (upper)
-  double* rinv = a + d * d;             // R^-1, then W_k
+  double* a = smem_upd;                 // W_k^-1, then its factor R (upper), then W0^-1 R^-T
+  double* rinv = a + d * d;             // R^-1
+  double* w0 = rinv + d * d;            // symmetrised W0^-1
   __shared__ double red[kUpdThreads / 32];
   __shared__ double mk[kMaxUpdateDim], dm[kMaxUpdateDim];
 
@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(kUpdThreads) gmm_global_update_kernel(const Gm
   double* w_inv_out = p.w_inv + static_cast<int64_t>(comp) * d * d;
   for (int i = tid; i < d * d; i += kUpdThreads) {
     const int r = i / d, c = i - r * d;
-    const double v = 0.5 * (p.w0_inv[i] + p.w0_inv[c * d + r]) + 0.5 * (sxx[i] + sxx[c * d + r]) +
+    const double w0_rc = 0.5 * (p.w0_inv[i] + p.w0_inv[c * d + r]);
+    w0[i] = w0_rc;
+    const double v = w0_rc + 0.5 * (sxx[i] + sxx[c * d + r]) +
                      p.beta0 * p.m0[r] * p.m0[c] - beta_k * mk[r] * mk[c];
     a[i] = v;
     w_inv_out[i] = v;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kUpdThreads) gmm_global_update_kernel(const Gm
   for (int idx = tid; idx < d * d; idx += kUpdThreads) {
     const int r = idx / d, j = idx - r * d;        // a[r][j] = sum_b W0inv[r][b] rinv[j][b]
     double acc = 0.0;
-    for (int b = j; b < d; ++b) acc += 0.5 * (p.w0_inv[r * d + b] + p.w0_inv[b * d + r]) * rinv[j * d + b];
+    for (int b = j; b < d; ++b) acc += w0[r * d + b] * rinv[j * d + b];
     a[idx] = acc;
   }
   __syncthreads();
@@ -227,10 +229,16 @@ __global__ void __launch_bounds__(kUpdThreads) gmm_global_update_kernel(const Gm
     if (r >= j) tr_part += rinv[j * d + r] * a[idx];
   }
   const double tr = block_sum(tr_part, red);
+  double lg_k_part = 0.0, lg_0_part = 0.0;
+  for (int i = tid; i < d; i += kUpdThreads) {
+    lg_k_part += lgamma(0.5 * (nu_k - i));
+    lg_0_part += lgamma(0.5 * (p.nu0 - i));
+  }
+  const double lg_k = block_sum(lg_k_part, red), lg_0 = block_sum(lg_0_part, red);
   if (tid == 0) {
     const double logdet_w0 = -p.prior_consts[0];
     const double logdet_wk = -logdet_winv;
-    const double kl_wishart = log_wishart_b(logdet_wk, nu_k, d) - log_wishart_b(logdet_w0, p.nu0, d) +
+    const double kl_wishart = log_wishart_b(logdet_wk, nu_k, d, lg_k) - log_wishart_b(logdet_w0, p.nu0, d, lg_0) +
                               0.5 * (nu_k - p.nu0) * e_logdet - 0.5 * nu_k * d + 0.5 * nu_k * tr;
     const double kl_gauss = 0.5 * (d * p.beta0 / beta_k + p.beta0 * nu_k * quad - d + d * log(beta_k / p.beta0));
     p.kl[comp] = kl_wishart + kl_gauss;
@@ -354,11 +362,11 @@ int launch_gmm_global_update(const double* nk, const double* sum_rx, const doubl
   }
   BB_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), stream));
   const int prior_smem = d * d * static_cast<int>(sizeof(double));
-  const int smem = 2 * prior_smem;
+  const int smem = 3 * prior_smem;
   // the opt-in is made once per device, so it must cover the largest d
   constexpr int kMaxMatrixBytes = kMaxUpdateDim * kMaxUpdateDim * static_cast<int>(sizeof(double));
   BB_CUDA_OK(g_optin_prior.ensure(gmm_prior_logdet_kernel, kMaxMatrixBytes));
-  BB_CUDA_OK(g_optin_update.ensure(gmm_global_update_kernel, 2 * kMaxMatrixBytes));
+  BB_CUDA_OK(g_optin_update.ensure(gmm_global_update_kernel, 3 * kMaxMatrixBytes));
   // kl has k + 2 slots: per-component KL, the Dirichlet KL, and log|W0^-1| (the prior constant the
   // per-component CTAs read)
   gmm_prior_logdet_kernel<<<1, kUpdThreads, prior_smem, stream>>>(w0_inv, d, kl + k + 1, status);
