@@ -13,7 +13,9 @@
 //     b2) and the MN-major operand of the second (features x rows);
 //   * W streams instead: a pre-kernel stacks the two BF16 parts of the 64 draws (= 128 MMA rows, in
 //     blocks of 16 draws: W1 rows then W2 rows) per 64-feature chunk in the UMMA layout, and a producer
-//     thread bulk-copies the L2-resident 16 KB chunks through a 4-stage mbarrier ring;
+//     thread bulk-copies the L2-resident 16 KB chunks through a 4-stage mbarrier ring -- except the
+//     first four chunks, which sit in the 128 TMEM columns Z and G leave free and feed their MMAs as
+//     the A operand straight from TMEM (no stream, no shared-memory fetch);
 //   * Z^T[(part, draw), (b1 | b2, row)] = [W1; W2] . [X1; X2]^T : ONE M128 x N128 MMA per K step gives
 //     all four partial products.  Sixteen worker warps are converter and epilogue in turn (the
 //     converter is idle exactly while the epilogue has work): as epilogue, a warp reads its TMEM lane
@@ -62,6 +64,8 @@ constexpr int kThreads = (kTmaWarp + 1) * 32;   // 576
 constexpr int kTmemCols = 512;
 constexpr int kTmemZ = 0;                       // 128 columns: [W1; W2] X1^T | [W1; W2] X2^T
 constexpr int kTmemG = 128;                     // up to 4 x 64 columns
+constexpr int kTmemW = 384;                     // up to 4 stacked-W chunks x 32 columns (A operand held in TMEM)
+constexpr int kMaxTmemChunks = 4;
 
 template <int kNSeg>
 struct __align__(1024) Smem {
@@ -104,6 +108,17 @@ __device__ __forceinline__ void mma_bf16_ss_lastuse(uint32_t d_tmem, uint64_t a_
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A operand from TMEM (lane = MMA row, 32-bit column j = the K pair (2 j, 2 j + 1), even element in
+// the low half; tests/cuda/ts_bf16_probe.cu): no shared-memory fetch for A.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -162,6 +177,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 struct Fused2Params {
+  int w_tmem_chunks;                // leading 64-feature chunks of the stacked W kept in TMEM (BB_FUSED2_W_TMEM, default 4)
   int prefetch;                     // L2 prefetch one converter step ahead of the register loads (BB_FUSED2_PREFETCH, default on)
   int collector;                    // A-operand collector reuse between MMAs that share A (BB_FUSED2_COLLECTOR, default on)
   const float* x;
@@ -209,6 +225,27 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  // The first n_tm chunks of the stacked W live in TMEM for the whole kernel (128 free columns = 4
+  // chunks): their MMAs take A from TMEM, so they neither stream through the ring nor fetch A from
+  // shared memory.  Warp q < 4 fills its lane quadrant from the UMMA image (row = lane).
+  const int n_tm = min(min(p.w_tmem_chunks, kMaxTmemChunks), kChunks);
+  if (warp < 4) {
+    const int r = warp * 32 + lane;
+    for (int c = 0; c < n_tm; ++c) {
+      const uint8_t* row = p.wprep + static_cast<int64_t>(c) * kWChunkBytes + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(row + ((j ^ (r & 7)) << 4)));
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(row + (((j + 1) ^ (r & 7)) << 4)));
+        const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        ptx::tmem_st_32x32b_x8(tmem + (static_cast<uint32_t>(warp * 32) << 16) + kTmemW + c * 32 + j * 4, v);
+      }
+    }
+    ptx::tmem_wait_st();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
 
   if (warp < kWorkerWarps) {
     // ---------------- worker warps: converter AND epilogue of every tile ----------------
@@ -414,8 +451,17 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
         ptx::mbar_wait_parked(&sm.z_empty, (static_cast<uint32_t>(t) & 1) ^ 1);
         for (int seg = 0; seg < kNSeg; ++seg) {
           ptx::mbar_wait_parked(&sm.x_full[seg], static_cast<uint32_t>(t) & 1);
-          for (int half = 0; half < 2; ++half, ++it) {
+          for (int half = 0; half < 2; ++half) {
             const int c = 2 * seg + half;
+            if (c < n_tm) {                       // A = stacked W chunk resident in TMEM
+              ptx::tc_fence_after_sync();
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t b12 = ptx::make_smem_desc(x1 + c * (2 * kChunkBytes) + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
+                mma_bf16_ts(tmem + kTmemZ, tmem + kTmemW + c * 32 + ks * 8, b12, idesc_a, (c == 0 && ks == 0) ? 0u : 1u);
+              }
+              continue;
+            }
             const int ws = static_cast<int>(it % kWStages);
             ptx::mbar_wait_parked(&sm.w_full[ws], static_cast<uint32_t>(it / kWStages) & 1);
             ptx::tc_fence_after_sync();
@@ -427,6 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
               mma_bf16_ss(tmem + kTmemZ, a, b12, idesc_a, (c == 0 && ks == 0) ? 0u : 1u);
             }
             ptx::mma_commit(&sm.w_empty[ws]);
+            ++it;
           }
         }
         ptx::mma_commit(&sm.z_full);
@@ -468,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
       int64_t it = 0;
       for (int t = 0; t < T; ++t)
-        for (int c = 0; c < kChunks; ++c, ++it) {
+        for (int c = n_tm; c < kChunks; ++c, ++it) {
           const int ws = static_cast<int>(it % kWStages);
           ptx::mbar_wait_parked(&sm.w_empty[ws], (static_cast<uint32_t>(it / kWStages) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&sm.w_full[ws], kWChunkBytes);
@@ -582,6 +629,8 @@ int launch_logistic_fused2(const float* x, const float* y, const float* w, int64
   static const int collector = getenv("BB_FUSED2_COLLECTOR") ? atoi(getenv("BB_FUSED2_COLLECTOR")) : 1;
   Fused2Params p;
   p.collector = collector;
+  static const int w_tmem = getenv("BB_FUSED2_W_TMEM") ? atoi(getenv("BB_FUSED2_W_TMEM")) : 4;
+  p.w_tmem_chunks = w_tmem;
   static const int prefetch = getenv("BB_FUSED2_PREFETCH") ? atoi(getenv("BB_FUSED2_PREFETCH")) : 1;
   p.prefetch = prefetch;
   p.x = x; p.y = y; p.wprep = wprep; p.partial_g = partial_g; p.partial_ll = partial_ll; p.n = n;
