@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 1500 python -m pytest tests -q -x -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -6 gpurun_out/pytest_gpu.log
 timeout 600 python tests/gpu_cfg_timing.py 2>&1 | tee gpurun_out/cfg_timing.log
 timeout 600 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 1600 gpurun_out/bench_n1.json
