@@ -503,6 +503,27 @@ def test_logistic_reparam_stats(n, d, s):
     assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 3e-5 * scale + 1e-12)
 
 
+def test_logistic_reparam_stats_saturated_logits():
+    """Logits far outside [-20, 20] (sigmoid saturates, exp(-|z|) underflows): softplus must stay
+    max(z, 0) + log1p(exp(-|z|)) and the residual exactly y - {0, 1}, as in float64."""
+    import torch
+    rng = np.random.RandomState(21)
+    n, d, s = 5000, 256, 64
+    X = rng.randn(n, d).astype(np.float32)
+    W = (rng.randn(s, d) * 8.0 / np.sqrt(d)).astype(np.float32)           # |z| up to ~ 40
+    W[3] *= 10.0                                                          # one draw with |z| in the hundreds
+    y = (rng.rand(n) < 0.5).astype(np.float32)
+    ll, G = S.logistic_reparam_stats(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(W).cuda())
+    Z = X.astype(np.float64) @ W.astype(np.float64).T
+    want_ll = (y[:, None] * Z - np.logaddexp(0.0, Z)).sum(0)
+    resid = y[:, None] - 1.0 / (1.0 + np.exp(-Z))
+    want_G = X.astype(np.float64).T @ resid
+    assert np.isfinite(ll.cpu().numpy()).all() and np.isfinite(G.cpu().numpy()).all()
+    np.testing.assert_allclose(ll.cpu().numpy(), want_ll, rtol=1e-4)
+    scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(resid, axis=0)[None, :]
+    assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 1e-4 * scale + 1e-12)
+
+
 @pytest.mark.parametrize('env', [{'BB_FUSED_V2': '0'}, {'BB_LOGISTIC_UNFUSED': '1'}])
 def test_logistic_reparam_alternative_kernels(env):
     """The kernels behind the same entry point that are not the default -- the W-resident single-kernel
