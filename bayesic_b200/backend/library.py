@@ -64,6 +64,8 @@ SIGNATURES = {
     'bb_release_staging': (ctypes.c_int, []),
     'bb_gaussian_expected_loglik': (ctypes.c_int, [_vp, _vp, _dbl, _vp, _vp, _dbl, _dbl, _i32,
                                                    _vp, _vp]),
+    'bb_suffstats_gaussian_loglik': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _dbl, _dbl, _vp,
+                                                    _vp, _i64, _vp]),
     'bb_suffstats_regression_workspace': (_i64, [_i64, _i32]),
     'bb_suffstats_regression': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     'bb_rowproj_workspace': (_i64, [_i64, _i32, _i32]),

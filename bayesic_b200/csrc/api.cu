@@ -149,6 +149,30 @@ BB_API int bb_suffstats_gaussian(const float* X, int64_t n, int32_t d, double* s
                           static_cast<cudaStream_t>(stream));
 }
 
+BB_API int bb_suffstats_gaussian_loglik(const float* X, int64_t n, int32_t d, double* sum_x, double* sum_xxT,
+                                 double n_total, const double* E_Lambda, const double* E_Lambda_mu,
+                                 double E_mu_L_mu, double E_logdet, double* out, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!sum_x || !sum_xxT || !E_Lambda || !E_Lambda_mu || !out) {
+    set_error("suffstats_gaussian_loglik: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  if (n > 0 && X != nullptr && d >= 1 && suffstats_tc_supported(n, d, X)) {
+    if (workspace_bytes < bb_suffstats_gaussian_workspace(n, d)) {
+      set_error("suffstats_gaussian_loglik: workspace %lld < %lld bytes", static_cast<long long>(workspace_bytes),
+                static_cast<long long>(bb_suffstats_gaussian_workspace(n, d)));
+      return BB_ERR_WORKSPACE;
+    }
+    // two launches: statistics, then finalize with the log-likelihood in its last block
+    return launch_suffstats_tc_loglik(X, n, d, sum_x, sum_xxT, n_total, E_Lambda, E_Lambda_mu, E_mu_L_mu, E_logdet,
+                                      out, workspace, workspace_bytes, st);
+  }
+  BB_TRY(suffstats_device(X, n, d, sum_x, sum_xxT, workspace, workspace_bytes, false, st));
+  return launch_gaussian_expected_loglik(sum_x, sum_xxT, n_total, E_Lambda, E_Lambda_mu, E_mu_L_mu, E_logdet, d, out,
+                                         st);
+}
+
 // Staging pool of the host-streaming entry point: two device chunk buffers, statistics and
 // kernel workspace; grown on demand, kept for the life of the process.
 namespace {

@@ -25,6 +25,10 @@ int launch_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, 
 // suffstats_sm100.cu
 bool suffstats_tc_supported(int64_t n, int d, const void* x);
 int64_t suffstats_tc_workspace(int64_t n);
+int launch_suffstats_tc_loglik(const float* x, int64_t n, int d, double* s1, double* s2, double n_total,
+                               const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
+                               double e_logdet, double* loglik, void* workspace, int64_t workspace_bytes,
+                               cudaStream_t stream);
 int launch_suffstats_tc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,
                         int64_t workspace_bytes, cudaStream_t stream);
 

@@ -155,8 +155,10 @@ __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, i
 __global__ void __launch_bounds__(kThreads, 1)
 suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
                     double* __restrict__ partial_s2,   // [grid][128][64]
-                    double* __restrict__ partial_s1) { // [grid][2][64]
+                    double* __restrict__ partial_s1,   // [grid][2][64]
+                    unsigned int* __restrict__ fin_counter) {   // block counter of the finalize kernel's tail
   extern __shared__ uint8_t smem_raw[];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *fin_counter = 0u;
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
@@ -285,11 +287,25 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
 // Blocks 0..nb-1: 32 consecutive outputs x 8 groups of partials each (fixed summation order:
 // deterministic); the last block reduces S1 (64 features x 4 groups).
 constexpr int kFinThreads = 256;
+
+// Optional consumer fused into the finalize kernel: the last block to finish evaluates the Gaussian
+// expected log-likelihood from the finished statistics (stats_kernels.cu has the stand-alone
+// kernel), which saves a launch on the single-GPU step.
+struct LoglikTail {
+  const double* e_lambda;
+  const double* e_lambda_mu;
+  double e_mu_l_mu, e_logdet, n;
+  double* out;                    // nullptr: no tail
+  unsigned int* counter;          // zeroed by suffstats_tc_kernel
+};
+
 __global__ void __launch_bounds__(kFinThreads)
 suffstats_finalize_kernel(const double* __restrict__ partial_s2,
                           const double* __restrict__ partial_s1, int n_partials, int d,
-                          int accumulate, double* __restrict__ s2, double* __restrict__ s1) {
+                          int accumulate, double* __restrict__ s2, double* __restrict__ s1,
+                          const LoglikTail tail) {
   __shared__ double red[kFinThreads];
+  __shared__ bool is_last;
   const int t = threadIdx.x;
   if (blockIdx.x + 1 < gridDim.x) {
     const int lane_c = t & 31, g = t >> 5;
@@ -323,6 +339,26 @@ suffstats_finalize_kernel(const double* __restrict__ partial_s2,
       s1[f] = accumulate ? s1[f] + total : total;
     }
   }
+  if (tail.out == nullptr) return;
+  __threadfence();                                   // this block's statistics are visible device-wide
+  __syncthreads();
+  if (t == 0) is_last = atomicAdd(tail.counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int i = t; i < d * d; i += kFinThreads) acc -= 0.5 * tail.e_lambda[i] * __ldcg(s2 + i);
+  for (int i = t; i < d; i += kFinThreads) acc += __ldcg(s1 + i) * tail.e_lambda_mu[i];
+  red[t] = acc;
+  __syncthreads();
+  for (int w = kFinThreads / 2; w > 0; w >>= 1) {
+    if (t < w) red[t] += red[t + w];
+    __syncthreads();
+  }
+  if (t == 0) {
+    const double log_2pi = 1.8378770664093454835606594728112;
+    tail.out[0] = red[0] - 0.5 * tail.n * d * log_2pi + 0.5 * tail.n * tail.e_logdet - 0.5 * tail.n * tail.e_mu_l_mu;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -355,13 +391,14 @@ int64_t suffstats_tc_workspace(int64_t n) {
   int64_t grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (tiles < grid) grid = tiles > 0 ? tiles : 1;
-  return grid * (128 * kFeat + 2 * kFeat) * static_cast<int64_t>(sizeof(double)) + 256;
+  return grid * (128 * kFeat + 2 * kFeat) * static_cast<int64_t>(sizeof(double)) + 512;   // + finalize counter
 }
 
+namespace {
 // s1 may be nullptr.  s1/s2 are device float64; with `accumulate` the results are added to them.
-int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double* s2,
-                            void* workspace, int64_t workspace_bytes, bool accumulate,
-                            cudaStream_t stream) {
+int launch_suffstats_tc_impl(const float* x, int64_t n, int d, double* s1, double* s2,
+                             void* workspace, int64_t workspace_bytes, bool accumulate, LoglikTail tail,
+                             cudaStream_t stream) {
   if (!suffstats_tc_supported(n, d, x)) {
     set_error("suffstats_tc: unsupported shape n=%lld d=%d", static_cast<long long>(n), d);
     return BB_ERR_UNSUPPORTED;
@@ -397,17 +434,36 @@ int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double
   double* partial_s2 = reinterpret_cast<double*>(
       (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
   double* partial_s1 = partial_s2 + static_cast<int64_t>(grid) * 128 * kFeat;
+  unsigned int* fin_counter = reinterpret_cast<unsigned int*>(partial_s1 + static_cast<int64_t>(grid) * 2 * kFeat);
+  tail.counter = fin_counter;
 
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout)) + 1024;
   static SmemOptIn smem_opt_in_0;
   BB_CUDA_OK(smem_opt_in_0.ensure(suffstats_tc_kernel, smem_bytes));
-  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial_s2, partial_s1);
+  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial_s2, partial_s1, fin_counter);
   BB_CHECK_LAUNCH("suffstats_tc_kernel");
   const int fin_blocks = (d * d + 31) / 32 + 1;
   suffstats_finalize_kernel<<<fin_blocks, kFinThreads, 0, stream>>>(partial_s2, partial_s1, grid, d,
-                                                                    accumulate ? 1 : 0, s2, s1);
+                                                                    accumulate ? 1 : 0, s2, s1, tail);
   BB_CHECK_LAUNCH("suffstats_finalize_kernel");
   return BB_OK;
+}
+}  // namespace
+
+int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double* s2,
+                            void* workspace, int64_t workspace_bytes, bool accumulate,
+                            cudaStream_t stream) {
+  LoglikTail none = {nullptr, nullptr, 0.0, 0.0, 0.0, nullptr, nullptr};
+  return launch_suffstats_tc_impl(x, n, d, s1, s2, workspace, workspace_bytes, accumulate, none, stream);
+}
+
+// statistics and, in the finalize kernel's last block, the expected log-likelihood from them (s1 required)
+int launch_suffstats_tc_loglik(const float* x, int64_t n, int d, double* s1, double* s2, double n_total,
+                               const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
+                               double e_logdet, double* loglik, void* workspace, int64_t workspace_bytes,
+                               cudaStream_t stream) {
+  LoglikTail tail = {e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, n_total, loglik, nullptr};
+  return launch_suffstats_tc_impl(x, n, d, s1, s2, workspace, workspace_bytes, false, tail, stream);
 }
 
 int launch_suffstats_tc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,

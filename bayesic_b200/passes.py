@@ -34,6 +34,13 @@ _LOG_2PI = math.log(2.0 * math.pi)
 def gaussian_pass(X, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet):
     """cfg1/cfg2: ``{n, sum x, sum x x^T}`` in one pass and the expected log-likelihood under
     q(mu, Lambda).  Returns ``(n, s1, s2, elbo_term)`` (float64 CUDA tensors)."""
+    torch = stats._torch()
+    if isinstance(X, torch.Tensor) and X.is_cuda:
+        # resident data: statistics + ELBO term through one entry point (two launches)
+        f64 = lambda a: torch.as_tensor(np.asarray(a.cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64),
+                                        device=X.device) if not (isinstance(a, torch.Tensor) and a.is_cuda) \
+            else a.to(torch.float64)
+        return stats.gaussian_suffstats_loglik(X, f64(e_lambda), f64(e_lambda_mu), e_mu_l_mu, e_logdet)
     n, s1, s2 = stats.gaussian_suffstats(X)
     ell = stats.gaussian_expected_loglik(n, s1, s2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet)
     return n, s1, s2, ell

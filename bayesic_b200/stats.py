@@ -17,7 +17,7 @@ import numpy as np
 
 from .backend import library as L
 
-__all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'log_responsibilities',
+__all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'gaussian_suffstats_loglik', 'log_responsibilities',
            'weighted_suffstats', 'regression_suffstats', 'row_projection', 'column_projection',
            'logistic_reparam_stats', 'logistic_reparam_supported', 'mixture_logits',
            'mixture_logits_supported', 'weighted_suffstats_from_logits', 'launch_count']
@@ -103,6 +103,37 @@ def gaussian_suffstats(X, out=None, chunk_rows=0):
                                            int(chunk_rows), _stream(device)),
             'bb_suffstats_gaussian_host')
     return n, s1, s2
+
+
+def gaussian_suffstats_loglik(X, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, n_total=None, out=None):
+    """``gaussian_suffstats`` and ``gaussian_expected_loglik`` in one call for resident data
+    (``bb_suffstats_gaussian_loglik``: the log-likelihood is evaluated by the last block of the
+    statistics' finalize kernel -- two launches instead of three).  ``e_lambda`` / ``e_lambda_mu``
+    are float64 CUDA tensors; ``out = (s1, s2, loglik)`` reuses buffers.  Returns
+    ``(n, s1, s2, loglik)``."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    n, d = X.shape
+    dev = X.device
+    for name, t, shape in (('e_lambda', e_lambda, (d, d)), ('e_lambda_mu', e_lambda_mu, (d,))):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float64 or tuple(t.shape) != shape:
+            raise TypeError("%s must be a float64 CUDA tensor of shape %s" % (name, shape))
+    e_lambda, e_lambda_mu = e_lambda.contiguous(), e_lambda_mu.contiguous()
+    with torch.cuda.device(dev):
+        if out is None:
+            s1 = torch.empty(d, dtype=torch.float64, device=dev)
+            s2 = torch.empty((d, d), dtype=torch.float64, device=dev)
+            loglik = torch.empty(1, dtype=torch.float64, device=dev)
+        else:
+            s1, s2, loglik = out
+        ws = _workspace(lib.bb_suffstats_gaussian_workspace(n, d), dev)
+        L.check(lib.bb_suffstats_gaussian_loglik(X.data_ptr(), n, d, s1.data_ptr(), s2.data_ptr(),
+                                                 float(n if n_total is None else n_total), e_lambda.data_ptr(),
+                                                 e_lambda_mu.data_ptr(), float(e_mu_l_mu), float(e_logdet),
+                                                 loglik.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+                'bb_suffstats_gaussian_loglik')
+    return n, s1, s2, loglik
 
 
 def gaussian_expected_loglik(n, s1, s2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, out=None):

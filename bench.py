@@ -292,6 +292,16 @@ def run_ours(args):
     elbo = torch.zeros(1, dtype=torch.float64, device=dev)
     total_rows = float(n * world)
 
+    def step_single(kernel_events=None):
+        # one GPU: statistics + ELBO through one entry point (the ELBO runs in the finalize kernel's
+        # last block: two launches per step)
+        if kernel_events is not None:
+            kernel_events[0].record()
+        S.gaussian_suffstats_loglik(X, e_lambda_d, e_lambda_mu_d, e_mu_l_mu, e_logdet, n_total=total_rows,
+                                    out=(s1, s2, elbo))
+        if kernel_events is not None:
+            kernel_events[1].record()
+
     def step_nccl(kernel_events=None):
         if kernel_events is not None:
             kernel_events[0].record()
@@ -347,7 +357,7 @@ def run_ours(args):
         else:
             collective = ("one-shot all-reduce of %d float64 over NVLink peer memory fused with the ELBO kernel "
                           "(1 launch per rank; checked against the NCCL all-reduce at start-up)" % packed.numel())
-    step = step_peer if peer is not None else step_nccl
+    step = step_peer if peer is not None else (step_nccl if distributed else step_single)
 
     def barrier():
         if distributed:
@@ -449,7 +459,8 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if n == N_PER_GPU else None,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured'
                          else "fallback (B200_PROFILING.md)",
-                         "kernel": "suffstats_tc_kernel + finalize", "kernel_ms": kernel_ms,
+                         "kernel": "suffstats_tc_kernel + finalize" + ("" if distributed else " (ELBO in its last block)"),
+                         "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "elbo": elbo_value,

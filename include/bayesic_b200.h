@@ -183,6 +183,16 @@ BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xx
                                 double E_muLmu, double E_logdet, int32_t d,
                                 double* out, void* stream);
 
+/* bb_suffstats_gaussian followed by bb_gaussian_expected_loglik in one call (the cfg2 step on one
+ * GPU): on the tcgen05 path the log-likelihood is evaluated by the last block of the statistics'
+ * finalize kernel, so the step is two launches instead of three.  sum_x is required; n_total is the
+ * row count the log-likelihood refers to (= n on one GPU). */
+BB_API int bb_suffstats_gaussian_loglik(const float* X, int64_t n, int32_t d, double* sum_x,
+                                 double* sum_xxT, double n_total, const double* E_Lambda,
+                                 const double* E_Lambda_mu, double E_mu_L_mu, double E_logdet,
+                                 double* out, void* workspace, int64_t workspace_bytes,
+                                 void* stream);
+
 /* Minibatch statistics of conjugate Bayesian linear regression / factor analysis
  * (natural-gradient SVI, README.md:69-80), i.e. the plans
  *   _tensordot(_dimshuffle(X,1,0), X, [1],[0]), _tensordot(_dimshuffle(X,1,0), y, [1],[0]),

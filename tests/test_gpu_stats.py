@@ -75,6 +75,33 @@ def test_host_streamed_matches_device_and_oracle():
     _close(q2, h2, rtol=1e-5)
 
 
+@pytest.mark.parametrize('n,d', [(1, 4), (1000, 16), (50000, 64), (4097, 10), (300, 100)])
+def test_suffstats_loglik_single_entry_point(n, d):
+    """bb_suffstats_gaussian_loglik (ELBO term in the finalize kernel's last block on the tcgen05
+    path, generic kernels otherwise) = bb_suffstats_gaussian + bb_gaussian_expected_loglik, also when
+    called repeatedly (the block counter must reset) and with recycled output buffers."""
+    import torch
+    rng = np.random.RandomState(n + d)
+    X = torch.from_numpy((rng.randn(n, d) * 1.1 + 0.2).astype(np.float32)).cuda()
+    a = rng.randn(d, d)
+    e_lambda = torch.from_numpy(a @ a.T / d + np.eye(d)).cuda()
+    e_lambda_mu = torch.from_numpy(rng.randn(d)).cuda()
+    cnt, s1, s2 = S.gaussian_suffstats(X)
+    want = S.gaussian_expected_loglik(cnt, s1, s2, e_lambda, e_lambda_mu, 0.37, -1.9)
+    out = None
+    for _ in range(3):
+        got_n, g1, g2, ell = S.gaussian_suffstats_loglik(X, e_lambda, e_lambda_mu, 0.37, -1.9, out=out)
+        out = (g1, g2, ell)
+        assert got_n == n
+        assert torch.equal(g1, s1) and torch.equal(g2, s2)
+        np.testing.assert_allclose(float(ell), float(want), rtol=1e-12)
+    ref = O.gaussian_expected_loglik(n, *O.gaussian_suffstats(X.cpu().numpy())[1:], e_lambda.cpu().numpy(),
+                                     e_lambda_mu.cpu().numpy(), 0.37, -1.9)
+    np.testing.assert_allclose(float(ell), ref, rtol=1e-4)
+    with pytest.raises(TypeError):
+        S.gaussian_suffstats_loglik(X, e_lambda.float(), e_lambda_mu, 0.37, -1.9)
+
+
 def test_full_size_cfg2_properties():
     # N = 16 Mi, D = 64 (BASELINE cfg2): size-independent properties instead of a CPU oracle
     import torch
