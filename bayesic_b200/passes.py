@@ -37,10 +37,11 @@ def gaussian_pass(X, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet):
     torch = stats._torch()
     if isinstance(X, torch.Tensor) and X.is_cuda:
         # resident data: statistics + ELBO term through one entry point (two launches)
-        f64 = lambda a: torch.as_tensor(np.asarray(a.cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64),
-                                        device=X.device) if not (isinstance(a, torch.Tensor) and a.is_cuda) \
-            else a.to(torch.float64)
-        return stats.gaussian_suffstats_loglik(X, f64(e_lambda), f64(e_lambda_mu), e_mu_l_mu, e_logdet)
+        def device_f64(a):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=X.device, dtype=torch.float64)
+            return torch.as_tensor(np.asarray(a, dtype=np.float64), device=X.device)
+        return stats.gaussian_suffstats_loglik(X, device_f64(e_lambda), device_f64(e_lambda_mu), e_mu_l_mu, e_logdet)
     n, s1, s2 = stats.gaussian_suffstats(X)
     ell = stats.gaussian_expected_loglik(n, s1, s2, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet)
     return n, s1, s2, ell
