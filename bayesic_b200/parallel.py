@@ -116,6 +116,13 @@ class PeerReducer(object):
         lo = ((self.epoch + 1) & 1) * self.stride
         return self.layout.views(self.payload[lo:lo + self.numel])
 
+    def set_constant(self, name, value):
+        """Write a field that does not change from step to step (e.g. this rank's row count) into
+        both payload slots once, instead of refilling it every step."""
+        for parity in (0, 1):
+            lo = parity * self.stride
+            self.layout.views(self.payload[lo:lo + self.numel])[name].fill_(value)
+
     def _call(self, loglik):
         from . import stats
         from .backend import library as L

@@ -340,10 +340,10 @@ def run_ours(args):
         S.gaussian_suffstats(X, out=(views_p['s1'], views_p['s2']))
         if kernel_events is not None:
             kernel_events[1].record()
-        views_p['count'].fill_(float(n))
         peer.reduce_loglik(e_lambda_d, e_lambda_mu_d, e_mu_l_mu, e_logdet, D, elbo)
 
     if peer is not None:
+        peer.set_constant('count', float(n))           # per-rank row count: the same every step
         step_nccl()
         want = float(elbo)
         step_peer()
