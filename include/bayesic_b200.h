@@ -184,7 +184,7 @@ BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xx
                                 double* out, void* stream);
 
 /* bb_suffstats_gaussian followed by bb_gaussian_expected_loglik in one call (the cfg2 step on one
- * GPU): on the tcgen05 path the log-likelihood is evaluated by the last block of the statistics'
+ * GPU; statistics of bayesic/distribution/base.py:328-332, log-likelihood of base.py:25-100): on the tcgen05 path the log-likelihood is evaluated by the last block of the statistics'
  * finalize kernel, so the step is two launches instead of three.  sum_x is required; n_total is the
  * row count the log-likelihood refers to (= n on one GPU). */
 BB_API int bb_suffstats_gaussian_loglik(const float* X, int64_t n, int32_t d, double* sum_x,
