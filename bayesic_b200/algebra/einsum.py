@@ -22,7 +22,7 @@ Deliberate divergences from the reference (defects):
 * index tuples are always stored as tuples (the reference leaks lists from
   ``algebra.py:592`` that later crash ``Counter`` at ``algebra.py:636``).
 """
-from .expr import Expression, eye, wrap_if_literal, var
+from .expr import Expression, eye, wrap_if_literal
 
 __all__ = ['einsum', 'Einsum', 'SUM', 'OUT', 'sum_index', 'out_index']
 

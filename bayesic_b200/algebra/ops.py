@@ -5,8 +5,6 @@ Mirrors the API surface of ``bayesic/algebra.py:1149-1278`` and ``:1416-1478``:
 same names, argument order and error behaviour (``ValueError`` on bad axes).
 ``sum`` shadows the builtin exactly like the reference does.
 """
-import builtins as _builtins
-
 from .expr import (Expression, wrap_if_literal, with_wrapped_literals, autobroadcast_or_match,
                    elemwise, add, OP_LOG, OP_EXP, OP_POW, OP_ABS, OP_LGAMMA)
 from .einsum import einsum, sum_index, out_index

@@ -33,8 +33,8 @@ which crash ``Counter`` at ``:636`` on the next elimination step (e.g.
 import copy
 from collections import Counter
 
-from .expr import Expression, constant
-from .einsum import Einsum, SUM, OUT, out_index
+from .expr import constant
+from .einsum import Einsum, OUT, out_index
 from .plan_ir import _sum, _mul, _dimshuffle, _tensordot, _diagonal
 
 __all__ = ['plan_einsum', 'lower_to_plan_ir']
