@@ -177,3 +177,23 @@ def test_gpu_conjugate_families():
     for name, ll, inputs, want in _conjugate_cases(seed=5):
         got = float(ll.compile()(**inputs))
         assert abs(got - want) <= 1e-4 * abs(want) + 1e-3, (name, got, want)
+
+
+def test_match_recovers_the_statistic_paired_with_a_natural_parameter():
+    """The statistic a natural parameter is paired with can be read off the interaction term with
+    ``match`` (algebra.py:1037-1063) -- the reference's route from a log-likelihood expression to the
+    contraction over the data axis that the device kernels serve."""
+    from bayesic_b200.algebra import match
+    from bayesic_b200.distribution import Categorical
+    eta2, slot2 = A.var('eta2', 2), A.var('slot2', 2)
+    s1, s2 = MultivariateNormal().iid().sufficient_statistics(X)
+    pair = [('sum', 0), ('sum', 1)]
+    term = A.einsum([(s2, pair), (eta2, pair)], 0)                       # <sum_n x x^T, eta2>
+    found = match(term, A.einsum([(slot2, pair), (eta2, pair)], 0), slot2)
+    assert found == s2 == A.dot(X.T, X)
+    M, lg, slot1 = A.var('M', 2), A.var('lg', 1), A.var('slot1', 1)
+    (counts,) = Categorical().iid().sufficient_statistics(M)
+    term = A.einsum([(counts, [('sum', 0)]), (lg, [('sum', 0)])], 0)     # <class counts, logits>
+    found = match(term, A.einsum([(slot1, [('sum', 0)]), (lg, [('sum', 0)])], 0), slot1)
+    assert found == counts and found._rewrite_as_special_case_ops() == _sum(M, 0)
+    assert match(term, A.einsum([(slot1, [('sum', 0)]), (A.var('other', 1), [('sum', 0)])], 0), slot1) is None
