@@ -289,6 +289,19 @@ int run_tensordot(Exec& ex, int idx, const bb_node_desc& nd) {
                          K >= 64 && K % 64 == 0 && K <= 32768 && N >= 16 && N % 16 == 0 && N <= 256 && N * K <= 32768;
   const bool col_shape = batch == 1 && small_dims && K >= kMinRows && x_mn_major && y_mn_major && M >= 128 &&
                          M % 128 == 0 && N >= 64 && N % 64 == 0 && (M / 128) * (N / 64) <= 4;
+  // Matrix-vector contractions over a tall matrix (dot(X.T, y), dot(X, w) and their mirror images with
+  // the vector on the left): one pass over the matrix at HBM rate instead of GEMM tiles that are 1 wide.
+  //   mat [rows, feats] dense row-major; vec dense.  cols: contract rows; rows: contract feats.
+  const bool vec_right = batch == 1 && N == 1 && ys[2] == 1, vec_left = batch == 1 && M == 1 && xs[2] == 1;
+  const bool gemv_cols_r = vec_right && K >= kMinRows && x_mn_major && M <= 4096;          // X^T y
+  const bool gemv_rows_r = vec_right && M >= kMinRows && x_k_major && K <= 65536;           // X w
+  const bool gemv_cols_l = !vec_right && vec_left && K >= kMinRows && ys[1] == 1 && ys[2] == N && N <= 4096;   // y^T X
+  const bool gemv_rows_l = !vec_right && vec_left && N >= kMinRows && ys[2] == 1 && ys[1] == K && K <= 65536;  // (X w)^T
+  void* gemv_ws = nullptr;
+  if (gemv_cols_r || gemv_cols_l) {
+    const int64_t feats = gemv_cols_r ? M : N;
+    BB_TRY(ex.alloc_scratch(gemv_cols_workspace(K, feats), &gemv_ws));
+  }
   void* tc_ws = nullptr;
   void* tc_aux = nullptr;      // rowproj: W transposed to (q, features); colproj: float64 result
   int64_t tc_ws_bytes = 0;
@@ -320,6 +333,21 @@ int run_tensordot(Exec& ex, int idx, const bb_node_desc& nd) {
       BB_TRY(launch_colproj_tc(X.ptr, Y.ptr, K, static_cast<int>(M), static_cast<int>(N),
                                static_cast<double*>(tc_aux), tc_ws, tc_ws_bytes, ex.stream));
       BB_TRY(launch_f64_to_f32(static_cast<const double*>(tc_aux), out.ptr, M * N, ex.stream));
+      done = true;
+    }
+    if (!done && (gemv_cols_r || gemv_cols_l)) {
+      const float* mat = gemv_cols_r ? X.ptr : Y.ptr;
+      const float* vec = gemv_cols_r ? Y.ptr : X.ptr;
+      const int64_t feats = gemv_cols_r ? M : N;
+      if (gemv_cols_supported(K, feats, mat)) {
+        BB_TRY(launch_gemv_cols(mat, vec, K, static_cast<int>(feats), out.ptr, gemv_ws, ex.stream));
+        done = true;
+      }
+    }
+    if (!done && (gemv_rows_r || gemv_rows_l)) {
+      const float* mat = gemv_rows_r ? X.ptr : Y.ptr;
+      const float* vec = gemv_rows_r ? Y.ptr : X.ptr;
+      BB_TRY(launch_gemv_rows(mat, vec, gemv_rows_r ? M : N, static_cast<int>(K), out.ptr, ex.stream));
       done = true;
     }
     if (!done)

@@ -495,4 +495,125 @@ int launch_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, 
   return BB_OK;
 }
 
+// ---- tall-skinny matrix-vector contractions (HBM-bound: X is read once) ---------------------------
+// gemv_cols: out[d] = sum_n X[n, d] y[n]   (plan of dot(X.T, y): contraction over the data axis)
+// gemv_rows: out[n] = sum_d X[n, d] w[d]   (plan of dot(X, w): the linear predictor)
+// The split-K GEMM tiles waste 63/64 of their work on these shapes.
+namespace {
+
+constexpr int kGemvThreads = 256;
+constexpr int kGemvMaxColBlocks = 4;          // gemv_cols: d <= 4 * 256 * 4 = 4096 in the vector path
+
+// X row-major [n, d], d % 4 == 0, 16-byte aligned rows.  Thread = (row lane, float4 column): fp32
+// partial sums over this CTA's row range, combined in float64 across row lanes, CTAs in the finalize.
+__global__ void __launch_bounds__(kGemvThreads)
+gemv_cols_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n, int d,
+                 double* __restrict__ partial) {
+  __shared__ double red[kGemvThreads * 4];
+  const int vec_cols = d >> 2;
+  const int cols_here = min(vec_cols, kGemvThreads);
+  const int rows_per_pass = kGemvThreads / cols_here;
+  const int tid = threadIdx.x;
+  const int r_lane = tid / cols_here, c_lane = tid - r_lane * cols_here;
+  const bool active = r_lane < rows_per_pass;
+  const int64_t row_begin = n * blockIdx.x / gridDim.x, row_end = n * (blockIdx.x + 1) / gridDim.x;
+  const int col_blocks = (vec_cols + kGemvThreads - 1) / kGemvThreads;
+  for (int cb = 0; cb < col_blocks; ++cb) {
+    const int c4 = cb * kGemvThreads + c_lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && c4 < vec_cols) {
+      const float4* col = reinterpret_cast<const float4*>(x) + c4;
+      for (int64_t r = row_begin + r_lane; r < row_end; r += rows_per_pass) {
+        const float4 v = __ldg(col + r * vec_cols);
+        const float w = __ldg(y + r);
+        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y);
+        acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+      }
+    }
+    red[tid * 4 + 0] = acc.x; red[tid * 4 + 1] = acc.y; red[tid * 4 + 2] = acc.z; red[tid * 4 + 3] = acc.w;
+    __syncthreads();
+    if (r_lane == 0 && c4 < vec_cols) {
+      double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      for (int rl = 0; rl < rows_per_pass; ++rl) {
+        const double* src = red + (rl * cols_here + c_lane) * 4;
+        t0 += src[0]; t1 += src[1]; t2 += src[2]; t3 += src[3];
+      }
+      double* dst = partial + static_cast<int64_t>(blockIdx.x) * d + c4 * 4;
+      dst[0] = t0; dst[1] = t1; dst[2] = t2; dst[3] = t3;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void gemv_cols_finalize_kernel(const double* __restrict__ partial, int n_ctas, int d,
+                                          float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double acc = 0.0;
+  for (int b = 0; b < n_ctas; ++b) acc += partial[static_cast<int64_t>(b) * d + c];
+  out[c] = static_cast<float>(acc);
+}
+
+// one warp per row; float4 loads when d % 4 == 0 and the rows are 16-byte aligned
+__global__ void __launch_bounds__(kGemvThreads)
+gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, int64_t n, int d, int vec,
+                 float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += n_warps) {
+    const float* row = x + r * d;
+    float acc = 0.f;
+    if (vec) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      const float4* w4 = reinterpret_cast<const float4*>(w);
+      for (int c = lane; c < (d >> 2); c += 32) {
+        const float4 a = __ldg(r4 + c), b = __ldg(w4 + c);
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) acc = fmaf(__ldg(row + c), __ldg(w + c), acc);
+    }
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[r] = acc;
+  }
+}
+
+int gemv_cols_grid(int64_t n) {
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(static_cast<int64_t>(sms) * 4, (n + 63) / 64)));
+}
+
+}  // namespace
+
+bool gemv_cols_supported(int64_t n, int64_t d, const void* x) {
+  return n > 0 && d >= 4 && d % 4 == 0 && d <= kGemvMaxColBlocks * kGemvThreads * 4 &&
+         reinterpret_cast<uintptr_t>(x) % 16 == 0;
+}
+
+int64_t gemv_cols_workspace(int64_t n, int64_t d) { return static_cast<int64_t>(gemv_cols_grid(n)) * d * 8 + 256; }
+
+int launch_gemv_cols(const float* x, const float* y, int64_t n, int d, float* out, void* workspace,
+                     cudaStream_t stream) {
+  double* partial = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  const int grid = gemv_cols_grid(n);
+  gemv_cols_kernel<<<grid, kGemvThreads, 0, stream>>>(x, y, n, d, partial);
+  BB_CHECK_LAUNCH("gemv_cols_kernel");
+  gemv_cols_finalize_kernel<<<(d + 255) / 256, 256, 0, stream>>>(partial, grid, d, out);
+  BB_CHECK_LAUNCH("gemv_cols_finalize_kernel");
+  return BB_OK;
+}
+
+int launch_gemv_rows(const float* x, const float* w, int64_t n, int d, float* out, cudaStream_t stream) {
+  if (n == 0) return BB_OK;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int vec = (d % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0) ? 1 : 0;
+  const int64_t blocks = std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(sms) * 16);
+  gemv_rows_kernel<<<static_cast<int>(blocks), kGemvThreads, 0, stream>>>(x, w, n, d, vec, out);
+  BB_CHECK_LAUNCH("gemv_rows_kernel");
+  return BB_OK;
+}
+
 }  // namespace bb

@@ -18,6 +18,12 @@ int64_t reduce_sum_scratch_bytes(int64_t kept_total);
 int launch_reduce_sum(const View& in, const bool* reduce_axis, const View& out, void* scratch,
                       cudaStream_t stream);
 int64_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch);
+// tall-skinny matrix-vector contractions: out[d] = sum_n X[n,d] y[n]; out[n] = sum_d X[n,d] w[d]
+bool gemv_cols_supported(int64_t n, int64_t d, const void* x);
+int64_t gemv_cols_workspace(int64_t n, int64_t d);
+int launch_gemv_cols(const float* x, const float* y, int64_t n, int d, float* out, void* workspace,
+                     cudaStream_t stream);
+int launch_gemv_rows(const float* x, const float* w, int64_t n, int d, float* out, cudaStream_t stream);
 int launch_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                 int64_t batch, int64_t sAb, int64_t sAm, int64_t sAk, int64_t sBb, int64_t sBk,
                 int64_t sBn, void* workspace, cudaStream_t stream);

@@ -165,3 +165,27 @@ def test_compiled_syrk_large_d_runs_on_the_cta_pair_kernel():
     want = Xh.astype(np.float64).T @ Xh.astype(np.float64)
     nrm = np.linalg.norm(Xh.astype(np.float64), axis=0)
     _scale_close(fn(X=Xh), want, nrm, nrm)
+
+
+@pytest.mark.parametrize('n,d', [(20000, 24), (20000, 256), (9000, 1000), (6000, 2048), (20000, 6)])
+def test_compiled_matrix_vector_contractions_over_the_data_axis(n, d):
+    """dot(X.T, y) / dot(y, X) (contraction over rows) and dot(X, w) / dot(w, X.T) (over features) on a
+    tall matrix: served by the one-pass matrix-vector kernels when the layout allows (d % 4 == 0),
+    by the split-K GEMM otherwise (d = 6) -- same values either way."""
+    rng = np.random.RandomState(n + d)
+    Xh = (rng.randn(n, d) * 1.1 + 0.2).astype(np.float32)
+    yh, wh = rng.randn(n).astype(np.float32), (rng.randn(d) / np.sqrt(d)).astype(np.float32)
+    X, y, w = A.var('X', 2), A.var('y', 1), A.var('w', 1)
+    X64 = Xh.astype(np.float64)
+    col_norms, row_norms = np.linalg.norm(X64, axis=0), np.linalg.norm(X64, axis=1)
+    ynorm, wnorm = np.array([np.linalg.norm(yh.astype(np.float64))]), np.array([np.linalg.norm(wh.astype(np.float64))])
+    want_cols, want_rows = X64.T @ yh.astype(np.float64), X64 @ wh.astype(np.float64)
+    f = A.dot(X.T, y).compile()
+    _scale_close(f(X=Xh, y=yh).reshape(d, 1), want_cols.reshape(d, 1), col_norms, ynorm)
+    if d % 4 == 0:
+        assert f.plan.last_launches <= 2               # one pass + finalize, not GEMM tiles + reduce
+    _scale_close(A.dot(y, X).compile()(X=Xh, y=yh).reshape(d, 1), want_cols.reshape(d, 1), col_norms, ynorm)
+    g = A.dot(X, w).compile()
+    _scale_close(g(X=Xh, w=wh).reshape(n, 1), want_rows.reshape(n, 1), row_norms, wnorm)
+    assert g.plan.last_launches == 1
+    _scale_close(A.dot(w, X.T).compile()(X=Xh, w=wh).reshape(n, 1), want_rows.reshape(n, 1), row_norms, wnorm)
