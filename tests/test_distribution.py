@@ -197,3 +197,16 @@ def test_match_recovers_the_statistic_paired_with_a_natural_parameter():
     found = match(term, A.einsum([(slot1, [('sum', 0)]), (lg, [('sum', 0)])], 0), slot1)
     assert found == counts and found._rewrite_as_special_case_ops() == _sum(M, 0)
     assert match(term, A.einsum([(slot1, [('sum', 0)]), (A.var('other', 1), [('sum', 0)])], 0), slot1) is None
+
+
+def test_conjugate_families_lower_to_a_faithful_descriptor():
+    """CPU check of the lowering: the flat plan descriptor the C-ABI executor would be given (incl. the
+    lgamma opcode), evaluated node by node in numpy, equals the expression-level value."""
+    from bayesic_b200.backend.compiled import CompiledPlan
+    from oracle.descriptor_eval import evaluate_descriptor
+    for name, ll, inputs, want in _conjugate_cases(seed=9):
+        low = CompiledPlan([ll]).lowered
+        arrays = [inputs[n] if n else low.bound_constants[i] for i, n in enumerate(low.input_names)]
+        (value,) = evaluate_descriptor(low.nodes, low.outputs, arrays)
+        np.testing.assert_allclose(float(value), want, rtol=1e-6, err_msg=name)
+        np.testing.assert_allclose(float(value), float(evaluate(ll, inputs)), rtol=1e-10, err_msg=name)
