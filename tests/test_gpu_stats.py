@@ -580,6 +580,23 @@ def test_logistic_reparam_alternative_kernels(env):
     assert run.returncode == 0 and run.stdout.strip().endswith('ok'), run.stdout + run.stderr
 
 
+def test_empty_minibatch_through_the_fused_entry_points():
+    """n = 0 (an empty shard / minibatch) gives zero statistics and empty per-row outputs, not an error."""
+    import torch
+    d, k, s = 64, 16, 64
+    X = torch.empty((0, d), device='cuda')
+    ll, G = S.logistic_reparam_stats(torch.empty((0, 128), device='cuda'), torch.empty(0, device='cuda'),
+                                     torch.randn(s, 128, device='cuda'))
+    assert float(ll.abs().sum()) == 0.0 and float(G.abs().sum()) == 0.0 and tuple(G.shape) == (128, s)
+    U = torch.eye(d, device='cuda').repeat(k, 1, 1).contiguous()
+    logits, lse, total = S.mixture_logits(X, U, torch.zeros(k, d, device='cuda'), torch.zeros(k, device='cuda'))
+    assert tuple(logits.shape) == (0, k) and tuple(lse.shape) == (0,) and float(total) == 0.0
+    nk, rx, rxx = S.weighted_suffstats_from_logits(X, logits, lse)
+    assert float(nk.abs().sum()) == 0.0 and float(rx.abs().sum()) == 0.0 and float(rxx.abs().sum()) == 0.0
+    log_resp, lse2, total2 = S.log_responsibilities(torch.empty((0, k), device='cuda'))
+    assert tuple(log_resp.shape) == (0, k) and float(total2) == 0.0
+
+
 # ---- error behaviour of the C-ABI entry points (status codes -> exceptions, INTEGRATION.md) ----
 
 def test_entry_points_reject_bad_arguments_and_small_workspaces():
