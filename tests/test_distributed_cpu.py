@@ -150,3 +150,24 @@ def test_two_rank_allreduce_of_the_regression_and_mixture_layouts():
         np.testing.assert_allclose(mix['nk'], nk, rtol=1e-12)
         np.testing.assert_allclose(mix['rx'], rx, rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(mix['rxx'], rxx, rtol=1e-12, atol=1e-12)
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_zero():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone runs the
+    CPU baseline and prints ONE JSON line with "impl": "reference"; the other rank exits 0 silently."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', '29593', os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+           '--steps', '1', '--warmup', '1']
+    run = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    lines = [ln for ln in run.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    record = json.loads(lines[0])
+    assert record['impl'] == 'reference' and record['n_gpus'] == 2 and record['gpu_launches'] == 0
+    assert record['e2e']['h2d_bytes_per_step'] == 0 and record['cpu_baseline']['kind'] in ('port', 'reference')
+    assert record['value'] > 0 and record['higher_is_better'] is True
