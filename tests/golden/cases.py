@@ -40,6 +40,11 @@ def make_inputs():
     inputs['P'] = np.abs(randn(5, 5)) + 0.5       # strictly positive, for log / pow
     inputs['T3'] = randn(4, 5, 5)
     inputs['U3'] = randn(4, 5, 3)
+    # cfg4 / cfg5 expressions (appended last so the draws above are unchanged): regression targets t[n],
+    # binary labels b01[n], parameter draws Wm[s, d]
+    inputs['t'] = randn(n)
+    inputs['b01'] = (rng.rand(n) < 0.5).astype('float32')
+    inputs['Wm'] = (0.5 * randn(3, d)).astype('float32')
     return inputs
 
 
@@ -47,8 +52,8 @@ YLIT = make_inputs()['Y']
 
 
 def _vars(A):
-    v = {name: A.var(name, 2) for name in ('X', 'Y', 'Z', 'W', 'D', 'L', 'R', 'Lg', 'M', 'P')}
-    v.update({name: A.var(name, 1) for name in ('x', 'y', 'eta')})
+    v = {name: A.var(name, 2) for name in ('X', 'Y', 'Z', 'W', 'D', 'L', 'R', 'Lg', 'M', 'P', 'Wm')}
+    v.update({name: A.var(name, 1) for name in ('x', 'y', 'eta', 't', 'b01')})
     v.update({name: A.var(name, 3) for name in ('S', 'T3', 'U3')})
     return v
 
@@ -147,4 +152,12 @@ CASES = [
                                                [2], [2], [0, 1], [0, 1]))),
     ('tensordot2', _c(lambda A, v: A.tensordot(v.T3, v.U3, [0, 1], [0, 1]))),
     ('planner_crash_case', _c(lambda A, v: A.dot(A.sum(v.D, 0), A.dot(v.L, v.eta)))),
+    # cfg4 (conjugate SVI statistics) and cfg5 (reparameterised logistic gradient) as the user writes them
+    ('hot_cfg4_xty', _c(lambda A, v: A.dot(v.D.T, v.t))),
+    ('hot_cfg4_yty', _c(lambda A, v: A.dot(v.t, v.t))),
+    ('hot_cfg5_z', _c(lambda A, v: A.dot(v.D, v.Wm.T))),
+    ('hot_cfg5_loglik', _c(lambda A, v: A.sum(v.b01.dimshuffle(0, 'x') * A.dot(v.D, v.Wm.T)
+                                              - A.log(1 + A.exp(A.dot(v.D, v.Wm.T))), axis=0))),
+    ('hot_cfg5_grad', _c(lambda A, v: A.dot(v.D.T, v.b01.dimshuffle(0, 'x')
+                                            - (1 + A.exp(-1 * A.dot(v.D, v.Wm.T))) ** -1))),
 ]
