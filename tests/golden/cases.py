@@ -45,6 +45,10 @@ def make_inputs():
     inputs['t'] = randn(n)
     inputs['b01'] = (rng.rand(n) < 0.5).astype('float32')
     inputs['Wm'] = (0.5 * randn(3, d)).astype('float32')
+    # cfg3 logits: per-component precision-like matrices Ak[k, d, d] and offsets ck[k]
+    a3 = randn(k, d, d)
+    inputs['Ak'] = (np.einsum('kij,klj->kil', a3, a3) / d + np.eye(d)).astype('float32')
+    inputs['ck'] = randn(k)
     return inputs
 
 
@@ -53,8 +57,8 @@ YLIT = make_inputs()['Y']
 
 def _vars(A):
     v = {name: A.var(name, 2) for name in ('X', 'Y', 'Z', 'W', 'D', 'L', 'R', 'Lg', 'M', 'P', 'Wm')}
-    v.update({name: A.var(name, 1) for name in ('x', 'y', 'eta', 't', 'b01')})
-    v.update({name: A.var(name, 3) for name in ('S', 'T3', 'U3')})
+    v.update({name: A.var(name, 1) for name in ('x', 'y', 'eta', 't', 'b01', 'ck')})
+    v.update({name: A.var(name, 3) for name in ('S', 'T3', 'U3', 'Ak')})
     return v
 
 
@@ -160,4 +164,9 @@ CASES = [
                                               - A.log(1 + A.exp(A.dot(v.D, v.Wm.T))), axis=0))),
     ('hot_cfg5_grad', _c(lambda A, v: A.dot(v.D.T, v.b01.dimshuffle(0, 'x')
                                             - (1 + A.exp(-1 * A.dot(v.D, v.Wm.T))) ** -1))),
+    # cfg3 logits c_k + x.b_k - 1/2 x^T A_k x as passes.GmmStep writes them (the reference plans a batched
+    # _tensordot whose evaluator is broken, algebra.py:1370-1373: the golden records plan + declared value)
+    ('hot_cfg3_logits', _c(lambda A, v: A.dot(v.D, v.M.T) + (-0.5) * A.einsum(
+        [(v.D, [('out', 0), ('sum', 0)]), (v.Ak, [('out', 1), ('sum', 0), ('sum', 1)]),
+         (v.D, [('out', 0), ('sum', 1)])], 2) + v.ck.dimshuffle('x', 0))),
 ]
