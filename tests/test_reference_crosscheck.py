@@ -1,0 +1,149 @@
+"""Seeded random expressions built twice -- with the UNMODIFIED reference ``bayesic.algebra``
+(imported through the numpy Theano shim; authoring container only, skipped where
+``/root/reference`` is absent) and with ``bayesic_b200.algebra`` -- must agree on the canonical
+form (``repr``), on the plan the planner emits, and on the value.  Complements the fixed golden
+cases (tests/golden) with shapes of expression nobody wrote down by hand.
+
+The reference's own defects are respected, not reproduced: when its planner raises
+the case only checks that ours does not; when its plan has batch axes its evaluator is known to be
+wrong or to crash (algebra.py:1364-1380), so the value is checked against the declared semantics
+only."""
+import json
+
+import numpy as np
+import pytest
+
+import bayesic_b200.algebra as A
+from oracle.plan_dump import dump_plan
+from oracle.reference_loader import load_reference_algebra, reference_available
+from oracle.semantics import evaluate
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason='reference tree not present')
+
+N_CASES = 160
+
+
+def _recipe(rng, rank, depth):
+    """Nested tuple describing an expression of the given rank over X, Y (5x5) and x, y (5)."""
+    leaf = depth <= 0 or rng.rand() < 0.25
+    if rank == 2:
+        if leaf:
+            return ('var', rng.choice(['X', 'Y']))
+        kind = rng.choice(['T', 'dot', 'mul', 'add', 'outer', 'scale', 'sub'])
+        if kind == 'T':
+            return ('T', _recipe(rng, 2, depth - 1))
+        if kind == 'outer':
+            return ('outer', _recipe(rng, 1, depth - 1), _recipe(rng, 1, depth - 1))
+        if kind == 'scale':
+            return ('scale', float(rng.choice([2.0, -0.5, 3.0])), _recipe(rng, 2, depth - 1))
+        return (kind, _recipe(rng, 2, depth - 1), _recipe(rng, 2, depth - 1))
+    if rank == 1:
+        if leaf:
+            return ('var', rng.choice(['x', 'y']))
+        kind = rng.choice(['matvec', 'vecmat', 'mul', 'add', 'sumax', 'diag', 'scale'])
+        if kind == 'matvec':
+            return ('dot', _recipe(rng, 2, depth - 1), _recipe(rng, 1, depth - 1))
+        if kind == 'vecmat':
+            return ('dot', _recipe(rng, 1, depth - 1), _recipe(rng, 2, depth - 1))
+        if kind == 'sumax':
+            return ('sumax', int(rng.randint(2)), _recipe(rng, 2, depth - 1))
+        if kind == 'diag':
+            return ('diag', _recipe(rng, 2, depth - 1))
+        if kind == 'scale':
+            return ('scale', float(rng.choice([2.0, -0.5])), _recipe(rng, 1, depth - 1))
+        return (kind, _recipe(rng, 1, depth - 1), _recipe(rng, 1, depth - 1))
+    kind = rng.choice(['inner', 'trace', 'sum1', 'sum2'])
+    if kind == 'inner':
+        return ('dot', _recipe(rng, 1, depth - 1), _recipe(rng, 1, depth - 1))
+    if kind == 'trace':
+        return ('trace', _recipe(rng, 2, depth - 1))
+    return ('sumall', _recipe(rng, 1 if kind == 'sum1' else 2, depth - 1))
+
+
+def _build(ns, recipe, variables):
+    op = recipe[0]
+    if op == 'var':
+        return variables[recipe[1]]
+    if op == 'T':
+        return _build(ns, recipe[1], variables).T
+    if op == 'scale':
+        return recipe[1] * _build(ns, recipe[2], variables)
+    if op == 'sumax':
+        return ns.sum(_build(ns, recipe[2], variables), axis=recipe[1])
+    if op == 'sumall':
+        return ns.sum(_build(ns, recipe[1], variables))
+    if op == 'diag':
+        return ns.diagonal(_build(ns, recipe[1], variables))
+    if op == 'trace':
+        return ns.trace(_build(ns, recipe[1], variables))
+    a, b = _build(ns, recipe[1], variables), _build(ns, recipe[2], variables)
+    if op == 'dot':
+        return ns.dot(a, b)
+    if op == 'outer':
+        return ns.outer(a, b)
+    if op == 'mul':
+        return a * b
+    if op == 'add':
+        return a + b
+    if op == 'sub':
+        return a - b
+    raise ValueError(op)
+
+
+def _variables(ns):
+    return {'X': ns.var('X', 2), 'Y': ns.var('Y', 2), 'x': ns.var('x', 1), 'y': ns.var('y', 1)}
+
+
+def _canon(plan):
+    if isinstance(plan, dict):
+        out = {k: _canon(v) for k, v in plan.items()}
+        if out.get('op') == '_mul':
+            out['factors'] = sorted(out['factors'], key=lambda f: json.dumps(f, sort_keys=True))
+        return out
+    if isinstance(plan, list):
+        return [_canon(p) for p in plan]
+    return plan
+
+
+def _has_batch_axes(plan):
+    if isinstance(plan, dict):
+        if plan.get('op') == '_tensordot' and plan.get('x_batch'):
+            return True
+        return any(_has_batch_axes(v) for v in plan.values())
+    if isinstance(plan, list):
+        return any(_has_batch_axes(p) for p in plan)
+    return False
+
+
+def test_random_expressions_agree_with_the_unmodified_reference():
+    ref = load_reference_algebra()
+    rng = np.random.RandomState(20260)
+    data = np.random.RandomState(7)
+    inputs = {'X': data.randn(5, 5).astype(np.float32), 'Y': data.randn(5, 5).astype(np.float32),
+              'x': data.randn(5).astype(np.float32), 'y': data.randn(5).astype(np.float32)}
+    planned = valued = 0
+    for case in range(N_CASES):
+        recipe = _recipe(rng, int(rng.randint(3)), 3)
+        theirs = _build(ref, recipe, _variables(ref))
+        ours = _build(A, recipe, _variables(A))
+        theirs, ours = ref.wrap_if_literal(theirs), A.wrap_if_literal(ours)
+        assert repr(ours) == repr(theirs), (case, recipe)
+        assert ours.ndim == theirs.ndim
+        want = evaluate(ours, {k: inputs[k] for k in ours.input_types})          # declared semantics, float64
+        try:
+            their_plan = dump_plan(theirs)
+        except Exception:                                                      # reference planner defect
+            dump_plan(ours)                                                    # ours must still plan
+            continue
+        assert _canon(dump_plan(ours)) == _canon(their_plan), (case, recipe)
+        planned += 1
+        if _has_batch_axes(their_plan):
+            continue
+        try:
+            got = theirs.compile()(**{k: inputs[k] for k in theirs.input_types})
+        except Exception:
+            continue
+        np.testing.assert_allclose(np.asarray(got, dtype=np.float64), want, rtol=2e-4, atol=2e-4,
+                                   err_msg=repr(ours))
+        valued += 1
+    assert planned >= N_CASES * 0.8 and valued >= N_CASES * 0.5, (planned, valued)
