@@ -147,3 +147,49 @@ def test_random_expressions_agree_with_the_unmodified_reference():
                                    err_msg=repr(ours))
         valued += 1
     assert planned >= N_CASES * 0.8 and valued >= N_CASES * 0.5, (planned, valued)
+
+
+def test_match_agrees_with_the_unmodified_reference():
+    """``match(expression, template, slot)`` (algebra.py:1037-1063) on random expression / template
+    pairs: same answer (by canonical form) or None on both sides."""
+    ref = load_reference_algebra()
+    rng = np.random.RandomState(911)
+    found = missed = 0
+    for case in range(120):
+        left, other = _recipe(rng, 2, 2), _recipe(rng, 2, 2)
+        fill = _recipe(rng, int(rng.choice([1, 2])), 1)
+        same_template = rng.rand() < 0.6
+        results = []
+        for ns in (ref, A):
+            variables = _variables(ns)
+            slot = ns.var('slot', _rank(fill))
+            expr = ns.dot(_build(ns, left, variables), _build(ns, fill, variables))
+            template = ns.dot(_build(ns, left if same_template else other, variables), slot)
+            try:
+                out = ns.match(expr, template, slot)
+            except Exception as exc:                   # same exception type on both sides
+                out = type(exc).__name__
+            results.append(None if out is None else (out if isinstance(out, str) else repr(ns.wrap_if_literal(out))))
+        assert results[0] == results[1], (case, left, fill, same_template, results)
+        if results[0] is None:
+            missed += 1
+        else:
+            found += 1
+    assert found >= 40 and missed >= 5, (found, missed)
+
+
+def _rank(recipe):
+    op = recipe[0]
+    if op == 'var':
+        return 2 if recipe[1] in ('X', 'Y') else 1
+    if op in ('T', 'outer'):
+        return 2
+    if op == 'scale':
+        return _rank(recipe[2])
+    if op in ('sumax', 'diag'):
+        return 1
+    if op in ('sumall', 'trace'):
+        return 0
+    if op == 'dot':
+        return _rank(recipe[1]) + _rank(recipe[2]) - 2
+    return _rank(recipe[1])
