@@ -193,3 +193,36 @@ def _rank(recipe):
     if op == 'dot':
         return _rank(recipe[1]) + _rank(recipe[2]) - 2
     return _rank(recipe[1])
+
+
+def _commute(rng, recipe):
+    """The same expression with the operands of some commutative nodes swapped."""
+    op = recipe[0]
+    if op == 'var':
+        return recipe
+    if op in ('mul', 'add') and rng.rand() < 0.7:
+        return (op, _commute(rng, recipe[2]), _commute(rng, recipe[1]))
+    return (op,) + tuple(_commute(rng, r) if isinstance(r, tuple) else r for r in recipe[1:])
+
+
+def test_expression_equality_agrees_with_the_unmodified_reference():
+    """``==`` on expressions (einsum isomorphism up to factor order and index renaming,
+    algebra.py:983-1034): same verdict as the reference on pairs that are equal by commutativity and on
+    unrelated pairs."""
+    ref = load_reference_algebra()
+    rng = np.random.RandomState(31)
+    equal = unequal = 0
+    for case in range(150):
+        rank = int(rng.randint(3))
+        first = _recipe(rng, rank, 3)
+        second = _commute(rng, first) if rng.rand() < 0.5 else _recipe(rng, rank, 3)
+        verdicts = []
+        for ns in (ref, A):
+            variables = _variables(ns)
+            a = ns.wrap_if_literal(_build(ns, first, variables))
+            b = ns.wrap_if_literal(_build(ns, second, variables))
+            verdicts.append(bool(a == b))
+        assert verdicts[0] == verdicts[1], (case, first, second, verdicts)
+        equal += verdicts[0]
+        unequal += not verdicts[0]
+    assert equal >= 40 and unequal >= 20, (equal, unequal)
