@@ -152,7 +152,8 @@ BB_API int bb_plan_last_launch_count(bb_plan* plan, int32_t* count);
  * (bayesic/distribution/base.py:328-332) for MultivariateNormal's (x, x x^T)
  * (bayesic/distribution/core.py:41-44), in ONE pass over X. */
 
-/* sum_x[d] = sum_n X[n,d];  sum_xxT[d,e] = sum_n X[n,d] X[n,e]   (float64 out).
+/* sum_x[d] = sum_n X[n,d];  sum_xxT[d,e] = sum_n X[n,d] X[n,e]   (float64 out): the plans of
+ * sum(X, 0) and dot(X.T, X) (algebra.py:1284-1294, :1151-1158), i.e. base.py:328-332 for core.py:41-44.
  * X is device float32 [n, d] row-major.  d <= 64 and d % 4 == 0 runs the
  * tcgen05 kernel; other d use the generic contraction kernels. */
 BB_API int64_t bb_suffstats_gaussian_workspace(int64_t n, int32_t d);
@@ -215,7 +216,7 @@ BB_API int bb_rowproj(const float* X, const float* W, int64_t n, int32_t d, int3
                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* G[d,q] = sum_n X[n,d] R[n,q] (float64 out): the plan _tensordot(_dimshuffle(X,1,0), R, [1],[0])
- * ("dot(X.T, R)") on tcgen05.  Needs d % 128 == 0, q % 64 == 0, (d/128)(q/64) <= 4. */
+ * ("dot(X.T, R)", algebra.py:1151-1158 -> 1347-1351) on tcgen05.  Needs d % 128 == 0, q % 64 == 0, (d/128)(q/64) <= 4. */
 BB_API int64_t bb_colproj_workspace(int64_t n, int32_t d, int32_t q);
 BB_API int bb_colproj(const float* X, const float* R, int64_t n, int32_t d, int32_t q, double* G,
                void* workspace, int64_t workspace_bytes, void* stream);
@@ -254,7 +255,9 @@ BB_API int bb_mixture_logits(const float* X, const float* U, const float* t, con
                       float* logits, float* lse, double* sum_lse,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Responsibility-weighted statistics in one pass over (R, X):
+/* Responsibility-weighted statistics in one pass over (R, X) -- the plans of sum(R, 0), dot(R.T, X)
+ * and einsum(R_nk X_nd X_ne -> kde), whose reference plan materialises K x D x N
+ * (algebra.py:527-765):
  *   Nk[k] = sum_n R[n,k];  sum_rx[k,d] = sum_n R[n,k] X[n,d];
  *   sum_rxx[k,d,e] = sum_n R[n,k] X[n,d] X[n,e]           (float64 out, device) */
 BB_API int64_t bb_suffstats_weighted_workspace(int64_t n, int32_t d, int32_t k);
@@ -262,7 +265,7 @@ BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int3
                           double* Nk, double* sum_rx, double* sum_rxx,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Same statistics with the responsibilities formed on the fly from the logits and their row
+/* Same statistics (same plans, algebra.py:527-765) with the responsibilities formed on the fly from the logits and their row
  * log-sum-exp (as bb_mixture_logits returns them): r[n,k] = exp(logits[n,k] - lse[n]) -- the
  * N x K responsibility matrix is never written.  tcgen05 path only: d % 8 == 0, d <= 64,
  * k % 4 == 0, k <= 256 (BB_ERR_UNSUPPORTED otherwise; normalise with bb_logsoftmax_rows and use
@@ -277,7 +280,7 @@ BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits
  * reparameterised gradients, :69-80 SVI).  All pointers are device pointers; nothing here
  * synchronises with the host, so a whole iteration can be enqueued on one stream. */
 
-/* VMP global step of a K-component Gaussian mixture with a Dirichlet(alpha0) prior on the
+/* VMP global step (README.md:30-37) of a K-component Gaussian mixture with a Dirichlet(alpha0) prior on the
  * weights and Gaussian-Wishart(m0, beta0, W0, nu0) priors on the components (Bishop PRML
  * 10.58-10.63), from the (all-reduced) statistics of the local step:
  *   alpha_k = alpha0 + N_k, beta_k = beta0 + N_k, nu_k = nu0 + N_k,
@@ -327,11 +330,12 @@ BB_API int bb_gather_rows(const float* X, int64_t n, int32_t d, const int64_t* i
 BB_API int bb_svi_natural_blend(double* eta, const double* eta_prior, const double* stat,
                          double scale, double rho, int64_t count, void* stream);
 
-/* Reparameterised draws W[s, j] = mu[j] + exp(log_sigma[j]) * eps[s, j]  (float32 out, [S, D]). */
+/* Reparameterised draws W[s, j] = mu[j] + exp(log_sigma[j]) * eps[s, j]  (float32 out, [S, D];
+ * README.md:47-51). */
 BB_API int bb_reparam_draws(const double* mu, const double* log_sigma, const double* eps,
                      int32_t d, int32_t s, float* W, void* stream);
 
-/* ELBO and its reparameterised gradient for q(w) = N(mu, diag sigma^2), prior N(0, I), from the
+/* ELBO and its reparameterised gradient (README.md:47-51) for q(w) = N(mu, diag sigma^2), prior N(0, I), from the
  * outputs of bb_logistic_reparam_pass (G[D, S], loglik[S]):
  *   elbo = mean_s loglik_s - KL,  grad_mu = mean_s G_s - mu,
  *   grad_log_sigma = mean_s (G_s * eps_s) * sigma - sigma^2 + 1. */
@@ -339,7 +343,8 @@ BB_API int bb_reparam_gradient(const double* G, const double* loglik, const doub
                         const double* mu, const double* log_sigma, int32_t d, int32_t s,
                         double* grad_mu, double* grad_log_sigma, double* elbo, void* stream);
 
-/* One Adam step on count float64 parameters (step counts from 1); maximize != 0 ascends. */
+/* One Adam step on count float64 parameters (step counts from 1); maximize != 0 ascends -- the
+ * optimiser step of the reparameterised-gradient loop (README.md:47-51). */
 BB_API int bb_adam_step(double* param, const double* grad, double* m, double* v, int64_t count,
                  double lr, double beta1, double beta2, double eps, int64_t step,
                  int32_t maximize, void* stream);
