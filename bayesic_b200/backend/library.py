@@ -8,6 +8,7 @@ exactly what this package replaces, not something it falls back to).
 import ctypes
 import os
 
+ABI_VERSION = 2
 MAX_DIMS = 8
 MAX_PARENTS = 8
 MAX_IPARAMS = 40
@@ -84,8 +85,18 @@ SIGNATURES = {
                                              _vp]),
     'bb_gmm_global_update': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'bb_allreduce_sum_p2p': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i64, ctypes.c_uint32, _dbl, _vp, _vp,
-                                            _vp, _vp, _dbl, _dbl, _i32, _vp, _vp]),
+    'bb_comm_flag_bytes': (_i64, [_i32]),
+    'bb_comm_create': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64,
+                                      _dbl, ctypes.POINTER(_vp)]),
+    'bb_comm_allreduce_sum': (ctypes.c_int, [_vp, _i64, _vp]),
+    'bb_comm_status': (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
+    'bb_comm_destroy': (ctypes.c_int, [_vp]),
+    'bb_gaussian_pass_create': (ctypes.c_int, [_i32, ctypes.POINTER(_vp)]),
+    'bb_gaussian_pass_peer_bytes': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    'bb_gaussian_pass_attach_peers': (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _dbl]),
+    'bb_gaussian_pass_run': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    'bb_gaussian_pass_status': (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
+    'bb_gaussian_pass_destroy': (ctypes.c_int, [_vp]),
     'bb_gather_rows': (ctypes.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
     'bb_svi_natural_blend': (ctypes.c_int, [_vp, _vp, _vp, _dbl, _dbl, _i64, _vp]),
     'bb_reparam_draws': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
@@ -110,7 +121,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bb_abi_version() != 1:
+    if lib.bb_abi_version() != ABI_VERSION:
         raise RuntimeError("bayesic_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -2,7 +2,9 @@
 
 The tree comes from ``Expression.lower()`` (every einsum replaced by its plan,
 ``bayesic/algebra.py:527-765``).  Lowering walks it once, de-duplicates shared
-sub-trees (structural equality), assigns input slots, and recognises three
+sub-trees (by object identity and by value-numbering the emitted descriptor rows -- NOT by the
+expressions' ``==``, which follows the reference in ignoring repeated factors / terms and
+batch-axis order, ``algebra.py:1297-1309``, and would merge ``X*X*Y`` with ``X*Y``), assigns input slots, and recognises three
 patterns that the executor serves with fused kernels instead of the reference's
 node-by-node evaluation (``algebra.py:34-40``):
 
@@ -62,21 +64,21 @@ def _is_scalar_literal(node, value):
     return isinstance(node, constant) and np.ndim(node.value) == 0 and node.value == value
 
 
-def _match_syrk(node):
+def _match_syrk(node, same):
     """X if node is ``_tensordot(_dimshuffle(X,1,0), X, [1],[0])`` (or the mirrored
     ``_tensordot(X', X, [0],[0])`` forms), else None."""
     if not isinstance(node, _tensordot) or node.X_batch_axes:
         return None
     a, b = node.parents
     if (isinstance(a, _dimshuffle) and a.axes == (1, 0) and a.parents[0].ndim == 2
-            and node.X_dot_axes == [1] and node.Y_dot_axes == [0] and a.parents[0] == b):
+            and node.X_dot_axes == [1] and node.Y_dot_axes == [0] and same(a.parents[0], b)):
         return b
-    if a.ndim == 2 and node.X_dot_axes == [0] and node.Y_dot_axes == [0] and a == b:
+    if a.ndim == 2 and node.X_dot_axes == [0] and node.Y_dot_axes == [0] and same(a, b):
         return b
     return None
 
 
-def _match_weighted_scatter(node):
+def _match_weighted_scatter(node, same):
     """(R, X) if node is the reference plan of ``sum_n R[n,k] X[n,d] X[n,e]``."""
     if not isinstance(node, _tensordot) or node.X_batch_axes:
         return None
@@ -93,12 +95,12 @@ def _match_weighted_scatter(node):
             found_r = factor.parents[0]
         elif factor.axes == ('x', 1, 0):
             found_x = factor.parents[0]
-    if found_r is None or found_x is None or found_x != x:
+    if found_r is None or found_x is None or not same(found_x, x):
         return None
     return found_r, x
 
 
-def _match_logsoftmax(node):
+def _match_logsoftmax(node, same):
     """Lg if node is ``Lg + (-1 * log(sum(exp(Lg), axis=last))) broadcast back``."""
     if not isinstance(node, add) or len(node.parents) != 2:
         return None
@@ -119,7 +121,7 @@ def _match_logsoftmax(node):
         if not isinstance(logsum, _sum) or logsum.axes != (1,):
             continue
         ex = logsum.parents[0]
-        if isinstance(ex, elemwise) and ex.name == 'exp' and ex.parents[0] == lg:
+        if isinstance(ex, elemwise) and ex.name == 'exp' and same(ex.parents[0], lg):
             return lg
     return None
 
@@ -146,8 +148,9 @@ def lower_plans(plan_trees, input_types, fuse=True):
     out = LoweredPlan()
     out.input_types = dict(input_types)
     slot_of_var = {}
-    memo = {}          # structural: Expression -> node index
-    by_id = {}
+    keep_alive = []    # ids in by_id stay valid while the nodes are referenced
+    by_id = {}         # id(Expression) -> node index (shared sub-trees)
+    numbered = {}      # (kind, ordered parents, iparams, fparam) -> node index
 
     def input_slot(name):
         if name not in slot_of_var:
@@ -155,68 +158,76 @@ def lower_plans(plan_trees, input_types, fuse=True):
             out.input_names.append(name)
         return slot_of_var[name]
 
+    def add_node(kind, parents=(), iparams=(), fparam=0.0, unique=False):
+        """Value numbering: two rows merge only when kind, the ORDERED parent list, every integer
+        parameter and the immediate agree -- so X*X*Y and X*Y, or tensordots that differ in
+        batch-axis order, stay distinct."""
+        key = (kind, tuple(parents), tuple(int(i) for i in iparams), float(fparam))
+        if not unique and key in numbered:
+            return numbered[key]
+        idx = out.add(kind, parents, iparams, fparam)
+        if not unique:
+            numbered[key] = idx
+        return idx
+
     def chain(kind, parents, iparams):
         """n-ary node with more parents than the descriptor holds: fold left."""
         parents = list(parents)
         while len(parents) > L.MAX_PARENTS:
-            head = out.add(kind, parents[:L.MAX_PARENTS], iparams)
+            head = add_node(kind, parents[:L.MAX_PARENTS], iparams)
             parents = [head] + parents[L.MAX_PARENTS:]
-        return out.add(kind, parents, iparams)
+        return add_node(kind, parents, iparams)
 
     def visit(node):
         if id(node) in by_id:
             return by_id[id(node)]
-        try:
-            if node in memo:
-                by_id[id(node)] = memo[node]
-                return memo[node]
-            hashable = True
-        except TypeError:
-            hashable = False
         idx = emit(node)
         by_id[id(node)] = idx
-        if hashable:
-            memo[node] = idx
+        keep_alive.append(node)
         return idx
+
+    def same(a, b):
+        """Strict equality of two sub-trees: they lower to the same descriptor row."""
+        return visit(a) == visit(b)
 
     def emit(node):
         if fuse:
-            x = _match_syrk(node)
+            x = _match_syrk(node, same)
             if x is not None:
-                return out.add(L.NODE_SYRK, [visit(x)])
-            rx = _match_weighted_scatter(node)
+                return add_node(L.NODE_SYRK, [visit(x)])
+            rx = _match_weighted_scatter(node, same)
             if rx is not None:
-                return out.add(L.NODE_WEIGHTED_SCATTER, [visit(rx[0]), visit(rx[1])])
-            lg = _match_logsoftmax(node)
+                return add_node(L.NODE_WEIGHTED_SCATTER, [visit(rx[0]), visit(rx[1])])
+            lg = _match_logsoftmax(node, same)
             if lg is not None:
-                return out.add(L.NODE_LOGSOFTMAX, [visit(lg)])
+                return add_node(L.NODE_LOGSOFTMAX, [visit(lg)])
         if isinstance(node, var):
-            return out.add(L.NODE_INPUT, iparams=[input_slot(node.name)])
+            return add_node(L.NODE_INPUT, iparams=[input_slot(node.name)])
         if isinstance(node, constant):
             value = np.asarray(node.value)
             if value.ndim == 0:
-                return out.add(L.NODE_SCALAR, fparam=float(value))
+                return add_node(L.NODE_SCALAR, fparam=float(value))
             slot = len(out.input_names)
             out.input_names.append('')
             out.bound_constants[slot] = np.ascontiguousarray(value, dtype=np.float32)
-            return out.add(L.NODE_INPUT, iparams=[slot])
+            return add_node(L.NODE_INPUT, iparams=[slot])
         if isinstance(node, shape):
-            return out.add(L.NODE_SHAPE, [visit(node.parents[0])], [node.axis])
+            return add_node(L.NODE_SHAPE, [visit(node.parents[0])], [node.axis])
         if isinstance(node, eye):
-            return out.add(L.NODE_EYE, [visit(node.parents[0])])
+            return add_node(L.NODE_EYE, [visit(node.parents[0])])
         if isinstance(node, _sum):
-            return out.add(L.NODE_SUM, [visit(node.parents[0])], sorted(node.axes))
+            return add_node(L.NODE_SUM, [visit(node.parents[0])], sorted(node.axes))
         if isinstance(node, _mul):
             return chain(L.NODE_MUL, [visit(p) for p in node.parents], [])
         if isinstance(node, _dimshuffle):
             axes = [-1 if a == 'x' else a for a in node.axes]
-            return out.add(L.NODE_DIMSHUFFLE, [visit(node.parents[0])], axes)
+            return add_node(L.NODE_DIMSHUFFLE, [visit(node.parents[0])], axes)
         if isinstance(node, _diagonal):
-            return out.add(L.NODE_DIAGONAL, [visit(node.parents[0])], [node.axis1, node.axis2])
+            return add_node(L.NODE_DIAGONAL, [visit(node.parents[0])], [node.axis1, node.axis2])
         if isinstance(node, _tensordot):
             params = ([len(node.X_dot_axes), len(node.X_batch_axes)] + node.X_dot_axes +
                       node.Y_dot_axes + node.X_batch_axes + node.Y_batch_axes)
-            return out.add(L.NODE_TENSORDOT, [visit(node.parents[0]), visit(node.parents[1])], params)
+            return add_node(L.NODE_TENSORDOT, [visit(node.parents[0]), visit(node.parents[1])], params)
         if isinstance(node, elemwise):        # includes add
             name = 'add' if isinstance(node, add) else node.name
             if name not in L.OP_CODES:
@@ -224,7 +235,7 @@ def lower_plans(plan_trees, input_types, fuse=True):
             parents = [visit(p) for p in node.parents]
             if name in ('add', 'mul'):
                 return chain(L.NODE_ELEMWISE, parents, [L.OP_CODES[name]])
-            return out.add(L.NODE_ELEMWISE, parents, [L.OP_CODES[name]])
+            return add_node(L.NODE_ELEMWISE, parents, [L.OP_CODES[name]])
         raise NotImplementedError("cannot lower %s to the plan descriptor" % type(node).__name__)
 
     for tree in plan_trees:

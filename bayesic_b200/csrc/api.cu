@@ -164,7 +164,7 @@ BB_API int bb_suffstats_gaussian_loglik(const float* X, int64_t n, int32_t d, do
                 static_cast<long long>(bb_suffstats_gaussian_workspace(n, d)));
       return BB_ERR_WORKSPACE;
     }
-    // two launches: statistics, then finalize with the log-likelihood in its last block
+    // one launch: statistics, cross-CTA reduction, log-likelihood by the last CTA
     return launch_suffstats_tc_loglik(X, n, d, sum_x, sum_xxT, n_total, E_Lambda, E_Lambda_mu, E_mu_L_mu, E_logdet,
                                       out, workspace, workspace_bytes, st);
   }
@@ -467,18 +467,203 @@ BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const do
                                   W_inv, U, t, c, kl, status, static_cast<cudaStream_t>(stream));
 }
 
-BB_API int bb_allreduce_sum_p2p(const void* peer_buffers, const void* peer_flags, int32_t rank, int32_t world,
-                         int64_t count, int64_t slot_stride, uint32_t epoch, double spin_limit_ms, double* out,
-                         int32_t* status, const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
-                         double e_logdet, int32_t d, double* elbo, void* stream) {
-  if (!peer_buffers || !peer_flags || !out || !status || (elbo && (!e_lambda || !e_lambda_mu))) {
-    set_error("allreduce_sum_p2p: bad arguments");
+// ---- multi-GPU: peer-memory communicator and the one-launch Gaussian pass ---------------------------
+
+struct bb_comm {
+  int rank = 0, world = 1, device = 0;
+  int64_t capacity = 0;
+  const double** in = nullptr;       // device arrays of `world` pointers
+  double** out = nullptr;
+  uint32_t** flags = nullptr;
+  int* status = nullptr;             // device: [0] status word, [1] epochs completed, [2] CTA ticket
+  double spin_limit_ms = 2000.0;
+};
+
+static int upload_ptrs(const void* const* host, int world, void** dev_out) {
+  void* dev = nullptr;
+  BB_CUDA_OK(cudaMalloc(&dev, sizeof(void*) * world));
+  cudaError_t e = cudaMemcpy(dev, host, sizeof(void*) * world, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    set_error("cudaMemcpy of the peer pointer table failed: %s", cudaGetErrorString(e));
+    return BB_ERR_CUDA;
+  }
+  *dev_out = dev;
+  return BB_OK;
+}
+
+BB_API int64_t bb_comm_flag_bytes(int32_t world) {
+  return static_cast<int64_t>(2) * world * BB_COMM_MAX_CTAS * sizeof(uint32_t);
+}
+
+BB_API int bb_comm_create(int32_t rank, int32_t world, const void* const* peer_in, const void* const* peer_out,
+                   const void* const* peer_flags, int64_t capacity, double spin_limit_ms, bb_comm** comm) {
+  if (comm == nullptr) { set_error("comm_create: null out-pointer"); return BB_ERR_INVALID; }
+  *comm = nullptr;
+  if (world < 1 || rank < 0 || rank >= world || capacity < 1 || !peer_in || !peer_out || !peer_flags) {
+    set_error("comm_create: bad arguments (rank %d world %d capacity %lld)", rank, world,
+              static_cast<long long>(capacity));
     return BB_ERR_INVALID;
   }
-  return launch_p2p_allreduce(static_cast<const double* const*>(peer_buffers),
-                              static_cast<uint32_t* const*>(const_cast<void*>(peer_flags)), rank, world, count,
-                              slot_stride, epoch, spin_limit_ms, out, status, e_lambda, e_lambda_mu, e_mu_l_mu,
-                              e_logdet, d, elbo, static_cast<cudaStream_t>(stream));
+  for (int r = 0; r < world; ++r)
+    if (!peer_in[r] || !peer_out[r] || !peer_flags[r] || reinterpret_cast<uintptr_t>(peer_in[r]) % 16 ||
+        reinterpret_cast<uintptr_t>(peer_out[r]) % 16) {
+      set_error("comm_create: peer buffer %d is null or not 16-byte aligned", r);
+      return BB_ERR_INVALID;
+    }
+  bb_comm* c = new (std::nothrow) bb_comm();
+  if (c == nullptr) { set_error("out of host memory"); return BB_ERR_INVALID; }
+  c->rank = rank; c->world = world; c->capacity = capacity;
+  if (spin_limit_ms > 0) c->spin_limit_ms = spin_limit_ms;
+  int st = BB_OK;
+  if (cudaGetDevice(&c->device) != cudaSuccess) st = BB_ERR_CUDA;
+  if (st == BB_OK) st = upload_ptrs(peer_in, world, reinterpret_cast<void**>(&c->in));
+  if (st == BB_OK) st = upload_ptrs(peer_out, world, reinterpret_cast<void**>(&c->out));
+  if (st == BB_OK) st = upload_ptrs(peer_flags, world, reinterpret_cast<void**>(&c->flags));
+  if (st == BB_OK && cudaMalloc(&c->status, 4 * sizeof(int)) != cudaSuccess) st = BB_ERR_CUDA;
+  if (st == BB_OK && cudaMemset(c->status, 0, 4 * sizeof(int)) != cudaSuccess) st = BB_ERR_CUDA;
+  if (st != BB_OK) {
+    if (st == BB_ERR_CUDA) set_error("comm_create: CUDA allocation failed");
+    bb_comm_destroy(c);
+    return st;
+  }
+  *comm = c;
+  return BB_OK;
+}
+
+BB_API int bb_comm_destroy(bb_comm* c) {
+  if (c == nullptr) return BB_OK;
+  if (c->in) cudaFree(c->in);
+  if (c->out) cudaFree(c->out);
+  if (c->flags) cudaFree(c->flags);
+  if (c->status) cudaFree(c->status);
+  delete c;
+  return BB_OK;
+}
+
+BB_API int bb_comm_allreduce_sum(bb_comm* c, int64_t count, void* stream) {
+  if (c == nullptr || count < 0 || count > c->capacity) {
+    set_error("comm_allreduce_sum: bad arguments (count %lld, capacity %lld)", static_cast<long long>(count),
+              c ? static_cast<long long>(c->capacity) : 0LL);
+    return BB_ERR_INVALID;
+  }
+  return launch_p2p_allreduce(c->in, c->out, c->flags, c->rank, c->world, count,
+                              reinterpret_cast<uint32_t*>(c->status + 1), reinterpret_cast<unsigned int*>(c->status + 2),
+                              c->spin_limit_ms, c->status, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_comm_status(bb_comm* c, int32_t* status, void* stream) {
+  if (c == nullptr || status == nullptr) { set_error("comm_status: null argument"); return BB_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int host = 0;
+  BB_CUDA_OK(cudaMemcpyAsync(&host, c->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BB_CUDA_OK(cudaStreamSynchronize(st));
+  *status = host;
+  return BB_OK;
+}
+
+struct bb_gaussian_pass {
+  int d = 0, device = 0;
+  void* ws = nullptr;
+  int64_t ws_bytes = 0;
+  int* status = nullptr;           // device: [0] status word, [1] epochs completed
+  int rank = 0, world = 1;
+  double** peer_recv = nullptr;
+  uint32_t** peer_flags = nullptr;
+  int64_t stride = 0;
+  double spin_limit_ms = 2000.0;
+};
+
+static int64_t pass_stride(int d) { return align_up(static_cast<int64_t>(d) * d + d + 1, 32); }
+
+BB_API int bb_gaussian_pass_peer_bytes(int32_t d, int32_t world, int64_t* recv_bytes, int64_t* flag_bytes) {
+  if (d < 1 || world < 1 || !recv_bytes || !flag_bytes) { set_error("gaussian_pass_peer_bytes: bad arguments"); return BB_ERR_INVALID; }
+  *recv_bytes = 2 * static_cast<int64_t>(world) * pass_stride(d) * sizeof(double);
+  *flag_bytes = static_cast<int64_t>(world) * BB_GAUSSIAN_PASS_SLICES * sizeof(uint32_t);
+  return BB_OK;
+}
+
+BB_API int bb_gaussian_pass_create(int32_t d, bb_gaussian_pass** pass) {
+  if (pass == nullptr) { set_error("gaussian_pass_create: null out-pointer"); return BB_ERR_INVALID; }
+  *pass = nullptr;
+  if (!(d >= 4 && d <= 64 && d % 4 == 0)) {
+    set_error("gaussian_pass_create: needs d <= 64 and d %% 4 == 0 (got %d)", d);
+    return BB_ERR_UNSUPPORTED;
+  }
+  bb_gaussian_pass* p = new (std::nothrow) bb_gaussian_pass();
+  if (p == nullptr) { set_error("out of host memory"); return BB_ERR_INVALID; }
+  p->d = d;
+  p->ws_bytes = suffstats_tc_workspace(int64_t(1) << 30) + 256;      // full grid
+  if (cudaGetDevice(&p->device) != cudaSuccess || cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess ||
+      cudaMalloc(&p->status, 2 * sizeof(int)) != cudaSuccess || cudaMemset(p->status, 0, 2 * sizeof(int)) != cudaSuccess) {
+    set_error("gaussian_pass_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    bb_gaussian_pass_destroy(p);
+    return BB_ERR_CUDA;
+  }
+  *pass = p;
+  return BB_OK;
+}
+
+BB_API int bb_gaussian_pass_attach_peers(bb_gaussian_pass* p, int32_t rank, int32_t world, const void* const* peer_recv,
+                                  const void* const* peer_flags, double spin_limit_ms) {
+  if (p == nullptr || world < 1 || rank < 0 || rank >= world || !peer_recv || !peer_flags) {
+    set_error("gaussian_pass_attach_peers: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  for (int r = 0; r < world; ++r)
+    if (!peer_recv[r] || !peer_flags[r]) { set_error("gaussian_pass_attach_peers: peer %d has a null buffer", r); return BB_ERR_INVALID; }
+  if (p->peer_recv) cudaFree(p->peer_recv);
+  if (p->peer_flags) cudaFree(p->peer_flags);
+  p->peer_recv = nullptr; p->peer_flags = nullptr;
+  BB_TRY(upload_ptrs(peer_recv, world, reinterpret_cast<void**>(&p->peer_recv)));
+  BB_TRY(upload_ptrs(peer_flags, world, reinterpret_cast<void**>(&p->peer_flags)));
+  p->rank = rank; p->world = world; p->stride = pass_stride(p->d);
+  BB_CUDA_OK(cudaMemset(p->status, 0, 2 * sizeof(int)));
+  if (spin_limit_ms > 0) p->spin_limit_ms = spin_limit_ms;
+  return BB_OK;
+}
+
+BB_API int bb_gaussian_pass_run(bb_gaussian_pass* p, const float* X, int64_t n, const double* E_Lambda,
+                         const double* E_Lambda_mu, double E_mu_L_mu, double E_logdet, double n_total,
+                         double* sum_x, double* sum_xxT, double* count_out, double* loglik, void* stream) {
+  if (p == nullptr || sum_xxT == nullptr || n < 0 || (n > 0 && X == nullptr)) {
+    set_error("gaussian_pass_run: bad arguments");
+    return BB_ERR_INVALID;
+  }
+  SuffstatsTail t;
+  memset(&t, 0, sizeof(t));
+  t.s2 = sum_xxT; t.s1 = sum_x; t.count_out = count_out;
+  t.e_lambda = E_Lambda; t.e_lambda_mu = E_Lambda_mu; t.e_mu_l_mu = E_mu_L_mu; t.e_logdet = E_logdet;
+  t.n_total = n_total; t.loglik = loglik;
+  t.local_count = static_cast<double>(n);
+  t.rank = p->rank; t.world = p->world;
+  t.status = p->status;
+  if (p->world > 1) {
+    t.peer_recv = p->peer_recv; t.peer_flags = p->peer_flags; t.stride = p->stride;
+    t.epoch_dev = reinterpret_cast<uint32_t*>(p->status + 1);
+    t.spin_limit = static_cast<long long>(p->spin_limit_ms * 2.0e6);
+  }
+  return launch_suffstats_tc_fused(X, n, p->d, p->ws, p->ws_bytes, t, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_gaussian_pass_status(bb_gaussian_pass* p, int32_t* status, void* stream) {
+  if (p == nullptr || status == nullptr) { set_error("gaussian_pass_status: null argument"); return BB_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int host = 0;
+  BB_CUDA_OK(cudaMemcpyAsync(&host, p->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BB_CUDA_OK(cudaStreamSynchronize(st));
+  *status = host;
+  return BB_OK;
+}
+
+BB_API int bb_gaussian_pass_destroy(bb_gaussian_pass* p) {
+  if (p == nullptr) return BB_OK;
+  if (p->ws) cudaFree(p->ws);
+  if (p->status) cudaFree(p->status);
+  if (p->peer_recv) cudaFree(p->peer_recv);
+  if (p->peer_flags) cudaFree(p->peer_flags);
+  delete p;
+  return BB_OK;
 }
 
 BB_API int bb_gather_rows(const float* X, int64_t n, int32_t d, const int64_t* index, int64_t m, float* out,

@@ -29,8 +29,34 @@ int launch_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, 
                 int64_t sBn, void* workspace, cudaStream_t stream);
 
 // suffstats_sm100.cu
+#define BB_GAUSSIAN_PASS_SLICES 128
+// What the statistics kernel does after its main loop, in the same launch: where the reduced
+// statistics go, the optional expected-log-likelihood consumer, and (world > 1) the peer-memory
+// exchange.  d, scratch and ticket are filled in by the launcher.
+struct SuffstatsTail {
+  double* s2;                  // [d, d] out (added to when accumulate)
+  double* s1;                  // [d] out, may be null
+  double* count_out;           // reduced row count out, may be null
+  int d, accumulate;
+  const double* e_lambda;      // consumer: E_q[sum_n log N(x_n | mu, Lambda^-1)] -> loglik (null: none)
+  const double* e_lambda_mu;
+  double e_mu_l_mu, e_logdet, n_total;   // n_total is used when world == 1; the reduced count otherwise
+  double* loglik;
+  double* scratch;             // [BB_GAUSSIAN_PASS_SLICES + 1]
+  unsigned int* ticket;
+  double local_count;          // this rank's row count (payload element d*d + d)
+  int rank, world;
+  double* const* peer_recv;    // device array [world]: receive buffers, [2][world][stride] float64 each
+  uint32_t* const* peer_flags; // device array [world]: flag arrays, [world][BB_GAUSSIAN_PASS_SLICES] uint32 each
+  int64_t stride;
+  uint32_t* epoch_dev;         // device word: epochs completed so far (this launch is stored + 1)
+  long long spin_limit;        // clock64 ticks
+  int* status;                 // 1 + rank of a lost peer
+};
 bool suffstats_tc_supported(int64_t n, int d, const void* x);
 int64_t suffstats_tc_workspace(int64_t n);
+int launch_suffstats_tc_fused(const float* x, int64_t n, int d, void* workspace, int64_t workspace_bytes,
+                              SuffstatsTail tail, cudaStream_t stream);
 int launch_suffstats_tc_loglik(const float* x, int64_t n, int d, double* s1, double* s2, double n_total,
                                const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
                                double e_logdet, double* loglik, void* workspace, int64_t workspace_bytes,
@@ -119,11 +145,12 @@ int launch_reparam_gradient(const double* g, const double* loglik, const double*
 int launch_adam_step(double* param, const double* grad, double* m, double* v, int64_t count, double lr, double b1,
                      double b2, double eps, int64_t step, int maximize, cudaStream_t stream);
 
-// p2p_reduce.cu: one-shot all-reduce over peer memory (+ fused expected log-likelihood)
-int launch_p2p_allreduce(const double* const* bufs, uint32_t* const* flags, int rank, int world, int64_t count,
-                         int64_t slot_stride, uint32_t epoch, double spin_limit_ms, double* out, int* status,
-                         const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu, double e_logdet, int d,
-                         double* elbo, cudaStream_t stream);
+// p2p_reduce.cu: two-shot all-reduce over peer memory, counterpart-CTA handshakes (no grid barrier)
+#define BB_COMM_MAX_CTAS 64
+int comm_grid_for(int64_t count, int world);
+int launch_p2p_allreduce(const double* const* in, double* const* out, uint32_t* const* flags, int rank, int world,
+                         int64_t count, uint32_t* epoch_dev, unsigned int* ticket, double spin_limit_ms, int* status,
+                         cudaStream_t stream);
 
 // stats_kernels.cu
 int launch_f32_to_f64(const float* in, double* out, int64_t n, cudaStream_t stream);

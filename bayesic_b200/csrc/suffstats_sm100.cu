@@ -27,17 +27,33 @@
 //   * FP32 accumulation in TMEM is drained every 512 rows into float64 registers by eight
 //     epilogue warps (double-buffered accumulators, so the MMA never waits);
 //   * Sigma x rides along for free in the split warps (they already touch every element);
-//   * per-CTA float64 partials go to a workspace; a tiny finalize kernel adds them up in a
-//     fixed order (deterministic) and applies the symmetrisation above.
+//   * per-CTA float64 partials go to a workspace (L2-resident, 148 x 65.5 KB) and the SAME launch
+//     finishes the job (round 2; round 1 needed a finalize launch + an all-reduce launch):
+//     one grid-wide barrier (cooperative launch), then the d*d + d + 1 outputs are cut into 128
+//     slices and CTA j adds up slice j over all partials in a fixed order (deterministic), applying
+//     the symmetrisation above;
+//   * multi-GPU (world > 1): CTA j then PUSHES its slice into every peer's receive buffer over
+//     NVLink (plain stores into peer memory), publishes a per-slice flag (st.release.sys), waits for
+//     the peers' flags of the same slice only (so the exchange pipelines slice by slice, no second
+//     grid barrier), and sums the world's contributions from LOCAL memory in rank order -- the result
+//     is bit-identical on every rank.  Receive buffers are double-buffered by epoch parity;
+//   * the expected log-likelihood (ELBO term) of the reduced statistics is a per-slice dot product
+//     with E[Lambda], E[Lambda mu]; the last CTA to finish (atomic ticket) adds the 128 slice terms
+//     in order.  One launch per step on any number of GPUs.
 //
 // Algorithmic traffic: 4*d bytes per row, read once.  Nothing else touches HBM except
 // 148 x 65.5 KB of partials.
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "kernels.h"
 #include "sm100_ptx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bb {
 
@@ -152,13 +168,148 @@ __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, i
     partial_s1[(static_cast<int64_t>(blockIdx.x) * 2 + khalf) * kFeat + half * 32 + lane] = s1;
 }
 
+// ---- fused tail: cross-CTA reduction, cross-GPU exchange, expected log-likelihood ----------------
+constexpr int kSlices = BB_GAUSSIAN_PASS_SLICES;   // output slices (and per-peer flags); grid-size independent so
+                                                   // that ranks whose grids differ agree on the slicing
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Runs in every CTA after its partials are written and the grid barrier has passed.
+// `red` is kThreads doubles of shared memory (the drained pipeline stages are reused).
+__device__ __forceinline__ void fused_tail(const SuffstatsTail& tp, const double* __restrict__ partial_s2,
+                                           const double* __restrict__ partial_s1, double* red,
+                                           volatile int* sflag) {
+  const int t = threadIdx.x;
+  const int d = tp.d;
+  const int elements = d * d + d + 1;                     // [S2 | S1 | row count]
+  const int per = (elements + kSlices - 1) / kSlices;     // outputs per slice (33 at d = 64)
+  const int groups = kThreads / per;                      // partial groups summed in parallel
+  const int e = t % per, g = t / per;
+  const int grid = gridDim.x;
+  const bool want_ll = tp.loglik != nullptr;
+  // the epoch lives in device memory (this launch uses stored + 1; the last CTA stores it back), so a
+  // captured CUDA graph can be replayed: no per-launch host argument changes
+  const uint32_t epoch = tp.world > 1 ? __ldcg(tp.epoch_dev) + 1u : 0u;
+  const int64_t parity_off = static_cast<int64_t>(epoch & 1u) * tp.world * tp.stride;
+  for (int slice = blockIdx.x; slice < kSlices && slice * per < elements; slice += grid) {
+    const int idx = slice * per + e;
+    double acc = 0.0;
+    if (g < groups && idx < elements) {
+      if (idx < d * d) {
+        const int r = idx / d, c = idx % d;
+        for (int p = g; p < grid; p += groups) {
+          const double* P = partial_s2 + static_cast<int64_t>(p) * 128 * kFeat;
+          acc += __ldcg(P + r * kFeat + c) + __ldcg(P + (kFeat + r) * kFeat + c) + __ldcg(P + (kFeat + c) * kFeat + r);
+        }
+      } else if (idx < d * d + d) {
+        const int f = idx - d * d;
+        for (int p = g; p < grid; p += groups)
+          acc += __ldcg(partial_s1 + static_cast<int64_t>(2 * p) * kFeat + f) +
+                 __ldcg(partial_s1 + static_cast<int64_t>(2 * p + 1) * kFeat + f);
+      } else if (g == 0) {
+        acc = tp.local_count;
+      }
+    }
+    if (g < groups) red[g * per + e] = acc;
+    if (t == 0) *sflag = 0;
+    __syncthreads();
+    const bool owner = g == 0 && idx < elements;          // threads 0 .. per-1
+    double v = 0.0;
+    if (owner)
+      for (int j = 0; j < groups; ++j) v += red[j * per + e];     // fixed order: deterministic
+    if (tp.world > 1) {
+      if (owner) {
+        // push this rank's slice into every rank's receive buffer (own included), slot [rank]
+        for (int r = 0; r < tp.world; ++r) tp.peer_recv[r][parity_off + tp.rank * tp.stride + idx] = v;
+        __threadfence_system();
+      }
+      __syncthreads();
+      if (t < tp.world) {
+        st_release_sys_u32(tp.peer_flags[t] + tp.rank * kSlices + slice, epoch);
+        const uint32_t* mine = tp.peer_flags[tp.rank] + t * kSlices + slice;
+        const long long t0 = clock64();
+        // epochs are compared as signed distances so that the counter may wrap
+        while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - epoch) < 0) {
+          if (clock64() - t0 > tp.spin_limit) {
+            atomicMax(tp.status, t + 1);
+            *sflag = 1;
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      if (owner) {
+        if (*sflag) {
+          v = __longlong_as_double(0x7ff8000000000000LL);  // lost peer: poison, never a partial sum
+        } else {
+          const double* mine = tp.peer_recv[tp.rank] + parity_off + idx;
+          v = 0.0;
+          for (int r = 0; r < tp.world; ++r) v += __ldcv(mine + r * tp.stride);   // rank order: same bits everywhere
+        }
+      }
+    }
+    double term = 0.0;
+    if (owner) {
+      if (idx < d * d) {
+        if (tp.accumulate) v += tp.s2[idx];
+        tp.s2[idx] = v;
+        if (want_ll) term = -0.5 * tp.e_lambda[idx] * v;
+      } else if (idx < d * d + d) {
+        const int f = idx - d * d;
+        if (tp.s1 != nullptr) {
+          if (tp.accumulate) v += tp.s1[f];
+          tp.s1[f] = v;
+        }
+        if (want_ll) term = v * tp.e_lambda_mu[f];
+      } else {
+        if (tp.count_out != nullptr) *tp.count_out = v;
+        tp.scratch[kSlices] = v;
+      }
+    }
+    __syncthreads();                                       // red[] is reused below
+    if (want_ll) {
+      if (t < per) red[t] = term;
+      __syncthreads();
+      if (t == 0) {
+        double total = 0.0;
+        for (int j = 0; j < per; ++j) total += red[j];
+        tp.scratch[slice] = total;
+      }
+      __syncthreads();
+    }
+  }
+  if (!want_ll && tp.world == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) *sflag = atomicAdd(tp.ticket, 1u) == static_cast<unsigned int>(grid) - 1u;
+  __syncthreads();
+  if (!*sflag || t != 0) return;
+  // last CTA of the grid: every CTA has read the stored epoch (before the grid barrier) and finished
+  __threadfence();
+  if (tp.world > 1) *tp.epoch_dev = epoch;
+  if (!want_ll) return;
+  double total = 0.0;
+  const int used = (elements + per - 1) / per;
+  for (int j = 0; j < used; ++j) total += __ldcg(tp.scratch + j);
+  const double n = tp.world > 1 ? __ldcg(tp.scratch + kSlices) : tp.n_total;
+  const double log_2pi = 1.8378770664093454835606594728112;
+  tp.loglik[0] = total - 0.5 * n * d * log_2pi + 0.5 * n * tp.e_logdet - 0.5 * n * tp.e_mu_l_mu;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
                     double* __restrict__ partial_s2,   // [grid][128][64]
                     double* __restrict__ partial_s1,   // [grid][2][64]
-                    unsigned int* __restrict__ fin_counter) {   // block counter of the finalize kernel's tail
+                    const SuffstatsTail tail) {
   extern __shared__ uint8_t smem_raw[];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *fin_counter = 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *tail.ticket = 0u;     // ordered before its use by the grid barrier
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
@@ -184,7 +335,7 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
     }
     __syncwarp();
     ptx::tmem_alloc(&sm.tmem_base, kTmemCols);
-  } else if (warp == kTmaWarp && lane == 0) {
+  } else if (warp == kTmaWarp && lane == 0 && n_tiles > 0) {
     ptx::prefetch_tensormap(&x_map);
   }
   ptx::tc_fence_before_sync();
@@ -281,84 +432,12 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
-}
-
-// S2[r,c] = sum_cta ( P[r][c] + P[64+r][c] + P[64+c][r] ),  S1[d] = sum_cta p1[d].
-// Blocks 0..nb-1: 32 consecutive outputs x 8 groups of partials each (fixed summation order:
-// deterministic); the last block reduces S1 (64 features x 4 groups).
-constexpr int kFinThreads = 256;
-
-// Optional consumer fused into the finalize kernel: the last block to finish evaluates the Gaussian
-// expected log-likelihood from the finished statistics (stats_kernels.cu has the stand-alone
-// kernel), which saves a launch on the single-GPU step.
-struct LoglikTail {
-  const double* e_lambda;
-  const double* e_lambda_mu;
-  double e_mu_l_mu, e_logdet, n;
-  double* out;                    // nullptr: no tail
-  unsigned int* counter;          // zeroed by suffstats_tc_kernel
-};
-
-__global__ void __launch_bounds__(kFinThreads)
-suffstats_finalize_kernel(const double* __restrict__ partial_s2,
-                          const double* __restrict__ partial_s1, int n_partials, int d,
-                          int accumulate, double* __restrict__ s2, double* __restrict__ s1,
-                          const LoglikTail tail) {
-  __shared__ double red[kFinThreads];
-  __shared__ bool is_last;
-  const int t = threadIdx.x;
-  if (blockIdx.x + 1 < gridDim.x) {
-    const int lane_c = t & 31, g = t >> 5;
-    const int idx = blockIdx.x * 32 + lane_c;
-    double acc = 0.0;
-    if (idx < d * d) {
-      const int r = idx / d, c = idx % d;
-#pragma unroll 4
-      for (int p = g; p < n_partials; p += 8) {
-        const double* P = partial_s2 + static_cast<int64_t>(p) * 128 * kFeat;
-        acc += P[r * kFeat + c] + P[(kFeat + r) * kFeat + c] + P[(kFeat + c) * kFeat + r];
-      }
-    }
-    red[t] = acc;
-    __syncthreads();
-    if (g == 0 && idx < d * d) {
-      double total = 0.0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) total += red[j * 32 + lane_c];
-      s2[idx] = accumulate ? s2[idx] + total : total;
-    }
-  } else if (s1 != nullptr) {
-    const int f = t & 63, g = t >> 6;
-    double acc = 0.0;
-#pragma unroll 4
-    for (int p = g; p < 2 * n_partials; p += 4) acc += partial_s1[static_cast<int64_t>(p) * kFeat + f];
-    red[t] = acc;
-    __syncthreads();
-    if (g == 0 && f < d) {
-      const double total = red[f] + red[64 + f] + red[128 + f] + red[192 + f];
-      s1[f] = accumulate ? s1[f] + total : total;
-    }
-  }
-  if (tail.out == nullptr) return;
-  __threadfence();                                   // this block's statistics are visible device-wide
-  __syncthreads();
-  if (t == 0) is_last = atomicAdd(tail.counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
+  // every CTA's partials are complete and visible before any CTA reads them
   __threadfence();
-  double acc = 0.0;
-  for (int i = t; i < d * d; i += kFinThreads) acc -= 0.5 * tail.e_lambda[i] * __ldcg(s2 + i);
-  for (int i = t; i < d; i += kFinThreads) acc += __ldcg(s1 + i) * tail.e_lambda_mu[i];
-  red[t] = acc;
-  __syncthreads();
-  for (int w = kFinThreads / 2; w > 0; w >>= 1) {
-    if (t < w) red[t] += red[t + w];
-    __syncthreads();
-  }
-  if (t == 0) {
-    const double log_2pi = 1.8378770664093454835606594728112;
-    tail.out[0] = red[0] - 0.5 * tail.n * d * log_2pi + 0.5 * tail.n * tail.e_logdet - 0.5 * tail.n * tail.e_mu_l_mu;
-  }
+  cg::this_grid().sync();
+  // the pipeline is drained (every TMA load was consumed): its first stage is scratch now
+  fused_tail(tail, partial_s2, partial_s1, reinterpret_cast<double*>(sm.stage[0]),
+             reinterpret_cast<volatile int*>(&sm.tmem_base));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -386,20 +465,28 @@ bool suffstats_tc_supported(int64_t n, int d, const void* x) {
          (reinterpret_cast<uintptr_t>(x) % 16) == 0 && n < (int64_t(1) << 31) - kTileRows;
 }
 
-int64_t suffstats_tc_workspace(int64_t n) {
+namespace {
+int grid_for(int64_t n) {
   const int64_t tiles = (n + kTileRows - 1) / kTileRows;
   int64_t grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (tiles < grid) grid = tiles > 0 ? tiles : 1;
-  return grid * (128 * kFeat + 2 * kFeat) * static_cast<int64_t>(sizeof(double)) + 512;   // + finalize counter
+  return static_cast<int>(grid);
+}
+}  // namespace
+
+// partials + [kSlices + 1] float64 tail scratch + ticket
+int64_t suffstats_tc_workspace(int64_t n) {
+  return grid_for(n) * (128 * kFeat + 2 * kFeat) * static_cast<int64_t>(sizeof(double)) +
+         (kSlices + 2) * static_cast<int64_t>(sizeof(double)) + 512;
 }
 
-namespace {
-// s1 may be nullptr.  s1/s2 are device float64; with `accumulate` the results are added to them.
-int launch_suffstats_tc_impl(const float* x, int64_t n, int d, double* s1, double* s2,
-                             void* workspace, int64_t workspace_bytes, bool accumulate, LoglikTail tail,
-                             cudaStream_t stream) {
-  if (!suffstats_tc_supported(n, d, x)) {
+// ONE cooperative launch: statistics, cross-CTA reduction, (world > 1) cross-GPU exchange, expected
+// log-likelihood.  `tail` carries outputs / consumers / peers; its scratch and ticket are carved from the
+// workspace here.  n == 0 is allowed (a rank with no rows still takes part in the exchange).
+int launch_suffstats_tc_fused(const float* x, int64_t n, int d, void* workspace, int64_t workspace_bytes,
+                              SuffstatsTail tail, cudaStream_t stream) {
+  if (n < 0 || d < 4 || d > kFeat || (d % 4) != 0 || (n > 0 && !suffstats_tc_supported(n, d, x))) {
     set_error("suffstats_tc: unsupported shape n=%lld d=%d", static_cast<long long>(n), d);
     return BB_ERR_UNSUPPORTED;
   }
@@ -409,61 +496,90 @@ int launch_suffstats_tc_impl(const float* x, int64_t n, int d, double* s1, doubl
               static_cast<long long>(need));
     return BB_ERR_WORKSPACE;
   }
-  EncodeTiledFn encode = get_encode_tiled();
-  if (encode == nullptr) {
-    set_error("cuTensorMapEncodeTiled unavailable from the driver");
-    return BB_ERR_CUDA;
+  if (tail.s2 == nullptr || (tail.loglik != nullptr && (tail.e_lambda == nullptr || tail.e_lambda_mu == nullptr)) ||
+      (tail.world > 1 && (tail.peer_recv == nullptr || tail.peer_flags == nullptr || tail.status == nullptr ||
+                          tail.accumulate || tail.rank < 0 || tail.rank >= tail.world ||
+                          tail.stride < static_cast<int64_t>(d) * d + d + 1 || tail.world > kThreads ||
+                          tail.epoch_dev == nullptr))) {
+    set_error("suffstats_tc: bad tail arguments");
+    return BB_ERR_INVALID;
   }
   CUtensorMap map;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d) * sizeof(float)};
-  const cuuint32_t box[2] = {kBoxCols, kTileRows};
-  const cuuint32_t estride[2] = {1, 1};
-  CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim,
-                       gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%lld d=%d)", static_cast<int>(cr),
-              static_cast<long long>(n), d);
-    return BB_ERR_CUDA;
+  memset(&map, 0, sizeof(map));
+  if (n > 0) {
+    EncodeTiledFn encode = get_encode_tiled();
+    if (encode == nullptr) {
+      set_error("cuTensorMapEncodeTiled unavailable from the driver");
+      return BB_ERR_CUDA;
+    }
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d) * sizeof(float)};
+    const cuuint32_t box[2] = {kBoxCols, kTileRows};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim,
+                         gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%lld d=%d)", static_cast<int>(cr),
+                static_cast<long long>(n), d);
+      return BB_ERR_CUDA;
+    }
   }
-  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
-  int grid = device_sm_count();
-  if (tiles < grid) grid = static_cast<int>(tiles);
+  int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  const int grid = grid_for(n);
   double* partial_s2 = reinterpret_cast<double*>(
       (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
   double* partial_s1 = partial_s2 + static_cast<int64_t>(grid) * 128 * kFeat;
-  unsigned int* fin_counter = reinterpret_cast<unsigned int*>(partial_s1 + static_cast<int64_t>(grid) * 2 * kFeat);
-  tail.counter = fin_counter;
+  tail.scratch = partial_s1 + static_cast<int64_t>(grid) * 2 * kFeat;
+  tail.ticket = reinterpret_cast<unsigned int*>(tail.scratch + kSlices + 1);
+  tail.d = d;
+  if (tail.world < 1) tail.world = 1;
 
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout)) + 1024;
   static SmemOptIn smem_opt_in_0;
   BB_CUDA_OK(smem_opt_in_0.ensure(suffstats_tc_kernel, smem_bytes));
-  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial_s2, partial_s1, fin_counter);
+  void* args[] = {&map, &tiles, &partial_s2, &partial_s1, &tail};
+  // cooperative: the grid barrier needs every CTA resident (grid <= SM count, one CTA per SM)
+  BB_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(suffstats_tc_kernel), dim3(grid), dim3(kThreads),
+                                         args, smem_bytes, stream));
   BB_CHECK_LAUNCH("suffstats_tc_kernel");
-  const int fin_blocks = (d * d + 31) / 32 + 1;
-  suffstats_finalize_kernel<<<fin_blocks, kFinThreads, 0, stream>>>(partial_s2, partial_s1, grid, d,
-                                                                    accumulate ? 1 : 0, s2, s1, tail);
-  BB_CHECK_LAUNCH("suffstats_finalize_kernel");
   return BB_OK;
+}
+
+namespace {
+SuffstatsTail local_tail(double* s1, double* s2, bool accumulate, double local_count) {
+  SuffstatsTail t;
+  memset(&t, 0, sizeof(t));
+  t.s1 = s1;
+  t.s2 = s2;
+  t.accumulate = accumulate ? 1 : 0;
+  t.local_count = local_count;
+  t.world = 1;
+  return t;
 }
 }  // namespace
 
 int launch_suffstats_tc_acc(const float* x, int64_t n, int d, double* s1, double* s2,
                             void* workspace, int64_t workspace_bytes, bool accumulate,
                             cudaStream_t stream) {
-  LoglikTail none = {nullptr, nullptr, 0.0, 0.0, 0.0, nullptr, nullptr};
-  return launch_suffstats_tc_impl(x, n, d, s1, s2, workspace, workspace_bytes, accumulate, none, stream);
+  return launch_suffstats_tc_fused(x, n, d, workspace, workspace_bytes,
+                                   local_tail(s1, s2, accumulate, static_cast<double>(n)), stream);
 }
 
-// statistics and, in the finalize kernel's last block, the expected log-likelihood from them (s1 required)
+// statistics and the expected log-likelihood from them in the same launch
 int launch_suffstats_tc_loglik(const float* x, int64_t n, int d, double* s1, double* s2, double n_total,
                                const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
                                double e_logdet, double* loglik, void* workspace, int64_t workspace_bytes,
                                cudaStream_t stream) {
-  LoglikTail tail = {e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet, n_total, loglik, nullptr};
-  return launch_suffstats_tc_impl(x, n, d, s1, s2, workspace, workspace_bytes, false, tail, stream);
+  SuffstatsTail t = local_tail(s1, s2, false, static_cast<double>(n));
+  t.e_lambda = e_lambda;
+  t.e_lambda_mu = e_lambda_mu;
+  t.e_mu_l_mu = e_mu_l_mu;
+  t.e_logdet = e_logdet;
+  t.n_total = n_total;
+  t.loglik = loglik;
+  return launch_suffstats_tc_fused(x, n, d, workspace, workspace_bytes, t, stream);
 }
 
 int launch_suffstats_tc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,

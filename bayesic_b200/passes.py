@@ -26,9 +26,34 @@ from . import stats
 from . import updates
 from .backend.compiled import compile_many
 
-__all__ = ['gaussian_pass', 'GmmStep', 'LinRegSviStep', 'FactorAnalysisStep', 'LogisticReparamGrad']
+__all__ = ['gaussian_pass', 'GmmStep', 'LinRegSviStep', 'FactorAnalysisStep', 'LogisticReparamGrad',
+           'gram_issued_flops_per_row', 'gmm_issued_flops_per_row']
 
 _LOG_2PI = math.log(2.0 * math.pi)
+
+
+def gram_issued_flops_per_row(d):
+    """Tensor-core flops ``gram_pair_kernel`` really issues per data row (csrc/gram_sm100.cu): the
+    upper-triangle 256 x 256 feature blocks, BF16x3 = three bf16 products per off-diagonal block and
+    two per diagonal block (b1^T b2 + its transpose gives the third)."""
+    nb = d // 256
+    off, diag = nb * (nb - 1) // 2, nb
+    return 2.0 * 256 * 256 * (3 * off + GRAM_DIAGONAL_PRODUCTS * diag)
+
+
+GRAM_DIAGONAL_PRODUCTS = 3     # products issued on a diagonal block (kernels.h: kept in step with gram_sm100.cu)
+
+
+def gmm_issued_flops_per_row(d, k, upper_triangular=True):
+    """Tensor-core flops the two kernels of the cfg3 local step issue per data row: the whitened
+    projection (BF16x3; 10 of 16 K-steps when the factors are upper triangular at d = 64) and the
+    weighted statistics R^T (X (x) X) over 36 symmetric 8 x 8 pair blocks + 1 linear block of 64 columns."""
+    steps = d // 16
+    kept = (sum(1 for j in range(steps) for i in range(steps) if i >= j) / float(steps * steps)
+            if upper_triangular else 1.0)
+    nb = d // 8
+    blocks = nb * (nb + 1) // 2 + 1
+    return 3 * kept * 2.0 * k * d * d + 3 * 2.0 * k * 64 * blocks
 
 
 def gaussian_pass(X, e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet):
@@ -85,6 +110,16 @@ class GmmStep(object):
         t = torch.linalg.solve_triangular(U.transpose(1, 2), bk.double().unsqueeze(-1), upper=False).squeeze(-1)
         c = ck.double() + 0.5 * (t * t).sum(1)
         return U.float().contiguous(), t.float().contiguous(), c.float().contiguous()
+
+    @staticmethod
+    def local_step(X, U, t, c):
+        """The whole local step from WHITENED parameters (``whiten`` once per global update, or the
+        ``U, t, c`` that ``updates.gmm_global_update`` emits): two kernels, nothing else -- logits + row
+        log-sum-exp, then {N_k, sum r x, sum r x x^T} with r = exp(logit - lse) formed inside the
+        operand conversion (the responsibility matrix is never written)."""
+        logits, lse, sum_lse = stats.mixture_logits(X, U, t, c, upper_triangular=True)
+        nk, rx, rxx = stats.weighted_suffstats_from_logits(X, logits, lse)
+        return {'logits': logits, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
 
     def __call__(self, X, Ak, bk, ck, fused=True, want_log_resp=True):
         import torch

@@ -33,11 +33,17 @@ def _torch():
 
 
 def _workspace(nbytes, device):
+    """Grow-only kernel scratch, one per (device, CUDA stream, host thread): calls issued on two
+    streams or from two threads never share a buffer.  A buffer that is outgrown is handed back to
+    torch's stream-ordered caching allocator (allocated and used on the same stream, so its reuse is
+    ordered after the kernels that still read it)."""
+    import threading
     torch = _torch()
-    buf = _scratch.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+    buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-        _scratch[device] = buf
+        _scratch[key] = buf
     return buf
 
 

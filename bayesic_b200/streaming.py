@@ -54,6 +54,14 @@ def streamed_pass(pass_fn, arrays, chunk_rows, device=None):
                     for h in hosts] for _ in range(2)]
         on_dev = [[torch.empty((rows,) + tuple(h.shape[1:]), dtype=torch.float32, device=dev) for h in hosts]
                   for _ in range(2)]
+        # The device buffers come from the caching allocator on the compute stream: earlier work on that
+        # stream (e.g. the previous call's last kernels, whose buffers the allocator may hand back here)
+        # must be finished before the copy stream writes them, and the blocks must not be reused before
+        # the copy stream is done with them.
+        copy.wait_stream(compute)
+        for pair in on_dev:
+            for t in pair:
+                t.record_stream(copy)
         copied = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
         staged = [torch.cuda.Event() for _ in range(2)]

@@ -1,21 +1,23 @@
-#!/usr/bin/env python
 """Benchmark of the hot path on BASELINE.json's metric:
 
     data points / second per sufficient-statistic + ELBO pass
 
-Workload (N=1 and weak scaling): BASELINE config[1] -- multivariate Gaussian-Wishart
-mean-field pass, X[16 Mi, 64] float32 per GPU resident in HBM.  One step =
-  {Sigma x, Sigma x x^T} in one tcgen05 pass over X  (+ NCCL all-reduce of the packed
-  float64 statistics when N > 1)  + the expected log-likelihood (ELBO term) from them.
+Workload: BASELINE config[1] -- multivariate Gaussian-Wishart mean-field pass over X[16 Mi, 64] float32,
+"sharded over N at 1-8 B200": the 16 Mi rows are the WHOLE job, cut into contiguous shards with
+``parallel.shard_bounds`` (strong scaling; each rank's shard is resident in its HBM).  One step =
+ONE kernel launch per rank (``bb_gaussian_pass_run``): {count, sum x, sum x x^T} of the shard on tcgen05,
+the cross-CTA reduction, the exchange of the 33 KB of partial statistics over NVLink peer memory and the
+expected log-likelihood (ELBO term) of the reduced statistics.  Weak scaling (16 Mi rows PER GPU) is
+measured in the same run and reported under the extra key ``weak``.
 
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
-    python bench.py --impl reference ...                   # reference CPU path (numpy/BLAS port)
+    python bench.py --impl reference ...                   # the UNMODIFIED reference on the host cores
 
-Prints ONE JSON line on rank 0 (contract in the task statement): value / ms_per_step are
-device-timed (CUDA events, max over ranks, barrier + synchronize on both sides); `e2e` is the
-same metric through the host-buffer API (pinned numpy in, numpy out: H2D copy of every step's
-X inside the timed region); `roofline` is the dominant kernel against the measured HBM peak;
-`cpu_baseline` is the oracle's numpy port timed on this box's host cores.
+Prints ONE JSON line on rank 0 (contract in the task statement): value / ms_per_step are device-timed
+(CUDA events, max over ranks, barrier + synchronize on both sides); `e2e` is the same metric through the
+host-buffer API (pinned numpy in, numpy out: H2D copy of every step's X inside the timed region);
+`roofline` is the one kernel of the step against the measured HBM peak; `cpu_baseline` is the unmodified
+reference (``oracle/_ref`` through the numpy Theano shim) timed on this box's host cores.
 """
 import argparse
 import json
@@ -32,22 +34,34 @@ sys.path.insert(0, ROOT)
 METRIC = "data points/sec per suff-stat+ELBO pass"
 UNIT = "points/s"
 D = 64
-N_PER_GPU = 1 << 24            # BASELINE cfg2: N = 16 Mi rows, D = 64, float32
+N_TOTAL = 1 << 24              # BASELINE cfg2: N = 16 Mi rows, D = 64, float32
 ALGO_BYTES_PER_POINT = 4 * D   # X read once, outputs negligible
 FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-# dram__bytes_read.sum + dram__bytes_write.sum of suffstats_tc_kernel at this workload, from
-# profiles/r01_suffstats_ncu_full.txt (one `ncu --set full` capture)
-NCU_TRAFFIC_BYTES = 4295027000 + 4994816
+
+
+def workload_config(rows_total=N_TOTAL):
+    """The `config` object -- identical for this repo's arm and the reference arm."""
+    return {"workload": "cfg2 Gaussian-Wishart suff-stats + ELBO: X[%d, %d] f32 in total, sharded over N "
+                        "across the GPUs (strong scaling)" % (rows_total, D),
+            "rows_total": int(rows_total), "d": D,
+            "l2": "inputs (%.1f GiB in total) larger than the 126 MB L2" % (rows_total * D * 4 / 2 ** 30)}
 
 
 def gw_hyperparameters(d, seed=1234):
-    """Fixed Gaussian-Wishart variational parameters (m, beta, W, nu) -> expectations."""
-    from oracle.closed_forms import gaussian_wishart_expectations
+    """Fixed Gaussian-Wishart variational parameters (m, beta, W, nu) -> the expectations the pass needs:
+    E[Lambda] = nu W, E[Lambda mu] = nu W m, E[mu^T Lambda mu] = d / beta + nu m^T W m,
+    E[log|Lambda|] = sum_i digamma((nu + 1 - i) / 2) + d log 2 + log|W|   (Bishop 10.64-10.65)."""
+    from scipy.special import digamma
     rng = np.random.RandomState(seed)
     m = rng.randn(d) * 0.1
     a = rng.randn(d, d)
     W = np.linalg.inv(a @ a.T / d + np.eye(d)) / (d + 4.0)
-    return gaussian_wishart_expectations(m, 2.0, W, d + 4.0)
+    beta, nu = 2.0, d + 4.0
+    e_lambda = nu * W
+    e_lambda_mu = e_lambda @ m
+    e_mu_l_mu = d / beta + float(m @ e_lambda @ m)
+    e_logdet = float(digamma(0.5 * (nu - np.arange(d))).sum() + d * np.log(2.0) + np.linalg.slogdet(W)[1])
+    return e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet
 
 
 def hbm_peak():
@@ -57,6 +71,18 @@ def hbm_peak():
             return float(json.load(fh)['hbm_gbs']), 'measured'
     except Exception:
         return FALLBACK_HBM_GBS, 'fallback'
+
+
+def ncu_traffic(rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the step's kernel from the committed
+    `ncu --set full` capture (profiles/suffstats_traffic.json, written by profiles/summarize_ncu.py), if
+    that capture was taken at this row count; None otherwise."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'suffstats_traffic.json')) as fh:
+            rec = json.load(fh)
+        return int(rec['dram_bytes']) if int(rec['rows']) == int(rows) else None
+    except Exception:
+        return None
 
 
 class ClockSampler(object):
@@ -126,7 +152,9 @@ def time_other_configs(dev):
     """The remaining BASELINE configs (parity-test cases, not the bench line) timed once each at
     N = 1 so that the driver's own run records them: device-resident inputs, CUDA events, 3
     warm-ups + 10 passes.  Returned under the extra key ``other_configs``; never affects the
-    headline numbers (any failure is recorded as a string)."""
+    headline numbers (any failure is recorded as a string).  Tensor-bound configs report BOTH
+    ``frac_issued`` (MMA flops the kernel really issues: BF16x3 products, full blocks) and
+    ``frac_useful`` (SURVEY.md 8(d) minimal symmetric / triangular flop count) of the measured BF16 peak."""
     import torch
     import bayesic_b200.stats as S
     import bayesic_b200.passes as P
@@ -146,19 +174,25 @@ def time_other_configs(dev):
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / reps
 
+    def tensor_roofline(issued_per_pt, useful_per_pt, n, ms, counts):
+        issued = issued_per_pt * n / (ms * 1e-3) / 1e12
+        useful = useful_per_pt * n / (ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": useful, "peak": tc, "unit": "TFLOP/s", "frac": useful / tc,
+                "frac_useful": useful / tc, "frac_issued": issued / tc, "issued_tflops": issued,
+                "peak_source": tc_src, "counts": counts}
+
     gen = torch.Generator(device=dev).manual_seed(4321)
     try:      # cfg4: {X^T X, X^T y, y^T y}, minibatch 1 Mi, D = 1024
         n, d = 1 << 20, 1024
         X = torch.randn(n, d, device=dev, generator=gen)
         y = X @ (torch.randn(d, device=dev, generator=gen) / d ** 0.5) + 0.1 * torch.randn(n, device=dev, generator=gen)
         ms = timed(lambda: S.regression_suffstats(X, y))
-        issued = 3 * 2.0 * 256 * 256 * 10 * n / (ms * 1e-3) / 1e12
+        issued_per_pt = P.gram_issued_flops_per_row(d)
         out['cfg4'] = {"workload": "linear-regression SVI statistics {X^T X, X^T y, y^T y}: X[1 Mi, 1024] f32",
                        "ms_per_pass": ms, "points_per_s": n / (ms * 1e-3),
-                       "roofline": {"bound": "tensor", "achieved": issued, "peak": tc, "unit": "TFLOP/s",
-                                    "frac": issued / tc, "peak_source": tc_src,
-                                    "counts": "issued BF16x3 MMA flops (3 products x 10 upper-triangle 256x256 blocks)",
-                                    "useful_tflops_symmetric": d * (d + 1.0) * n / (ms * 1e-3) / 1e12}}
+                       "roofline": tensor_roofline(issued_per_pt, 1051648.0, n, ms,
+                                                   "useful = SURVEY 8(d) symmetric-half 1 051 648 flop/pt; issued = BF16x3 "
+                                                   "products over the upper-triangle 256x256 blocks (%d flop/pt)" % issued_per_pt)}
         del X, y
     except Exception as exc:
         out['cfg4'] = "failed: %s" % exc
@@ -183,42 +217,54 @@ def time_other_configs(dev):
         bk = torch.randn(k, d, device=dev, generator=gen)
         ck = torch.randn(k, device=dev, generator=gen)
         step = P.GmmStep()
-        ms = timed(lambda: step(X, Ak, bk, ck), reps=5)
-        issued = (3 * 2.0 * k * d * d + 3 * 2.0 * k * 64 * 37) * n / (ms * 1e-3) / 1e12
-        out['cfg3'] = {"workload": "GMM VMP local step (logits -> log-softmax -> weighted statistics): "
-                                   "X[2 Mi, 64] f32, K = 256",
+        U, t, c = step.whiten(Ak, bk, ck)                     # once per global update, not per minibatch
+        ms = timed(lambda: step.local_step(X, U, t, c), reps=5)
+        issued_per_pt = P.gmm_issued_flops_per_row(d, k, upper_triangular=True)
+        out['cfg3'] = {"workload": "GMM VMP local step, two kernels (logits + row log-sum-exp; weighted statistics "
+                                   "with r = exp(logit - lse) formed on the fly): X[2 Mi, 64] f32, K = 256",
                        "ms_per_pass": ms, "points_per_s": n / (ms * 1e-3),
-                       "roofline": {"bound": "tensor", "achieved": issued, "peak": tc, "unit": "TFLOP/s",
-                                    "frac": issued / tc, "peak_source": tc_src,
-                                    "counts": "issued BF16x3 MMA flops of the logits and statistics kernels over the whole step"}}
-        del X, Ak, bk, ck
+                       "roofline": tensor_roofline(issued_per_pt, 2195456.0, n, ms,
+                                                   "useful = SURVEY 8(d) minimal 2 195 456 flop/pt; issued = BF16x3 MMAs: "
+                                                   "logits 3 x 0.625 (triangular factors) x 2 K D^2 + statistics "
+                                                   "3 x 2 K x 64 x 37 blocks (%d flop/pt)" % issued_per_pt)}
+        del X, Ak, bk, ck, U, t, c
     except Exception as exc:
         out['cfg3'] = "failed: %s" % exc
     torch.cuda.empty_cache()
     return out
 
 
-def cpu_pass(X, expectations):
-    """The reference's CPU evaluation of the pass, as a numpy port (oracle): the plans
-    _tensordot(_dimshuffle(X,1,0), X, [1],[0]) and _sum(X, 0) (bayesic/algebra.py:527-551)
-    lowered to numpy/BLAS exactly as Theano's tensordot / sum would be
-    (algebra.py:1290-1291, 1347-1351), then the ELBO term from the statistics."""
-    from oracle.closed_forms import gaussian_expected_loglik
-    s2 = np.tensordot(X.T, X, ([1], [0]))
-    s1 = X.sum(axis=0)
-    e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet = expectations
-    return gaussian_expected_loglik(X.shape[0], s1.astype(np.float64), s2.astype(np.float64),
-                                    e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet)
+def blas_threads():
+    """Threads the BLAS behind numpy will really use (threadpoolctl), not os.cpu_count()."""
+    try:
+        from threadpoolctl import threadpool_info
+        counts = [int(lib['num_threads']) for lib in threadpool_info() if lib.get('user_api') == 'blas']
+        return max(counts) if counts else 1
+    except Exception:
+        return 1
+
+
+def reference_pass(expectations):
+    """The cfg2 pass through the UNMODIFIED reference: its own ``compile()`` -> ``f(**inputs)``
+    (bayesic/algebra.py:50-58) from ``oracle/_ref`` (or /root/reference), Theano replaced by the numpy shim."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count(), user_api='blas')     # torchrun exports OMP_NUM_THREADS=1
+    except Exception:
+        pass
+    from oracle.reference_pass import ReferenceGaussianPass
+    return ReferenceGaussianPass(*expectations)
 
 
 def time_cpu_baseline(sample_rows, reps, expectations):
     rng = np.random.default_rng(0)
     X = rng.standard_normal((sample_rows, D), dtype=np.float32)
-    cpu_pass(X[: 1 << 16], expectations)           # warm BLAS threads
+    ref = reference_pass(expectations)
+    ref(X[: 1 << 16])                              # warm BLAS threads
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_pass(X, expectations)
+        ref(X)
         times.append(time.perf_counter() - t0)
     best = min(times)
     return sample_rows / best, best, times
@@ -229,31 +275,35 @@ def run_reference(args):
     if rank != 0:
         return 0
     expectations = gw_hyperparameters(D)
-    sample_rows = 1 << 22          # 4 Mi rows (1 GiB) per step: bounded sample of the 16 Mi workload
-    cpu_pass(np.zeros((1 << 16, D), dtype=np.float32), expectations)
+    rows = args.rows_total
+    ref = reference_pass(expectations)
     rng = np.random.default_rng(0)
-    X = rng.standard_normal((sample_rows, D), dtype=np.float32)
-    for _ in range(max(args.warmup, 1)):
-        cpu_pass(X, expectations)
+    X = np.empty((rows, D), dtype=np.float32)
+    for lo in range(0, rows, 1 << 20):             # bounded temporaries while filling 4 GiB
+        X[lo:lo + (1 << 20)] = rng.standard_normal((min(1 << 20, rows - lo), D), dtype=np.float32)
+    X *= 1.3
+    X += 0.4
+    ref(X[: 1 << 16])
+    for _ in range(args.warmup):
+        ref(X)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_pass(X, expectations)
+        n, s1, s2, elbo = ref(X)
     elapsed = time.perf_counter() - t0
-    value = sample_rows * args.steps / elapsed
+    value = rows * args.steps / elapsed
+    threads = blas_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 Gaussian-Wishart suff-stats + ELBO, D=64; bounded sample of "
-                               "%d rows per step of the 16 Mi-row workload" % sample_rows,
-                   "d": D, "rows_per_step": sample_rows},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": "%d rows x %d steps, numpy/BLAS port of the reference plan "
-                                   "(reference is Python+Theano; Theano is not installable here)"
-                                   % (sample_rows, args.steps)},
+        "config": workload_config(rows),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": "the whole %d-row workload x %d steps through the UNMODIFIED reference "
+                                   "(oracle/_ref: bayesic.algebra compile() -> f(**inputs); Theano replaced by the numpy "
+                                   "shim, BLAS threads = %d of %d host cores)" % (rows, args.steps, threads, os.cpu_count())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "elbo": elbo,
     }
     print(json.dumps(line))
     return 0
@@ -263,6 +313,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import bayesic_b200.stats as S
+    from bayesic_b200.parallel import GaussianPass, shard_bounds
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -276,128 +327,133 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
 
-    n = args.rows
+    rows_total = args.rows_total
+    lo, hi = shard_bounds(rows_total, world, rank)
+    n_strong = hi - lo                                   # this rank's shard of the fixed 16 Mi-row job
+    n_weak = rows_total                                  # weak scaling: the whole size per GPU
+    n_alloc = n_weak if (distributed and not args.no_weak) else n_strong
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    X = torch.randn(n, D, device=dev, dtype=torch.float32, generator=gen)
+    X = torch.randn(n_alloc, D, device=dev, dtype=torch.float32, generator=gen)
     X.mul_(1.3).add_(0.4)
     e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet = gw_hyperparameters(D)
     e_lambda_d = torch.as_tensor(e_lambda, dtype=torch.float64, device=dev)
     e_lambda_mu_d = torch.as_tensor(e_lambda_mu, dtype=torch.float64, device=dev)
-    # packed per-GPU partial statistics: [S2 (d*d) | S1 (d) | count] float64 -> one all-reduce
+
+    # ONE launch per rank per step: statistics + reduction + NVLink exchange + ELBO term.  Construction is
+    # collective (symmetric-memory rendezvous); BB_P2P_ALLREDUCE=0 or a failed set-up falls back to
+    # "statistics kernel, NCCL all-reduce, ELBO kernel".
+    gpass, collective = None, "none (1 GPU)"
+    ok = 1.0
+    if os.environ.get('BB_P2P_ALLREDUCE', '1') != '0' or not distributed:
+        try:
+            gpass = GaussianPass(D, dev)
+        except Exception as exc:                       # noqa: BLE001 -- any setup problem means "use NCCL"
+            sys.stderr.write("bench: one-launch pass unavailable (%s); using NCCL\n" % exc)
+            ok = 0.0
+    else:
+        ok = 0.0
+    if distributed:
+        flag = torch.tensor([ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag) == 0.0:
+            gpass = None
     from bayesic_b200.parallel import PackedStats, allreduce_packed
     layout = PackedStats.gaussian(D)
     packed = layout.allocate(dev)
     views = layout.views(packed)
-    s2, s1, count = views['s2'], views['s1'], views['count']
-    elbo = torch.zeros(1, dtype=torch.float64, device=dev)
-    total_rows = float(n * world)
+    elbo_nccl = torch.zeros(1, dtype=torch.float64, device=dev)
 
-    def step_single(kernel_events=None):
-        # one GPU: statistics + ELBO through one entry point (the ELBO runs in the finalize kernel's
-        # last block: two launches per step)
-        if kernel_events is not None:
-            kernel_events[0].record()
-        S.gaussian_suffstats_loglik(X, e_lambda_d, e_lambda_mu_d, e_mu_l_mu, e_logdet, n_total=total_rows,
-                                    out=(s1, s2, elbo))
-        if kernel_events is not None:
-            kernel_events[1].record()
+    def step_nccl(Xs):
+        S.gaussian_suffstats(Xs, out=(views['s1'], views['s2']))
+        views['count'].fill_(float(Xs.shape[0]))
+        allreduce_packed(packed)
+        S.gaussian_expected_loglik(float(Xs.shape[0] * world), views['s1'], views['s2'], e_lambda_d, e_lambda_mu_d,
+                                   e_mu_l_mu, e_logdet, out=elbo_nccl)
+        return elbo_nccl
 
-    def step_nccl(kernel_events=None):
-        if kernel_events is not None:
-            kernel_events[0].record()
-        S.gaussian_suffstats(X, out=(s1, s2))
-        if kernel_events is not None:
-            kernel_events[1].record()
-        if distributed:
-            count.fill_(float(n))
-            allreduce_packed(packed)
-        S.gaussian_expected_loglik(total_rows, s1, s2, e_lambda_d, e_lambda_mu_d, e_mu_l_mu,
-                                   e_logdet, out=elbo)
+    def step_pass(Xs):
+        return gpass.run(Xs, e_lambda_d, e_lambda_mu_d, e_mu_l_mu, e_logdet)[3]
 
-    # N > 1: the exchange is 33 KB, i.e. pure latency -- one single-CTA kernel per rank sums the peers'
-    # partial statistics over NVLink peer memory and evaluates the ELBO (csrc/p2p_reduce.cu) instead of
-    # "NCCL all-reduce, then the ELBO kernel".  Checked against the NCCL path before it is used;
-    # BB_P2P_ALLREDUCE=0 (or any failure to set up peer memory) keeps NCCL.
-    peer = None
-    collective = "one NCCL all-reduce of %d float64 per step" % packed.numel() if distributed else "none (1 GPU)"
-    if distributed and os.environ.get('BB_P2P_ALLREDUCE', '1') != '0':
-        ok = 1.0
-        try:
-            from bayesic_b200.parallel import PeerReducer
-            peer = PeerReducer(layout, dev)
-        except Exception as exc:                       # noqa: BLE001 -- any setup problem means "use NCCL"
-            sys.stderr.write("bench: peer-memory all-reduce unavailable (%s); using NCCL\n" % exc)
-            ok = 0.0
-        flag = torch.tensor([ok], dtype=torch.float64, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if float(flag) == 0.0:
-            peer = None
-
-    def step_peer(kernel_events=None):
-        views_p = peer.slot()
-        if kernel_events is not None:
-            kernel_events[0].record()
-        S.gaussian_suffstats(X, out=(views_p['s1'], views_p['s2']))
-        if kernel_events is not None:
-            kernel_events[1].record()
-        peer.reduce_loglik(e_lambda_d, e_lambda_mu_d, e_mu_l_mu, e_logdet, D, elbo)
-
-    if peer is not None:
-        peer.set_constant('count', float(n))           # per-rank row count: the same every step
-        step_nccl()
-        want = float(elbo)
-        step_peer()
-        got = float(elbo)
-        agree = torch.tensor([1.0 if abs(got - want) <= 1e-9 * abs(want) and int(peer.status.item()) == 0 else 0.0],
-                             dtype=torch.float64, device=dev)
+    if gpass is not None and distributed:
+        # the one-launch pass must agree with the NCCL path before it is timed
+        Xs = X[:n_strong]
+        want = float(step_nccl(Xs))
+        got = float(step_pass(Xs))
+        gpass.check()
+        agree = torch.tensor([1.0 if abs(got - want) <= 1e-9 * abs(want) else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(agree, op=dist.ReduceOp.MIN)
         if float(agree) == 0.0:
-            sys.stderr.write("bench: peer-memory all-reduce disagreed with NCCL (%r vs %r); using NCCL\n" % (got, want))
-            peer = None
-        else:
-            collective = ("one-shot all-reduce of %d float64 over NVLink peer memory fused with the ELBO kernel "
-                          "(1 launch per rank; checked against the NCCL all-reduce at start-up)" % packed.numel())
-    step = step_peer if peer is not None else (step_nccl if distributed else step_single)
+            sys.stderr.write("bench: one-launch pass disagreed with NCCL (%r vs %r); using NCCL\n" % (got, want))
+            gpass = None
+    if distributed:
+        collective = ("fused into the statistics kernel: per-slice push of %d float64 into the peers' receive buffers "
+                      "over NVLink + flags (1 launch per rank per step; checked against the NCCL all-reduce at start-up)"
+                      % layout.numel) if gpass is not None else "one NCCL all-reduce of %d float64 per step" % layout.numel
+    step = step_pass if gpass is not None else step_nccl
+    launches_per_step = 1 if gpass is not None else (3 if distributed else 2)
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    def timed_run(Xs, use_graph):
+        """W warm-ups, then K steps between CUDA events (barrier + synchronize on both sides);
+        returns (ms per step, max over ranks; last ELBO; kernels launched)."""
+        warm = max(args.warmup, 3)
+        graph = None
+        if use_graph:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step(Xs)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                step(Xs)
+        run = graph.replay if graph is not None else (lambda: step(Xs))
+        for _ in range(warm):
+            run()
+        barrier()
+        before = S.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            run()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launched = (S.launch_count() - before) if graph is None else launches_per_step * args.steps
+        if distributed:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        out = gpass.loglik if gpass is not None else elbo_nccl
+        return ms / args.steps, float(out), int(launched)
+
+    use_graph = bool(args.graph) and gpass is not None
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    launches_before = S.launch_count()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        step(kev[i])
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = S.launch_count() - launches_before
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    ms_per_step, elbo_value, launches = timed_run(X[:n_strong], use_graph)
     clocks = sampler.stop() if rank == 0 else None
-    if distributed:
-        t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, kernel_ms = float(t[0]), float(t[1])
-    ms_per_step = elapsed_ms / args.steps
-    value = total_rows / (ms_per_step * 1e-3)
-    elbo_value = float(elbo)
+    value = rows_total / (ms_per_step * 1e-3)
+    if gpass is not None:
+        gpass.check()
+    weak = None
+    if distributed and not args.no_weak:
+        w_ms, w_elbo, _ = timed_run(X, use_graph)
+        weak = {"value": n_weak * world / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms, "rows_per_gpu": n_weak,
+                "scaling": "weak", "elbo": w_elbo}
 
     # ---- end to end: host buffers through the public API, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
-        host.copy_(X)
+        host = torch.empty((n_strong, D), dtype=torch.float32, pin_memory=True)
+        host.copy_(X[:n_strong])
         e_steps = max(1, min(args.steps, args.e2e_steps))
 
         def e2e_step():
@@ -423,8 +479,8 @@ def run_ours(args):
             t = torch.tensor([e_elapsed], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_elapsed = float(t[0])
-        e2e = {"value": total_rows * e_steps / e_elapsed, "unit": UNIT,
-               "h2d_bytes_per_step": int(n * D * 4),
+        e2e = {"value": rows_total * e_steps / e_elapsed, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_strong * D * 4),
                "d2h_bytes_per_step": int((D * D + D) * 8 + 8), "steps": e_steps,
                "ms_per_step": 1e3 * e_elapsed / e_steps,
                "elbo_matches_device_path": bool(abs(e2e_value - elbo_value) <= 1e-6 * abs(elbo_value))}
@@ -437,34 +493,40 @@ def run_ours(args):
         other = time_other_configs(dev)
     if rank == 0:
         peak, peak_kind = hbm_peak()
-        achieved = ALGO_BYTES_PER_POINT * n / (kernel_ms * 1e-3) / 1e9
+        achieved = ALGO_BYTES_PER_POINT * n_strong / (ms_per_step * 1e-3) / 1e9
         cpu = None
-        if not args.no_cpu_baseline:
-            cpu_value, cpu_best, cpu_times = time_cpu_baseline(1 << 22, 5, (e_lambda, e_lambda_mu,
-                                                                             e_mu_l_mu, e_logdet))
-            cpu = {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                   "sample": "4 Mi rows x 5 reps (best), numpy/BLAS port of the reference plan "
-                             "_tensordot(X^T, X) + _sum(X, 0) + ELBO from statistics"}
+        if not args.no_cpu_baseline and world == 1:
+            cpu_value, cpu_best, cpu_times = time_cpu_baseline(1 << 22, 5, (e_lambda, e_lambda_mu, e_mu_l_mu, e_logdet))
+            threads = blas_threads()
+            cpu = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": "4 Mi rows x 5 reps (best): the UNMODIFIED reference (oracle/_ref, bayesic.algebra "
+                             "compile() -> f(**inputs), numpy Theano shim): dot(X.T, X), sum(X, 0), ELBO from the "
+                             "statistics; BLAS threads = %d of %d host cores" % (threads, os.cpu_count())}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2 Gaussian-Wishart suff-stats + ELBO: X[%d, %d] f32 per GPU, "
-                                   "sharded over N" % (n, D),
-                       "rows_per_gpu": n, "d": D, "arithmetic": "error-compensated TF32 (hi/lo split) on "
-                       "tcgen05, fp32 TMEM accumulate drained to f64",
-                       "l2": "inputs (%.1f GiB per GPU) larger than the 126 MB L2" % (n * D * 4 / 2 ** 30),
-                       "collective": collective},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(rows_total),
+            "impl_notes": {"rows_per_gpu": n_strong,
+                           "arithmetic": "error-compensated TF32 (hi/lo split, one MMA) on tcgen05; fp32 TMEM "
+                                         "accumulate drained to f64 every 512 rows",
+                           "collective": collective, "cuda_graph": use_graph,
+                           "launches_per_step": launches_per_step},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if n == N_PER_GPU else None,
+                         "frac": achieved / peak, "traffic": ncu_traffic(n_strong),
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured'
                          else "fallback (B200_PROFILING.md)",
-                         "kernel": "suffstats_tc_kernel + finalize" + ("" if distributed else " (ELBO in its last block)"),
-                         "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
+                         "kernel": "suffstats_tc_kernel (the step's only launch: statistics + cross-CTA reduction"
+                                   + (" + NVLink exchange" if distributed else "") + " + ELBO term)",
+                         "kernel_ms": ms_per_step,
+                         "timing": "the step is exactly one launch of this kernel, so its average duration is taken "
+                                   "as ms_per_step (CUDA events around the K timed launches; launch gaps included)",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n_strong},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "elbo": elbo_value,
         }
+        if weak is not None:
+            line["weak"] = weak
         if other is not None:
             line["other_configs"] = other
         print(json.dumps(line))
@@ -479,14 +541,19 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--rows', type=int, default=N_PER_GPU, help='rows per GPU (default: cfg2, 16 Mi)')
+    ap.add_argument('--rows-total', type=int, default=N_TOTAL, help='rows of the whole job (default: cfg2, 16 Mi)')
     ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--graph', type=int, default=int(os.environ.get('BB_BENCH_GRAPH', '0')),
+                    help='1: capture the step in a CUDA graph and replay it')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-weak', action='store_true', help='N > 1: skip the weak-scaling measurement')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-other-configs', action='store_true',
                     help='skip the one-off timings of cfg3/4/5 recorded under "other_configs" (N = 1 only)')
     args = ap.parse_args()
     if args.impl == 'reference':
+        if args.steps == 100:
+            args.steps = 5              # default run: a few minutes of CPU at most
         return run_reference(args)
     return run_ours(args)
 

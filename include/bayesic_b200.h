@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2
 #define BB_MAX_DIMS 8
 #define BB_MAX_PARENTS 8
 #define BB_MAX_IPARAMS 40
@@ -185,8 +185,9 @@ BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xx
                                 double* out, void* stream);
 
 /* bb_suffstats_gaussian followed by bb_gaussian_expected_loglik in one call (the cfg2 step on one
- * GPU; statistics of bayesic/distribution/base.py:328-332, log-likelihood of base.py:25-100): on the tcgen05 path the log-likelihood is evaluated by the last block of the statistics'
- * finalize kernel, so the step is two launches instead of three.  sum_x is required; n_total is the
+ * GPU; statistics of bayesic/distribution/base.py:328-332, log-likelihood of base.py:25-100): on the
+ * tcgen05 path statistics, cross-CTA reduction and log-likelihood are ONE launch (the last CTA to
+ * finish evaluates the log-likelihood; see bb_gaussian_pass for N GPUs).  sum_x is required; n_total is the
  * row count the log-likelihood refers to (= n on one GPU). */
 BB_API int bb_suffstats_gaussian_loglik(const float* X, int64_t n, int32_t d, double* sum_x,
                                  double* sum_xxT, double n_total, const double* E_Lambda,
@@ -298,26 +299,65 @@ BB_API int bb_gmm_global_update(const double* Nk, const double* sum_rx, const do
                          double* alpha, double* beta, double* nu, double* m, double* W_inv,
                          float* U, float* t, float* c, double* kl, int32_t* status, void* stream);
 
-/* Multi-GPU combine of the per-rank partial statistics (distribution/base.py:328-332 sums over the
- * iid axis) as ONE kernel per rank over NVLink peer memory, fused with the consumer:
- * publish "epoch e complete" into every peer's flag array (system-scope release), wait for all
- * peers, sum the world's partial buffers by direct peer loads in rank order (bit-identical on all
- * ranks) into out[count], and -- when elbo != NULL -- evaluate bb_gaussian_expected_loglik from the
- * reduced packed layout [S2 (d*d) | S1 (d) | row count] in the same kernel.
- *   peer_buffers  device array of `world` pointers to float64 buffers of 2 * slot_stride elements
- *                 (slot = epoch & 1), each rank's own buffer and its peers' mapped into this process;
- *                 this rank's partial statistics for the epoch must already be in its slot
- *                 (stream order);
- *   peer_flags    device array of `world` pointers to uint32[>= world] flag arrays, zeroed before
- *                 the first call; epoch must advance by 1 per call on every rank, starting at 1;
- *   spin_limit_ms a lost peer sets *status (device int32) to 1 + its rank instead of hanging.
- * Meant for the small payloads of this path (cfg2 33 KB, cfg5 260 KB); NCCL serves the MB-sized
- * ones. */
-BB_API int bb_allreduce_sum_p2p(const void* peer_buffers, const void* peer_flags, int32_t rank,
-                         int32_t world, int64_t count, int64_t slot_stride, uint32_t epoch,
-                         double spin_limit_ms, double* out, int32_t* status,
-                         const double* e_lambda, const double* e_lambda_mu, double e_mu_l_mu,
-                         double e_logdet, int32_t d, double* elbo, void* stream);
+/* ---- multi-GPU combine over NVLink peer memory ---------------------------------------------
+ * What it replaces: nothing the reference has -- ExpFamIndependentObservations.sufficient_statistics
+ * (bayesic/distribution/base.py:328-332) sums the per-point statistics over the iid axis; with the
+ * data axis sharded over one process per GPU that sum needs one combine of the per-rank partial
+ * statistics per minibatch.  The library does not bootstrap inter-process memory:
+ * the host binding allocates the buffers below on every rank, maps its peers' buffers into its own
+ * address space (CUDA IPC / cuMem fabric handles; bayesic_b200/parallel.py uses torch's symmetric
+ * memory for exactly that) and passes HOST arrays of `world` DEVICE pointers, index = rank.
+ *
+ * bb_comm: a two-shot all-reduce(sum) of float64[count] as ONE kernel per rank: counterpart CTAs
+ * handshake through epoch flags (no grid barrier), each rank pulls and reduces its 1/world chunk from
+ * all ranks' input buffers in rank order (bit-identical everywhere) and pushes the sums into all
+ * ranks' output buffers (csrc/p2p_reduce.cu).
+ *   peer_in / peer_out   float64[capacity] per rank, 16-byte aligned; this rank writes its partial
+ *                        statistics into its own input buffer (stream order) before the call and finds
+ *                        the reduced payload in its own output buffer after it;
+ *   peer_flags           bb_comm_flag_bytes(world) bytes per rank, ZEROED on every rank (and a
+ *                        host-side barrier passed) before the first call;
+ *   every rank must call bb_comm_allreduce_sum the same number of times with the same count;
+ *   consumers of the output must be ordered on `stream` before the next call;
+ *   a peer that does not answer within spin_limit_ms (<= 0: 2000) sets the status word to 1 + its
+ *   rank and the output is filled with NaN -- never a partial sum; bb_comm_status reads the word
+ *   (synchronises `stream`). */
+typedef struct bb_comm bb_comm;
+BB_API int64_t bb_comm_flag_bytes(int32_t world);
+BB_API int bb_comm_create(int32_t rank, int32_t world, const void* const* peer_in,
+                   const void* const* peer_out, const void* const* peer_flags, int64_t capacity,
+                   double spin_limit_ms, bb_comm** comm);
+BB_API int bb_comm_allreduce_sum(bb_comm* comm, int64_t count, void* stream);
+BB_API int bb_comm_status(bb_comm* comm, int32_t* status, void* stream);
+BB_API int bb_comm_destroy(bb_comm* comm);
+
+/* bb_gaussian_pass: the whole cfg2 step -- statistics of base.py:328-332 for core.py:41-44, their
+ * combine over the ranks, and the expected log-likelihood of base.py:25-100 -- as ONE kernel launch
+ * per step on any number of GPUs (csrc/suffstats_sm100.cu: tcgen05 pass, grid barrier, per-slice
+ * reduction, per-slice push into the peers' receive buffers + flags, ELBO term by the last CTA).
+ * The handle owns its workspace (the only device allocation; one handle = one stream at a time).
+ *   d                    4 <= d <= 64, d % 4 == 0;
+ *   attach_peers         optional (world > 1): peer_recv = bb_gaussian_pass_peer_bytes' recv_bytes per
+ *                        rank, peer_flags = flag_bytes per rank, zeroed + barrier before the first run;
+ *   run                  X device float32 [n, d] (this rank's rows; n may be 0 on a rank).  Outputs
+ *                        (device float64): sum_x[d] (may be NULL), sum_xxT[d, d], count_out (may be
+ *                        NULL), loglik (may be NULL; needs E_Lambda[d, d], E_Lambda_mu[d]) -- all
+ *                        REDUCED over the ranks when peers are attached, bit-identical on every rank.
+ *                        n_total is the row count the log-likelihood refers to on one GPU; with
+ *                        peers the reduced count is used;
+ *   status               1 + rank of a peer that did not answer (outputs are NaN then). */
+typedef struct bb_gaussian_pass bb_gaussian_pass;
+BB_API int bb_gaussian_pass_create(int32_t d, bb_gaussian_pass** pass);
+BB_API int bb_gaussian_pass_peer_bytes(int32_t d, int32_t world, int64_t* recv_bytes, int64_t* flag_bytes);
+BB_API int bb_gaussian_pass_attach_peers(bb_gaussian_pass* pass, int32_t rank, int32_t world,
+                                  const void* const* peer_recv, const void* const* peer_flags,
+                                  double spin_limit_ms);
+BB_API int bb_gaussian_pass_run(bb_gaussian_pass* pass, const float* X, int64_t n,
+                         const double* E_Lambda, const double* E_Lambda_mu, double E_mu_L_mu,
+                         double E_logdet, double n_total, double* sum_x, double* sum_xxT,
+                         double* count_out, double* loglik, void* stream);
+BB_API int bb_gaussian_pass_status(bb_gaussian_pass* pass, int32_t* status, void* stream);
+BB_API int bb_gaussian_pass_destroy(bb_gaussian_pass* pass);
 
 /* Minibatch selection on the device (README.md:71-73 "subsample the data"): out[j, :] = X[index[j], :]
  * for j < m.  Indices outside [0, n) are counted in *n_out_of_range (device int32) and their rows

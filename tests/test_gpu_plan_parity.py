@@ -189,3 +189,20 @@ def test_compiled_matrix_vector_contractions_over_the_data_axis(n, d):
     _scale_close(g(X=Xh, w=wh).reshape(n, 1), want_rows.reshape(n, 1), row_norms, wnorm)
     assert g.plan.last_launches == 1
     _scale_close(A.dot(w, X.T).compile()(X=Xh, w=wh).reshape(n, 1), want_rows.reshape(n, 1), row_norms, wnorm)
+
+
+def test_repeated_factors_and_terms_are_evaluated_not_merged():
+    """Round-1 advisor finding: sharing sub-trees by the expressions' frozenset-based ``==``
+    computed 2*X*X*Y for X*X*Y + X*Y.  Sharing is by identity / strict value numbering now."""
+    rng = np.random.RandomState(31)
+    Xh, Yh = rng.randn(37, 11).astype(np.float32), rng.randn(37, 11).astype(np.float32)
+    X, Y = A.var('X', 2), A.var('Y', 2)
+    X64, Y64 = Xh.astype(np.float64), Yh.astype(np.float64)
+    got = (X * X * Y + X * Y).compile()(X=Xh, Y=Yh)
+    np.testing.assert_allclose(got, X64 * X64 * Y64 + X64 * Y64, rtol=RTOL, atol=ATOL)
+    a, b = compile_many([X + X + Y, X + Y])(X=Xh, Y=Yh)
+    np.testing.assert_allclose(a, 2 * X64 + Y64, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(b, X64 + Y64, rtol=RTOL, atol=ATOL)
+    got = (X ** 3 + X ** 2 + X * X * X).compile()(X=np.abs(Xh) + 0.5)
+    x = np.abs(X64) + 0.5
+    np.testing.assert_allclose(got, 2 * x ** 3 + x ** 2, rtol=RTOL, atol=ATOL)

@@ -78,61 +78,3 @@ def test_gather_rows_is_exact_and_flags_bad_indices(d):
     assert int(count.item()) == 2 and bool(torch.isnan(rows[3]).all()) and torch.equal(rows[4], X[idx[4]])
     with pytest.raises(TypeError):
         streaming.gather_rows(X, idx.int())
-
-
-def test_p2p_allreduce_protocol_two_ranks_on_one_gpu():
-    """bb_allreduce_sum_p2p with both "ranks" on one device (two buffers, two flag arrays, two
-    streams): the flag protocol, the double-buffered slots across several epochs, the rank-ordered
-    sum and the fused expected log-likelihood.  Real NVLink peers are exercised by bench.py --gpus N."""
-    import ctypes
-    import torch
-    from bayesic_b200.backend import library as L
-    from bayesic_b200.parallel import PackedStats
-    lib = L.load()
-    d, world = 16, 2
-    layout = PackedStats.gaussian(d)
-    count, stride = layout.numel, (layout.numel + 31) // 32 * 32
-    dev = torch.device('cuda')
-    bufs = [torch.zeros(2 * stride, dtype=torch.float64, device=dev) for _ in range(world)]
-    flags = [torch.zeros(64, dtype=torch.int32, device=dev) for _ in range(world)]
-    buf_ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
-    flag_ptrs = torch.tensor([f.data_ptr() for f in flags], dtype=torch.int64, device=dev)
-    outs = [torch.zeros(count, dtype=torch.float64, device=dev) for _ in range(world)]
-    status = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
-    elbo = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
-    streams = [torch.cuda.Stream() for _ in range(world)]
-    rng = np.random.RandomState(0)
-    e_lambda = torch.from_numpy(np.eye(d) + 0.1 * rng.randn(d, d)).to(dev)
-    e_lambda_mu = torch.from_numpy(rng.randn(d)).to(dev)
-    torch.cuda.synchronize()
-    for epoch in range(1, 6):
-        parts = [rng.randn(count) for _ in range(world)]
-        for r in range(world):
-            parts[r][-1] = 1000.0 + r                  # row counts
-            lo = (epoch & 1) * stride
-            bufs[r][lo:lo + count].copy_(torch.from_numpy(parts[r]))
-        torch.cuda.synchronize()
-        for r in range(world):
-            with torch.cuda.stream(streams[r]):
-                L.check(lib.bb_allreduce_sum_p2p(buf_ptrs.data_ptr(), flag_ptrs.data_ptr(), r, world, count, stride,
-                                                 epoch, 2000.0, outs[r].data_ptr(), status[r].data_ptr(),
-                                                 e_lambda.data_ptr(), e_lambda_mu.data_ptr(), 0.7, -1.3, d,
-                                                 elbo[r].data_ptr(), ctypes.c_void_p(streams[r].cuda_stream)))
-        torch.cuda.synchronize()
-        want = parts[0] + parts[1]
-        s2, s1, n = want[:d * d].reshape(d, d), want[d * d:d * d + d], want[-1]
-        want_elbo = O.gaussian_expected_loglik(n, s1, s2, e_lambda.cpu().numpy(), e_lambda_mu.cpu().numpy(), 0.7, -1.3)
-        for r in range(world):
-            assert int(status[r].item()) == 0
-            np.testing.assert_array_equal(outs[r].cpu().numpy(), want)          # rank-ordered: bit-identical
-            np.testing.assert_allclose(float(elbo[r].item()), want_elbo, rtol=1e-12)
-    # a peer that never arrives is reported, not waited for forever
-    with torch.cuda.stream(streams[0]):
-        L.check(lib.bb_allreduce_sum_p2p(buf_ptrs.data_ptr(), flag_ptrs.data_ptr(), 0, world, count, stride, 6, 5.0,
-                                         outs[0].data_ptr(), status[0].data_ptr(), None, None, 0.0, 0.0, 0, None,
-                                         ctypes.c_void_p(streams[0].cuda_stream)))
-    torch.cuda.synchronize()
-    assert int(status[0].item()) == 2                                           # 1 + rank of the missing peer
-    with pytest.raises(ValueError):
-        L.check(lib.bb_allreduce_sum_p2p(buf_ptrs.data_ptr(), flag_ptrs.data_ptr(), 3, world, count, stride, 7, 5.0,
-                                         outs[0].data_ptr(), status[0].data_ptr(), None, None, 0.0, 0.0, 0, None, None))

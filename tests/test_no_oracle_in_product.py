@@ -60,6 +60,6 @@ def test_library_exports_every_declared_symbol():
     assert declared, 'no BB_API declarations found'
     assert declared == set(library.SIGNATURES)
     lib = library.load()                        # raises if any symbol is missing
-    assert lib.bb_abi_version() == 1
+    assert lib.bb_abi_version() == 2
     for name in declared:
         assert hasattr(lib, name)
