@@ -6,7 +6,7 @@
 """
 from collections import Counter, defaultdict  # noqa: F401  (reference re-exports these via *)
 
-from .expr import (Expression, var, constant, shape, elemwise, add, eye,  # noqa: F401
+from .expr import (Expression, var, constant, shape, elemwise, add, eye, logdet,  # noqa: F401
                    wrap_if_literal, with_wrapped_literals, autobroadcast_or_match)
 from .einsum import einsum, Einsum  # noqa: F401
 from .plan_ir import _sum, _mul, _dimshuffle, _tensordot, _diagonal  # noqa: F401
@@ -23,6 +23,6 @@ __all__ = [
     'find_duplicate', 'equivalence_classes', 'submultisets_of_size',
     'find_injection', 'find_injections', 'find_bijection', 'find_bijections',
     'dot', 'tensordot', 'mul', 'outer', 'sum', 'trace', 'diagonal', 'transpose', 'dimshuffle',
-    'div', 'neg', 'sub', 'log', 'exp', 'pow', 'abs_', 'lgamma',
+    'div', 'neg', 'sub', 'log', 'exp', 'pow', 'abs_', 'lgamma', 'logdet',
     'Counter', 'defaultdict',
 ]

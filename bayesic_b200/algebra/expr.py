@@ -18,7 +18,7 @@ Differences from the reference, all deliberate:
 import numpy as np
 
 __all__ = [
-    'Expression', 'var', 'constant', 'shape', 'elemwise', 'add', 'eye',
+    'Expression', 'var', 'constant', 'shape', 'elemwise', 'add', 'eye', 'logdet',
     'wrap_if_literal', 'with_wrapped_literals', 'autobroadcast_or_match',
 ]
 
@@ -269,3 +269,19 @@ class eye(Expression):
 
     def __hash__(self):
         return hash(self.__class__)
+
+
+class logdet(Expression):
+    """``log|X|`` over the last two axes of a stack of symmetric positive-definite matrices:
+    ``X[..., d, d] -> [...]``.  Not in the reference's executable vocabulary: its
+    ``MultivariateNormal.log_normalizer`` calls a ``T.logdet`` that Theano never had
+    (``bayesic/distribution/core.py:49-52``).  Needed by every log-normaliser with a precision or scale
+    matrix in it (MVN, Wishart, Gaussian-Wishart); evaluated on the device by a float64 Cholesky
+    (``BB_NODE_LOGDET``).  Not multilinear, so it stays an opaque node, like ``log``."""
+
+    def __init__(self, X):
+        X = wrap_if_literal(X)
+        if X.ndim < 2:
+            raise ValueError("logdet needs at least two axes, got %d" % X.ndim)
+        self.ndim = X.ndim - 2
+        Expression.__init__(self, (X,))

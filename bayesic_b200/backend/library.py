@@ -16,7 +16,7 @@ MAX_IPARAMS = 40
 # bb_node_kind
 NODE_INPUT, NODE_SCALAR, NODE_SHAPE, NODE_EYE, NODE_SUM, NODE_MUL = 0, 1, 2, 3, 4, 5
 NODE_DIMSHUFFLE, NODE_TENSORDOT, NODE_DIAGONAL, NODE_ELEMWISE = 6, 7, 8, 9
-NODE_LOGSOFTMAX, NODE_SYRK, NODE_WEIGHTED_SCATTER = 20, 21, 22
+NODE_LOGSOFTMAX, NODE_SYRK, NODE_WEIGHTED_SCATTER, NODE_LOGDET = 20, 21, 22, 23
 # bb_elemwise_op
 OP_CODES = {'add': 0, 'mul': 1, 'log': 2, 'exp': 3, 'pow': 4, 'abs_': 5, 'lgamma': 6}
 
@@ -43,6 +43,8 @@ class ResultInfo(ctypes.Structure):
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                         'lib', 'libbayesic_b200.so')
+if os.environ.get('BB_LIB_PATH'):          # developer knob: an experimental build variant of the same library
+    LIB_PATH = os.environ['BB_LIB_PATH']
 
 # every symbol include/bayesic_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double

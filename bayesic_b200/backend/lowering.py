@@ -21,7 +21,7 @@ be switched off (``fuse=False``) and the parity tests run both ways.
 """
 import numpy as np
 
-from ..algebra.expr import var, constant, shape, elemwise, add, eye
+from ..algebra.expr import var, constant, shape, elemwise, add, eye, logdet
 from ..algebra.plan_ir import _sum, _mul, _dimshuffle, _tensordot, _diagonal
 from . import library as L
 
@@ -215,6 +215,8 @@ def lower_plans(plan_trees, input_types, fuse=True):
             return add_node(L.NODE_SHAPE, [visit(node.parents[0])], [node.axis])
         if isinstance(node, eye):
             return add_node(L.NODE_EYE, [visit(node.parents[0])])
+        if isinstance(node, logdet):
+            return add_node(L.NODE_LOGDET, [visit(node.parents[0])])
         if isinstance(node, _sum):
             return add_node(L.NODE_SUM, [visit(node.parents[0])], sorted(node.axes))
         if isinstance(node, _mul):

@@ -34,7 +34,7 @@ namespace bb {
 namespace {
 
 constexpr int kStageRows = 16;                 // one K = 16 step per stage
-constexpr int kFlushIters = 128;               // 2048 rows per TMEM accumulation chain
+constexpr int kFlushIters = 128 / BB_CHAIN_DIV;               // 2048 rows per TMEM accumulation chain
 constexpr int kConvWarps = 16;
 constexpr int kConvGroups = 2;
 constexpr int kEpiWarps = 4;

@@ -10,6 +10,13 @@
 
 #include "../../include/bayesic_b200.h"
 
+// Length of the fp32 TMEM accumulation chains of the BF16x3 kernels, as a divisor of the default
+// 2048 rows (the tensor core truncates its fp32 accumulate, so chain length trades accuracy against
+// drain traffic; profiles/r02_parity_report.txt has the measured trade).  Build-time knob.
+#ifndef BB_CHAIN_DIV
+#define BB_CHAIN_DIV 1
+#endif
+
 namespace bb {
 
 void set_error(const char* fmt, ...);

@@ -567,6 +567,30 @@ int run_node(Exec& ex, int idx) {
       }
       break;
     }
+    case BB_NODE_LOGDET: {
+      View X = ex.vals[nd.parents[0]];
+      if (X.ndim < 2 || X.is_host) { set_error("node %d: logdet needs a device tensor of rank >= 2", idx); return BB_ERR_UNSUPPORTED; }
+      const int64_t d = X.shape[X.ndim - 1];
+      if (d != X.shape[X.ndim - 2]) {
+        set_error("node %d: logdet of non-square matrices (%lld x %lld)", idx,
+                  static_cast<long long>(X.shape[X.ndim - 2]), static_cast<long long>(d));
+        return BB_ERR_SHAPE;
+      }
+      if (d > 4096) { set_error("node %d: logdet supports d <= 4096 (got %lld)", idx, static_cast<long long>(d)); return BB_ERR_UNSUPPORTED; }
+      out.ndim = X.ndim - 2;
+      for (int a = 0; a < out.ndim; ++a) out.shape[a] = X.shape[a];
+      out.set_contiguous_strides();
+      if (ex.needed[idx]) {
+        const int64_t batch = out.numel();
+        BB_TRY(ex.materialize(X, &X));
+        BB_TRY(ex.alloc_floats(idx, batch, &out.ptr));
+        void* scratch = nullptr;
+        const int64_t bytes = logdet_scratch_bytes(batch, d);
+        if (bytes > 0) BB_TRY(ex.alloc_scratch(bytes, &scratch));
+        if (!ex.dry()) BB_TRY(launch_logdet_spd(X.ptr, batch, static_cast<int>(d), out.ptr, scratch, ex.stream));
+      }
+      break;
+    }
     default:
       set_error("node %d: unknown kind %d", idx, nd.kind);
       return BB_ERR_INVALID;
@@ -677,7 +701,7 @@ int plan_validate(const bb_node_desc* nodes, int32_t n_nodes, const int32_t* out
         if (nd.n_iparams != 1) { set_error("node %d: shape needs one axis", i); return BB_ERR_INVALID; }
         break;
       case BB_NODE_EYE: case BB_NODE_SUM: case BB_NODE_DIMSHUFFLE: case BB_NODE_LOGSOFTMAX:
-      case BB_NODE_SYRK:
+      case BB_NODE_SYRK: case BB_NODE_LOGDET:
         want_parents = 1; break;
       case BB_NODE_DIAGONAL:
         want_parents = 1;

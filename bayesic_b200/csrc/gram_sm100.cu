@@ -55,7 +55,7 @@ constexpr int kStageRows = 32;            // data rows per pipeline stage (2 MMA
 constexpr int kStages = 6;
 constexpr int kTileBytes = kHalf * kStageRows * 2;      // one bf16 operand tile: 8 KB
 constexpr int kStageBytes = 4 * kTileBytes;             // A.b1, A.b2, B.b1, B.b2: 32 KB
-constexpr int kFlushIters = 64;           // TMEM accumulators drained every 64 stages = 2048 rows
+constexpr int kFlushIters = 64 / BB_CHAIN_DIV;           // TMEM accumulators drained every 64 stages = 2048 rows
 constexpr int kConvWarps = 16;
 constexpr int kConvGroups = 2;           // warp groups taking alternate stages
 constexpr int kRowsPerWarp = kStageRows / (kConvWarps / kConvGroups);   // 4

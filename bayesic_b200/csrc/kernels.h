@@ -42,8 +42,9 @@ struct SuffstatsTail {
   const double* e_lambda_mu;
   double e_mu_l_mu, e_logdet, n_total;   // n_total is used when world == 1; the reduced count otherwise
   double* loglik;
-  double* scratch;             // [BB_GAUSSIAN_PASS_SLICES + 1]
-  unsigned int* ticket;
+  double* scratch;             // [BB_GAUSSIAN_PASS_SLICES + 2]
+  unsigned int* bar_arrive;    // monotonic arrival counter of the grid barrier + completion ticket (never reset)
+  unsigned int* bar_base;      // its value at the start of this launch (stored by the previous launch's last CTA)
   double local_count;          // this rank's row count (payload element d*d + d)
   int rank, world;
   double* const* peer_recv;    // device array [world]: receive buffers, [2][world][stride] float64 each
@@ -151,6 +152,10 @@ int comm_grid_for(int64_t count, int world);
 int launch_p2p_allreduce(const double* const* in, double* const* out, uint32_t* const* flags, int rank, int world,
                          int64_t count, uint32_t* epoch_dev, unsigned int* ticket, double spin_limit_ms, int* status,
                          cudaStream_t stream);
+
+// linalg_kernels.cu: batched log|X| of SPD float32 matrices via float64 Cholesky
+int64_t logdet_scratch_bytes(int64_t batch, int64_t d);
+int launch_logdet_spd(const float* x, int64_t batch, int d, float* out, void* scratch, cudaStream_t stream);
 
 // stats_kernels.cu
 int launch_f32_to_f64(const float* in, double* out, int64_t n, cudaStream_t stream);

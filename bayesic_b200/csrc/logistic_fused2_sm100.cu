@@ -56,7 +56,7 @@ constexpr int kChunkBytes = 8192;               // 64 rows x 64 features, one bf
 constexpr int kWChunkBytes = 16384;             // [W1; W2]: 128 rows x 64 features bf16
 constexpr int kWStages = 4;
 constexpr int kResidPart = 8192;                // 64 draws x 64 rows bf16
-constexpr int kChainTiles = 32;                 // G accumulators drained every 32 tiles = 2048 rows
+constexpr int kChainTiles = 32 / BB_CHAIN_DIV;                 // G accumulators drained every 32 tiles = 2048 rows
 constexpr int kWorkerWarps = 16;                // converter + epilogue
 constexpr int kMmaWarp = kWorkerWarps;
 constexpr int kTmaWarp = kMmaWarp + 1;

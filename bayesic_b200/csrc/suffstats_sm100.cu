@@ -47,6 +47,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -99,6 +100,7 @@ struct __align__(1024) SmemLayout {
   uint64_t a_free[2];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  double s1_part[2][kFeat];      // Sigma x of the two row halves (split warps)
   uint32_t tmem_base;
 };
 
@@ -115,8 +117,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 // store 8 data rows at a time as 8 TMEM columns.
 template <bool kIsLo>
 __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, int q, int khalf,
-                                                int lane, int my_tiles,
-                                                double* __restrict__ partial_s1) {
+                                                int lane, int my_tiles) {
   const int half = q & 1;             // which 32-feature column block
   // byte offset of (row j of an 8-row group, feature = lane) inside a stage: rows are 128 B,
   // 32-byte chunks XOR-swizzled with (row & 3)  (TMA SWIZZLE_128B_ATOM_32B)
@@ -164,16 +165,41 @@ __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, i
     if (lane == 0) ptx::mbar_arrive(&sm.a_ready[b]);
     if (!kIsLo) s1 += static_cast<double>(s1_tile);
   }
-  if (!kIsLo)
-    partial_s1[(static_cast<int64_t>(blockIdx.x) * 2 + khalf) * kFeat + half * 32 + lane] = s1;
+  if (!kIsLo) sm.s1_part[khalf][half * 32 + lane] = s1;
 }
 
+// Developer timeline (variant build -DBB_SUFFSTATS_TIMELINE): CTA 0 / thread 0 stamps %globaltimer at the
+// phase boundaries and prints the deltas (ns) at the end of every launch.
+#ifdef BB_SUFFSTATS_TIMELINE
+__device__ unsigned long long g_tl[16];
+__device__ unsigned long long g_cta[2][256];      // per-CTA time of kernel entry / end of the main loop
+__device__ __forceinline__ void tl_stamp(int i) {
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || i == 0 || i == 2)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (blockIdx.x == 0) g_tl[i] = t;
+    if (i == 0) g_cta[0][blockIdx.x] = t;
+    if (i == 2) g_cta[1][blockIdx.x] = t;
+  }
+}
+#define BB_TL(i) tl_stamp(i)
+#else
+#define BB_TL(i)
+#endif
+
 // ---- fused tail: cross-CTA reduction, cross-GPU exchange, expected log-likelihood ----------------
+constexpr int kPartialDoubles = kFeat * kFeat + kFeat;      // one CTA's partial: [S2 (64 x 64) | S1 (64)] float64
+constexpr long long kGridBarrierSpinLimit = 4000000000LL;  // ~2 s of clock64 ticks
 constexpr int kSlices = BB_GAUSSIAN_PASS_SLICES;   // output slices (and per-peer flags); grid-size independent so
                                                    // that ranks whose grids differ agree on the slicing
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
@@ -183,9 +209,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
 
 // Runs in every CTA after its partials are written and the grid barrier has passed.
 // `red` is kThreads doubles of shared memory (the drained pipeline stages are reused).
-__device__ __forceinline__ void fused_tail(const SuffstatsTail& tp, const double* __restrict__ partial_s2,
-                                           const double* __restrict__ partial_s1, double* red,
-                                           volatile int* sflag) {
+__device__ __forceinline__ void fused_tail(const SuffstatsTail& tp, const double* __restrict__ partial,
+                                           unsigned int bar_base, double* red, volatile int* sflag) {
   const int t = threadIdx.x;
   const int d = tp.d;
   const int elements = d * d + d + 1;                     // [S2 | S1 | row count]
@@ -202,17 +227,22 @@ __device__ __forceinline__ void fused_tail(const SuffstatsTail& tp, const double
     const int idx = slice * per + e;
     double acc = 0.0;
     if (g < groups && idx < elements) {
-      if (idx < d * d) {
-        const int r = idx / d, c = idx % d;
-        for (int p = g; p < grid; p += groups) {
-          const double* P = partial_s2 + static_cast<int64_t>(p) * 128 * kFeat;
-          acc += __ldcg(P + r * kFeat + c) + __ldcg(P + (kFeat + r) * kFeat + c) + __ldcg(P + (kFeat + c) * kFeat + r);
+      if (idx < d * d + d) {
+        // element of the packed output -> element of a CTA's [64 x 64 | 64] partial
+        const int pidx = idx < d * d ? (idx / d) * kFeat + idx % d : kFeat * kFeat + (idx - d * d);
+        const double* src = partial + pidx;
+        // fixed assignment of partials to groups and a fixed combination order: deterministic; four
+        // independent accumulators keep the L2 loads in flight together
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int p = g;
+        for (; p + 3 * groups < grid; p += 4 * groups) {
+          a0 += __ldcg(src + static_cast<int64_t>(p) * kPartialDoubles);
+          a1 += __ldcg(src + static_cast<int64_t>(p + groups) * kPartialDoubles);
+          a2 += __ldcg(src + static_cast<int64_t>(p + 2 * groups) * kPartialDoubles);
+          a3 += __ldcg(src + static_cast<int64_t>(p + 3 * groups) * kPartialDoubles);
         }
-      } else if (idx < d * d + d) {
-        const int f = idx - d * d;
-        for (int p = g; p < grid; p += groups)
-          acc += __ldcg(partial_s1 + static_cast<int64_t>(2 * p) * kFeat + f) +
-                 __ldcg(partial_s1 + static_cast<int64_t>(2 * p + 1) * kFeat + f);
+        for (; p < grid; p += groups) a0 += __ldcg(src + static_cast<int64_t>(p) * kPartialDoubles);
+        acc = (a0 + a1) + (a2 + a3);
       } else if (g == 0) {
         acc = tp.local_count;
       }
@@ -285,14 +315,16 @@ __device__ __forceinline__ void fused_tail(const SuffstatsTail& tp, const double
       __syncthreads();
     }
   }
-  if (!want_ll && tp.world == 1) return;
+  BB_TL(4);
+  // completion ticket = second round of arrivals on the barrier counter
   __threadfence();
   __syncthreads();
-  if (t == 0) *sflag = atomicAdd(tp.ticket, 1u) == static_cast<unsigned int>(grid) - 1u;
+  if (t == 0) *sflag = atomicAdd(tp.bar_arrive, 1u) == bar_base + 2u * static_cast<unsigned int>(grid) - 1u;
   __syncthreads();
   if (!*sflag || t != 0) return;
-  // last CTA of the grid: every CTA has read the stored epoch (before the grid barrier) and finished
+  // last CTA of the grid: every CTA has read the stored base / epoch and finished
   __threadfence();
+  *tp.bar_base = bar_base + 2u * static_cast<unsigned int>(grid);
   if (tp.world > 1) *tp.epoch_dev = epoch;
   if (!want_ll) return;
   double total = 0.0;
@@ -305,11 +337,10 @@ __device__ __forceinline__ void fused_tail(const SuffstatsTail& tp, const double
 
 __global__ void __launch_bounds__(kThreads, 1)
 suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
-                    double* __restrict__ partial_s2,   // [grid][128][64]
-                    double* __restrict__ partial_s1,   // [grid][2][64]
+                    double* __restrict__ partial,      // [grid][kPartialDoubles]
                     const SuffstatsTail tail) {
   extern __shared__ uint8_t smem_raw[];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *tail.ticket = 0u;     // ordered before its use by the grid barrier
+  BB_TL(0);
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
@@ -342,6 +373,7 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  BB_TL(1);
 
   if (warp == kTmaWarp) {
     // ---------------- TMA producer ----------------
@@ -393,8 +425,8 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
     // Warp w owns TMEM lanes [32 (w&3), +32): quadrants 0,1 hold hi of features 0-31 / 32-63,
     // quadrants 2,3 hold lo.  The two warps sharing a quadrant take rows 0-63 / 64-127 of a tile.
     const int q = warp & 3;
-    if (q < 2) split_warp_loop<false>(sm, tmem, q, warp >> 2, lane, my_tiles, partial_s1);
-    else split_warp_loop<true>(sm, tmem, q, warp >> 2, lane, my_tiles, partial_s1);
+    if (q < 2) split_warp_loop<false>(sm, tmem, q, warp >> 2, lane, my_tiles);
+    else split_warp_loop<true>(sm, tmem, q, warp >> 2, lane, my_tiles);
   } else {
     // ---------------- epilogue warps: TMEM fp32 chunks -> float64 registers ----------------
     const int q = warp & 3;
@@ -423,21 +455,85 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
         acc[16 + j] += static_cast<double>(__uint_as_float(v1[j]));
       }
     }
-    double* out = partial_s2 + (static_cast<int64_t>(blockIdx.x) * 128 + q * 32 + lane) * kFeat +
-                  chalf * kCols;
+    // every MMA of this CTA has completed (last acc_full), so every pipeline stage has been consumed: the
+    // first two stages become the CTA's [128][64] float64 scratch (hi^T hi on rows 0-63, lo^T hi on 64-127)
+    double* out = reinterpret_cast<double*>(sm.stage[0]) + (q * 32 + lane) * kFeat + chalf * kCols;
 #pragma unroll
     for (int c = 0; c < kCols; ++c) out[c] = acc[c];
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  BB_TL(2);
   if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
+  // this CTA's partial statistics in the packed output layout [S2 (64 x 64) | S1 (64)]:
+  // S2[r][c] = hi^T hi [r][c] + lo^T hi [r][c] + lo^T hi [c][r]
+  {
+    const double* P = reinterpret_cast<const double*>(sm.stage[0]);
+    double* mine = partial + static_cast<int64_t>(blockIdx.x) * kPartialDoubles;
+    for (int e = threadIdx.x; e < kPartialDoubles; e += kThreads) {
+      double v;
+      if (e < kFeat * kFeat) {
+        const int r = e >> 6, c = e & 63;
+        v = P[r * kFeat + c] + P[(kFeat + r) * kFeat + c] + P[(kFeat + c) * kFeat + r];
+      } else {
+        v = sm.s1_part[0][e - kFeat * kFeat] + sm.s1_part[1][e - kFeat * kFeat];
+      }
+      mine[e] = v;
+    }
+  }
   // every CTA's partials are complete and visible before any CTA reads them
   __threadfence();
+  __syncthreads();
+#ifdef BB_SUFFSTATS_COOP
   cg::this_grid().sync();
-  // the pipeline is drained (every TMA load was consumed): its first stage is scratch now
-  fused_tail(tail, partial_s2, partial_s1, reinterpret_cast<double*>(sm.stage[0]),
+  const unsigned int bar_base = __ldcg(tail.bar_base);
+#else
+  // Grid barrier on the monotonic arrival counter (all CTAs are resident: grid <= SM count, one CTA per
+  // SM).  The counter is never reset: this launch's arrivals run from bar_base (stored by the previous
+  // launch's last CTA) to bar_base + 2 grid -- first the barrier, then the completion ticket.
+  __shared__ unsigned int bar_base_s;
+  __shared__ int bar_lost_s;
+  if (threadIdx.x == 0) {
+    const unsigned int base = __ldcg(tail.bar_base);
+    bar_base_s = base;
+    bar_lost_s = 0;
+    atomicAdd(tail.bar_arrive, 1u);
+    const unsigned int target = base + gridDim.x;
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_gpu_u32(tail.bar_arrive) - target) < 0) {
+      if (clock64() - t0 > kGridBarrierSpinLimit) {         // a CTA of this grid is not resident: never hang
+        if (tail.status != nullptr) atomicMax(tail.status, 0x40000000);
+        bar_lost_s = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned int bar_base = bar_base_s;
+  if (bar_lost_s) return;
+#endif
+  BB_TL(3);
+  // the pipeline is drained (every TMA load was consumed): its third stage is scratch now
+  fused_tail(tail, partial, bar_base, reinterpret_cast<double*>(sm.stage[2]),
              reinterpret_cast<volatile int*>(&sm.tmem_base));
+#ifdef BB_SUFFSTATS_TIMELINE
+  BB_TL(5);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    printf("timeline ns: init %llu  main+partials %llu  gridsync %llu  slice-reduce %llu  rest-of-tail(cta0) %llu  | since previous launch's end %lld\n",
+           g_tl[1] - g_tl[0], g_tl[2] - g_tl[1], g_tl[3] - g_tl[2], g_tl[4] - g_tl[3], g_tl[5] - g_tl[4],
+           static_cast<long long>(g_tl[0] - g_tl[6]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long s0 = ~0ull, s1 = 0, m0 = ~0ull, m1 = 0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) {
+      s0 = min(s0, g_cta[0][b]); s1 = max(s1, g_cta[0][b]);
+      m0 = min(m0, g_cta[1][b]); m1 = max(m1, g_cta[1][b]);
+    }
+    printf("   CTA entry skew %llu ns, main-loop-end skew %llu ns (CTA 0 entry at +%llu, main end at +%llu of the earliest)\n",
+           s1 - s0, m1 - m0, g_tl[0] - s0, g_tl[2] - m0);
+    g_tl[6] = g_tl[5];
+  }
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -475,9 +571,10 @@ int grid_for(int64_t n) {
 }
 }  // namespace
 
-// partials + [kSlices + 1] float64 tail scratch + ticket
+// partials + [kSlices + 2] float64 tail scratch (the last one holds the two barrier words of the
+// caller-workspace entry points)
 int64_t suffstats_tc_workspace(int64_t n) {
-  return grid_for(n) * (128 * kFeat + 2 * kFeat) * static_cast<int64_t>(sizeof(double)) +
+  return grid_for(n) * kPartialDoubles * static_cast<int64_t>(sizeof(double)) +
          (kSlices + 2) * static_cast<int64_t>(sizeof(double)) + 512;
 }
 
@@ -528,21 +625,33 @@ int launch_suffstats_tc_fused(const float* x, int64_t n, int d, void* workspace,
   }
   int64_t tiles = (n + kTileRows - 1) / kTileRows;
   const int grid = grid_for(n);
-  double* partial_s2 = reinterpret_cast<double*>(
+  double* partial = reinterpret_cast<double*>(
       (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
-  double* partial_s1 = partial_s2 + static_cast<int64_t>(grid) * 128 * kFeat;
-  tail.scratch = partial_s1 + static_cast<int64_t>(grid) * 2 * kFeat;
-  tail.ticket = reinterpret_cast<unsigned int*>(tail.scratch + kSlices + 1);
+  tail.scratch = partial + static_cast<int64_t>(grid) * kPartialDoubles;
+  if (tail.bar_arrive == nullptr) {
+    // caller-provided (uninitialised) workspace: the barrier words live behind the scratch and are zeroed
+    // per launch; a bb_gaussian_pass handle owns persistent ones instead (no memset in its step)
+    tail.bar_arrive = reinterpret_cast<unsigned int*>(tail.scratch + kSlices + 1);
+    tail.bar_base = tail.bar_arrive + 1;
+    BB_CUDA_OK(cudaMemsetAsync(tail.bar_arrive, 0, 2 * sizeof(unsigned int), stream));
+  }
   tail.d = d;
   if (tail.world < 1) tail.world = 1;
 
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout)) + 1024;
   static SmemOptIn smem_opt_in_0;
   BB_CUDA_OK(smem_opt_in_0.ensure(suffstats_tc_kernel, smem_bytes));
-  void* args[] = {&map, &tiles, &partial_s2, &partial_s1, &tail};
-  // cooperative: the grid barrier needs every CTA resident (grid <= SM count, one CTA per SM)
+#ifdef BB_SUFFSTATS_COOP
+  void* args[] = {&map, &tiles, &partial, &tail};
   BB_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(suffstats_tc_kernel), dim3(grid), dim3(kThreads),
                                          args, smem_bytes, stream));
+#else
+  // a plain launch: the grid barrier inside needs every CTA resident, which grid <= SM count with one CTA
+  // per SM gives as long as no other kernel occupies SMs indefinitely (one pass at a time per device; a CTA
+  // that cannot become resident turns into a status flag after ~2 s, not a hang).  A cooperative launch
+  // would guarantee residency but was measured to add ~10 us of launch latency per step.
+  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial, tail);
+#endif
   BB_CHECK_LAUNCH("suffstats_tc_kernel");
   return BB_OK;
 }

@@ -47,7 +47,7 @@ constexpr int kTileCols = 256;                   // pair-feature columns per CTA
 constexpr int kRPart = kStageRows * kMaxK * 2;   // 8 KB: R tile, one bf16 part
 constexpr int kPPart = kStageRows * kTileCols * 2;   // 8 KB: Phi tile, one bf16 part
 constexpr int kStageBytes = 2 * kRPart + 2 * kPPart; // 32 KB
-constexpr int kFlushIters = 128;                 // 2048 rows per TMEM accumulation chain
+constexpr int kFlushIters = 128 / BB_CHAIN_DIV;                 // 2048 rows per TMEM accumulation chain
 constexpr int kConvWarps = 16;
 constexpr int kConvGroups = 2;
 constexpr int kEpiWarps = 4;

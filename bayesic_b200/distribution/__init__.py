@@ -6,8 +6,9 @@ MultivariateNormal); ``conjugate.py`` adds the families the BASELINE configurati
 from .base import (ConditionalDistribution, IndependentObservations, ExponentialFamily,  # noqa: F401
                    ExpFamIndependentObservations)
 from .core import Normal, MultivariateNormal  # noqa: F401
-from .conjugate import BernoulliLogit, Exponential, Gamma, Categorical, Dirichlet  # noqa: F401
+from .conjugate import (BernoulliLogit, Exponential, Gamma, Categorical, Dirichlet,  # noqa: F401
+                        Wishart, GaussianWishart)
 
 __all__ = ['ConditionalDistribution', 'IndependentObservations', 'ExponentialFamily',
            'ExpFamIndependentObservations', 'Normal', 'MultivariateNormal',
-           'BernoulliLogit', 'Exponential', 'Gamma', 'Categorical', 'Dirichlet']
+           'BernoulliLogit', 'Exponential', 'Gamma', 'Categorical', 'Dirichlet', 'Wishart', 'GaussianWishart']

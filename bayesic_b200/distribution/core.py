@@ -10,9 +10,10 @@ Log-normalisers are the mathematically correct ones (the reference's ``Normal.lo
 core.py:22-25, has the wrong sign on the 2 pi term and squares ``mean/variance``):
   Normal:  1/2 log 2pi + 1/2 log var + 1/2 mu^2 / var
   MVN:     1/2 D log 2pi - 1/2 log|Lambda| + 1/2 mu^T Lambda mu      (core.py:49-52 intent)
-``log|Lambda|`` is not expressible in the algebra's vocabulary (the reference calls a
-``T.logdet`` that Theano never had), so it is an explicit scalar parameter
-``log_det_precision`` -- in VMP it is E[log|Lambda|] anyway.
+``log|Lambda|``: the reference calls a ``T.logdet`` that Theano never had (core.py:51); here it is the
+``logdet`` node of the algebra (``BB_NODE_LOGDET``, float64 Cholesky on the device), so the normaliser
+is an expression of (mean, precision) as core.py:49-52 intends.  ``log_det_precision`` may still be
+passed explicitly -- in VMP it is E[log|Lambda|], which is not the log-determinant of E[Lambda].
 """
 import numpy as np
 
@@ -80,8 +81,10 @@ class MultivariateNormal(ExponentialFamily):
                          (mean, batch + [('sum', 0)])], lead + 1)
         return eta1, -0.5 * precision
 
-    def log_normalizer(self, mean, precision, log_det_precision, data_shape=None):
+    def log_normalizer(self, mean, precision, log_det_precision=None, data_shape=None):
         mean, precision = A.wrap_if_literal(mean), A.wrap_if_literal(precision)
+        if log_det_precision is None:
+            log_det_precision = A.logdet(precision)
         lead = mean.ndim - 1
         batch = [('out', i) for i in range(lead)]
         quad = A.einsum([(mean, batch + [('sum', 0)]),

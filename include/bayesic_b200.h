@@ -89,8 +89,14 @@ typedef enum {
   BB_NODE_LOGSOFTMAX = 20,/* x - log(sum(exp(x), axis=-1)) over the last axis, max-subtracted;
                              the pattern add(Lg, einsum(-1 * log(einsum(sum exp(Lg)))))          */
   BB_NODE_SYRK = 21,      /* _tensordot(_dimshuffle(X,1,0), X, [1],[0]): X^T X over the data axis */
-  BB_NODE_WEIGHTED_SCATTER = 22 /* sum_n R[n,k] X[n,d] X[n,e] -> [k,d,e] without materialising
+  BB_NODE_WEIGHTED_SCATTER = 22,/* sum_n R[n,k] X[n,d] X[n,e] -> [k,d,e] without materialising
                              the K x D x N intermediate of algebra.py's plan; parents: [R, X]    */
+  /* extension of the vocabulary (like BB_OP_LGAMMA) */
+  BB_NODE_LOGDET = 23     /* log|X| over the last two axes of a stack of symmetric positive-definite
+                             matrices X[..., d, d] -> [...]: the `T.logdet(precision)` that the
+                             reference's MultivariateNormal log-normaliser calls
+                             (distribution/core.py:49-52) and Theano never had; float64 Cholesky;
+                             NaN for a matrix that is not positive definite.  parents: [x]        */
 } bb_node_kind;
 
 typedef enum {

@@ -10,11 +10,11 @@ The fused nodes are defined by the sub-trees they replace (``backend/lowering.py
 import numpy as np
 from scipy.special import log_softmax
 
-from .semantics import tensordot_declared
+from .semantics import logdet_spd, tensordot_declared
 
 KIND = {0: 'input', 1: 'scalar', 2: 'shape', 3: 'eye', 4: 'sum', 5: 'mul', 6: 'dimshuffle',
         7: 'tensordot', 8: 'diagonal', 9: 'elemwise', 20: 'logsoftmax', 21: 'syrk',
-        22: 'weighted_scatter'}
+        22: 'weighted_scatter', 23: 'logdet'}
 OPS = {0: 'add', 1: 'mul', 2: 'log', 3: 'exp', 4: 'pow', 5: 'abs', 6: 'lgamma'}
 
 
@@ -79,6 +79,8 @@ def evaluate_descriptor(nodes, outputs, input_arrays, dtype=np.float64):
             value = par[0].T @ par[0]
         elif kind == 'weighted_scatter':
             value = np.einsum('nk,nd,ne->kde', par[0], par[1], par[1])
+        elif kind == 'logdet':
+            value = logdet_spd(par[0])
         else:
             raise ValueError(kind)
         vals.append(np.asarray(value))

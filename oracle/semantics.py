@@ -88,6 +88,8 @@ def evaluate(expr, inputs, dtype=np.float64):
         if kind in ('elemwise', 'add'):
             name = 'add' if kind == 'add' else node.name
             return _POINTWISE[name](*[ev(p) for p in node.parents])
+        if kind == 'logdet':
+            return logdet_spd(ev(node.parents[0])).astype(dtype)
         if kind == '_sum':
             return ev(node.parents[0]).sum(axis=tuple(node.axes))
         if kind == '_mul':
@@ -105,6 +107,17 @@ def evaluate(expr, inputs, dtype=np.float64):
         raise TypeError("oracle: unknown node type %s" % kind)
 
     return ev(expr)
+
+
+def logdet_spd(X):
+    """log|X| over the last two axes for symmetric positive-definite matrices; NaN for a matrix that is
+    not positive definite (the log-determinant is defined through the Cholesky factor)."""
+    X = np.asarray(X, dtype=np.float64)
+    _, value = np.linalg.slogdet(X)
+    if X.shape[-1] == 0:
+        return value
+    definite = np.linalg.eigvalsh(0.5 * (X + np.swapaxes(X, -1, -2))).min(axis=-1) > 0
+    return np.where(definite, value, np.nan)
 
 
 def tensordot_declared(X, Y, x_dot, y_dot, x_batch=(), y_batch=()):
