@@ -117,6 +117,10 @@ class CompiledPlan(object):
             raise TypeError("input %s: expected ndim %d, got %d" % (name, ndim, arr.ndim))
         if ndim == 0:
             return None, (), float(arr)
+        if arr.dtype.kind in 'iu' and arr.size and int(np.abs(arr).max()) > (1 << 24):
+            # the device path computes in float32: integers beyond 2^24 would be rounded silently, where
+            # Theano (the reference's evaluator, algebra.py:34-40) keeps the integer dtype
+            raise ValueError("input %s: integer values beyond 2**24 are not exact in the float32 device path" % name)
         t = torch.from_numpy(np.ascontiguousarray(arr, dtype=_FLOAT32)).to(device)
         keep.append(t)
         return t.data_ptr(), tuple(t.shape), None

@@ -566,7 +566,7 @@ struct bb_gaussian_pass {
   int d = 0, device = 0;
   void* ws = nullptr;
   int64_t ws_bytes = 0;
-  int* status = nullptr;           // device: [0] status word, [1] epochs completed, [2] barrier arrivals, [3] barrier base
+  int* status = nullptr;           // device: [0] status word, [1] epochs completed, [2] completion ticket
   int rank = 0, world = 1;
   double** peer_recv = nullptr;
   uint32_t** peer_flags = nullptr;
@@ -593,8 +593,9 @@ BB_API int bb_gaussian_pass_create(int32_t d, bb_gaussian_pass** pass) {
   bb_gaussian_pass* p = new (std::nothrow) bb_gaussian_pass();
   if (p == nullptr) { set_error("out of host memory"); return BB_ERR_INVALID; }
   p->d = d;
-  p->ws_bytes = suffstats_tc_workspace(int64_t(1) << 30) + 256;      // full grid
+  p->ws_bytes = suffstats_tc_workspace(int64_t(1) << 30) + 256;
   if (cudaGetDevice(&p->device) != cudaSuccess || cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess ||
+      cudaMemset(p->ws, 0, p->ws_bytes) != cudaSuccess ||
       cudaMalloc(&p->status, 4 * sizeof(int)) != cudaSuccess || cudaMemset(p->status, 0, 4 * sizeof(int)) != cudaSuccess) {
     set_error("gaussian_pass_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     bb_gaussian_pass_destroy(p);
@@ -638,8 +639,8 @@ BB_API int bb_gaussian_pass_run(bb_gaussian_pass* p, const float* X, int64_t n, 
   t.local_count = static_cast<double>(n);
   t.rank = p->rank; t.world = p->world;
   t.status = p->status;
-  t.bar_arrive = reinterpret_cast<unsigned int*>(p->status + 2);
-  t.bar_base = reinterpret_cast<unsigned int*>(p->status + 3);
+  t.accum = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p->ws) + 255) & ~static_cast<uintptr_t>(255));
+  t.ticket = reinterpret_cast<unsigned int*>(p->status + 2);
   if (p->world > 1) {
     t.peer_recv = p->peer_recv; t.peer_flags = p->peer_flags; t.stride = p->stride;
     t.epoch_dev = reinterpret_cast<uint32_t*>(p->status + 1);

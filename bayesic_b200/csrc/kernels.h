@@ -42,13 +42,13 @@ struct SuffstatsTail {
   const double* e_lambda_mu;
   double e_mu_l_mu, e_logdet, n_total;   // n_total is used when world == 1; the reduced count otherwise
   double* loglik;
-  double* scratch;             // [BB_GAUSSIAN_PASS_SLICES + 2]
-  unsigned int* bar_arrive;    // monotonic arrival counter of the grid barrier + completion ticket (never reset)
-  unsigned int* bar_base;      // its value at the start of this launch (stored by the previous launch's last CTA)
+  double* accum;               // [64 * 64 + 64] float64 accumulator block, zero between launches (null: carved from
+                               // the workspace and zeroed per launch)
+  unsigned int* ticket;        // completion ticket, zero between launches
   double local_count;          // this rank's row count (payload element d*d + d)
   int rank, world;
   double* const* peer_recv;    // device array [world]: receive buffers, [2][world][stride] float64 each
-  uint32_t* const* peer_flags; // device array [world]: flag arrays, [world][BB_GAUSSIAN_PASS_SLICES] uint32 each
+  uint32_t* const* peer_flags; // device array [world]: flag arrays, [world][BB_GAUSSIAN_PASS_SLICES] uint32 each (word 0 of a row is used)
   int64_t stride;
   uint32_t* epoch_dev;         // device word: epochs completed so far (this launch is stored + 1)
   long long spin_limit;        // clock64 ticks

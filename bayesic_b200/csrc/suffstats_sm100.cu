@@ -27,23 +27,20 @@
 //   * FP32 accumulation in TMEM is drained every 512 rows into float64 registers by eight
 //     epilogue warps (double-buffered accumulators, so the MMA never waits);
 //   * Sigma x rides along for free in the split warps (they already touch every element);
-//   * per-CTA float64 partials go to a workspace (L2-resident, 148 x 65.5 KB) and the SAME launch
-//     finishes the job (round 2; round 1 needed a finalize launch + an all-reduce launch):
-//     one grid-wide barrier (cooperative launch), then the d*d + d + 1 outputs are cut into 128
-//     slices and CTA j adds up slice j over all partials in a fixed order (deterministic), applying
-//     the symmetrisation above;
-//   * multi-GPU (world > 1): CTA j then PUSHES its slice into every peer's receive buffer over
-//     NVLink (plain stores into peer memory), publishes a per-slice flag (st.release.sys), waits for
-//     the peers' flags of the same slice only (so the exchange pipelines slice by slice, no second
-//     grid barrier), and sums the world's contributions from LOCAL memory in rank order -- the result
-//     is bit-identical on every rank.  Receive buffers are double-buffered by epoch parity;
-//   * the expected log-likelihood (ELBO term) of the reduced statistics is a per-slice dot product
-//     with E[Lambda], E[Lambda mu]; the last CTA to finish (atomic ticket) adds the 128 slice terms
-//     in order.  One launch per step on any number of GPUs.
+//   * the SAME launch finishes the job (round 1 needed a finalize launch + an all-reduce launch): every CTA
+//     adds its float64 partial statistics (upper triangle of S2, S1: 2144 values) into one 33 KB accumulator
+//     block with L2 reductions (red.global.add.f64) and takes a ticket; the LAST CTA to finish reads the
+//     block, re-zeroes it for the next launch and does the rest alone -- no grid barrier, no partial
+//     workspace.  (The sum over CTAs is in arrival order: float64, so run-to-run differences are ~1e-16
+//     relative; everything after it is in a fixed order.)
+//   * multi-GPU (world > 1): the last CTA PUSHES the rank's 33 KB payload into every peer's receive buffer
+//     over NVLink (plain stores into peer memory), publishes one flag per peer (st.release.sys), waits for the
+//     peers' flags, and sums the world's contributions from LOCAL memory in rank order -- the result is
+//     bit-identical on every rank.  Receive buffers are double-buffered by epoch parity;
+//   * the expected log-likelihood (ELBO term) of the reduced statistics is a dot product with E[Lambda],
+//     E[Lambda mu] in the same CTA (fixed reduction tree).  One launch per step on any number of GPUs.
 //
-// Algorithmic traffic: 4*d bytes per row, read once.  Nothing else touches HBM except
-// 148 x 65.5 KB of partials.
-#include <cooperative_groups.h>
+// Algorithmic traffic: 4*d bytes per row, read once.  Nothing else touches HBM.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -53,8 +50,6 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace bb {
 
@@ -168,16 +163,16 @@ __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, i
   if (!kIsLo) sm.s1_part[khalf][half * 32 + lane] = s1;
 }
 
-// Developer timeline (variant build -DBB_SUFFSTATS_TIMELINE): CTA 0 / thread 0 stamps %globaltimer at the
-// phase boundaries and prints the deltas (ns) at the end of every launch.
+// Developer timeline (variant build -DBB_SUFFSTATS_TIMELINE): thread 0 of CTA 0 (stamps 0-3) and of the last
+// CTA to finish (stamps 4-7) record %globaltimer at the phase boundaries; the last CTA prints the deltas (ns).
 #ifdef BB_SUFFSTATS_TIMELINE
 __device__ unsigned long long g_tl[16];
 __device__ unsigned long long g_cta[2][256];      // per-CTA time of kernel entry / end of the main loop
 __device__ __forceinline__ void tl_stamp(int i) {
-  if (threadIdx.x == 0 && (blockIdx.x == 0 || i == 0 || i == 2)) {
+  if (threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (blockIdx.x == 0) g_tl[i] = t;
+    if (blockIdx.x == 0 || i >= 3) g_tl[i] = t;
     if (i == 0) g_cta[0][blockIdx.x] = t;
     if (i == 2) g_cta[1][blockIdx.x] = t;
   }
@@ -188,18 +183,18 @@ __device__ __forceinline__ void tl_stamp(int i) {
 #endif
 
 // ---- fused tail: cross-CTA reduction, cross-GPU exchange, expected log-likelihood ----------------
-constexpr int kPartialDoubles = kFeat * kFeat + kFeat;      // one CTA's partial: [S2 (64 x 64) | S1 (64)] float64
-constexpr long long kGridBarrierSpinLimit = 4000000000LL;  // ~2 s of clock64 ticks
-constexpr int kSlices = BB_GAUSSIAN_PASS_SLICES;   // output slices (and per-peer flags); grid-size independent so
-                                                   // that ranks whose grids differ agree on the slicing
+// Round 2, second design.  The first one-launch version wrote per-CTA partials, crossed a grid barrier and cut
+// the outputs into slices summed by all CTAs: 16 us of tail on one GPU (timeline build) and ~60 us more with
+// peers (128 CTAs x system-scope fences).  Now every CTA adds its partial statistics into ONE float64
+// accumulator block with L2 reductions (red.global.add.f64; upper triangle only: 2144 per CTA), takes a ticket,
+// and the LAST CTA alone reads the block (33 KB), re-zeroes it for the next launch, exchanges it with the peers
+// and evaluates the ELBO term.  No grid barrier, no co-residency requirement, no partial workspace.
+constexpr int kAccumDoubles = kFeat * kFeat + kFeat;        // [S2 (64 x 64, upper triangle used) | S1 (64)] float64
+constexpr int kScratchStride = kFeat + 1;                   // padded row stride of the CTA's [128][64] float64 scratch
+constexpr int kSlices = BB_GAUSSIAN_PASS_SLICES;            // stride of a rank's flag words in a peer's flag array
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
@@ -207,137 +202,168 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   return v;
 }
 
-// Runs in every CTA after its partials are written and the grid barrier has passed.
-// `red` is kThreads doubles of shared memory (the drained pipeline stages are reused).
-__device__ __forceinline__ void fused_tail(const SuffstatsTail& tp, const double* __restrict__ partial,
-                                           unsigned int bar_base, double* red, volatile int* sflag) {
+// Runs in the last CTA to finish only.  `pay` is d*d + d + 1 doubles of shared memory (drained pipeline
+// stages), `coef` as many, `red` one double per warp.  Every phase issues all of a thread's loads before the first dependent
+// instruction or store (one memory latency per phase, not one per element).
+constexpr int kPerThread = (kFeat * kFeat + kFeat + 1 + kThreads - 1) / kThreads;     // 8 payload elements per thread
+constexpr int kAccPerThread = (kAccumDoubles + kThreads - 1) / kThreads;              // 8 accumulator slots per thread
+
+__device__ __forceinline__ void last_cta_tail(const SuffstatsTail& tp, double* pay, double* coef, double* red,
+                                              volatile int* sflag) {
   const int t = threadIdx.x;
   const int d = tp.d;
-  const int elements = d * d + d + 1;                     // [S2 | S1 | row count]
-  const int per = (elements + kSlices - 1) / kSlices;     // outputs per slice (33 at d = 64)
-  const int groups = kThreads / per;                      // partial groups summed in parallel
-  const int e = t % per, g = t / per;
-  const int grid = gridDim.x;
+  const int elements = d * d + d + 1;                     // packed payload [S2 | S1 | row count]
   const bool want_ll = tp.loglik != nullptr;
-  // the epoch lives in device memory (this launch uses stored + 1; the last CTA stores it back), so a
-  // captured CUDA graph can be replayed: no per-launch host argument changes
-  const uint32_t epoch = tp.world > 1 ? __ldcg(tp.epoch_dev) + 1u : 0u;
-  const int64_t parity_off = static_cast<int64_t>(epoch & 1u) * tp.world * tp.stride;
-  for (int slice = blockIdx.x; slice < kSlices && slice * per < elements; slice += grid) {
-    const int idx = slice * per + e;
-    double acc = 0.0;
-    if (g < groups && idx < elements) {
-      if (idx < d * d + d) {
-        // element of the packed output -> element of a CTA's [64 x 64 | 64] partial
-        const int pidx = idx < d * d ? (idx / d) * kFeat + idx % d : kFeat * kFeat + (idx - d * d);
-        const double* src = partial + pidx;
-        // fixed assignment of partials to groups and a fixed combination order: deterministic; four
-        // independent accumulators keep the L2 loads in flight together
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int p = g;
-        for (; p + 3 * groups < grid; p += 4 * groups) {
-          a0 += __ldcg(src + static_cast<int64_t>(p) * kPartialDoubles);
-          a1 += __ldcg(src + static_cast<int64_t>(p + groups) * kPartialDoubles);
-          a2 += __ldcg(src + static_cast<int64_t>(p + 2 * groups) * kPartialDoubles);
-          a3 += __ldcg(src + static_cast<int64_t>(p + 3 * groups) * kPartialDoubles);
-        }
-        for (; p < grid; p += groups) a0 += __ldcg(src + static_cast<int64_t>(p) * kPartialDoubles);
-        acc = (a0 + a1) + (a2 + a3);
-      } else if (g == 0) {
-        acc = tp.local_count;
-      }
+  // 0. the consumer's coefficients for this thread's payload elements: issued first, needed last
+  //    (parked in shared memory: registers are short in the exchange)
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) {
+    const int idx = t + k * kThreads;
+    double c = 0.0;
+    if (want_ll && idx < d * d) c = -0.5 * __ldg(tp.e_lambda + idx);
+    else if (want_ll && idx < d * d + d) c = __ldg(tp.e_lambda_mu + (idx - d * d));
+    if (idx < elements) coef[idx] = c;
+  }
+  // 1. this rank's statistics out of the accumulator block (re-zeroed for the next launch), mirrored into the
+  //    packed payload
+  {
+    double v[kAccPerThread];
+#pragma unroll
+    for (int k = 0; k < kAccPerThread; ++k) {
+      const int e = t + k * kThreads;
+      const int r = e >> 6, c = e & 63;
+      const bool used = e < kFeat * kFeat ? (r <= c && c < d) : (e < kAccumDoubles && e - kFeat * kFeat < d);
+      v[k] = used ? __ldcg(tp.accum + e) : 0.0;
     }
-    if (g < groups) red[g * per + e] = acc;
-    if (t == 0) *sflag = 0;
-    __syncthreads();
-    const bool owner = g == 0 && idx < elements;          // threads 0 .. per-1
-    double v = 0.0;
-    if (owner)
-      for (int j = 0; j < groups; ++j) v += red[j * per + e];     // fixed order: deterministic
-    if (tp.world > 1) {
-      if (owner) {
-        // push this rank's slice into every rank's receive buffer (own included), slot [rank]
-        for (int r = 0; r < tp.world; ++r) tp.peer_recv[r][parity_off + tp.rank * tp.stride + idx] = v;
-        __threadfence_system();
-      }
-      __syncthreads();
-      if (t < tp.world) {
-        st_release_sys_u32(tp.peer_flags[t] + tp.rank * kSlices + slice, epoch);
-        const uint32_t* mine = tp.peer_flags[tp.rank] + t * kSlices + slice;
-        const long long t0 = clock64();
-        // epochs are compared as signed distances so that the counter may wrap
-        while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - epoch) < 0) {
-          if (clock64() - t0 > tp.spin_limit) {
-            atomicMax(tp.status, t + 1);
-            *sflag = 1;
-            break;
-          }
+#pragma unroll
+    for (int k = 0; k < kAccPerThread; ++k) {
+      const int e = t + k * kThreads;
+      const int r = e >> 6, c = e & 63;
+      if (e < kFeat * kFeat) {
+        if (r <= c && c < d) {
+          tp.accum[e] = 0.0;
+          pay[r * d + c] = v[k];
+          pay[c * d + r] = v[k];
         }
+      } else if (e < kAccumDoubles && e - kFeat * kFeat < d) {
+        tp.accum[e] = 0.0;
+        pay[d * d + (e - kFeat * kFeat)] = v[k];
       }
-      __syncthreads();
-      if (owner) {
-        if (*sflag) {
-          v = __longlong_as_double(0x7ff8000000000000LL);  // lost peer: poison, never a partial sum
-        } else {
-          const double* mine = tp.peer_recv[tp.rank] + parity_off + idx;
-          v = 0.0;
-          for (int r = 0; r < tp.world; ++r) v += __ldcv(mine + r * tp.stride);   // rank order: same bits everywhere
-        }
-      }
-    }
-    double term = 0.0;
-    if (owner) {
-      if (idx < d * d) {
-        if (tp.accumulate) v += tp.s2[idx];
-        tp.s2[idx] = v;
-        if (want_ll) term = -0.5 * tp.e_lambda[idx] * v;
-      } else if (idx < d * d + d) {
-        const int f = idx - d * d;
-        if (tp.s1 != nullptr) {
-          if (tp.accumulate) v += tp.s1[f];
-          tp.s1[f] = v;
-        }
-        if (want_ll) term = v * tp.e_lambda_mu[f];
-      } else {
-        if (tp.count_out != nullptr) *tp.count_out = v;
-        tp.scratch[kSlices] = v;
-      }
-    }
-    __syncthreads();                                       // red[] is reused below
-    if (want_ll) {
-      if (t < per) red[t] = term;
-      __syncthreads();
-      if (t == 0) {
-        double total = 0.0;
-        for (int j = 0; j < per; ++j) total += red[j];
-        tp.scratch[slice] = total;
-      }
-      __syncthreads();
     }
   }
+  if (t == 0) {
+    pay[d * d + d] = tp.local_count;
+    *sflag = 0;
+  }
+  __syncthreads();
   BB_TL(4);
-  // completion ticket = second round of arrivals on the barrier counter
-  __threadfence();
+  double val[kPerThread];
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) {
+    const int idx = t + k * kThreads;
+    val[k] = idx < elements ? pay[idx] : 0.0;
+  }
+  // 2. exchange: push the payload into every PEER's receive buffer, slot [rank], over NVLink; one flag per
+  //    (sender, receiver); sum the world's slots (own payload from registers, the peers' from LOCAL memory) in
+  //    rank order, so the result is bit-identical on every rank.  Receive buffers are double-buffered by epoch
+  //    parity; the epoch lives in device memory (this launch uses stored + 1), so a captured CUDA graph can be
+  //    replayed.
+  uint32_t epoch = 0u;
+  if (tp.world > 1) {
+    epoch = __ldcg(tp.epoch_dev) + 1u;
+    const int64_t parity_off = static_cast<int64_t>(epoch & 1u) * tp.world * tp.stride;
+    for (int i = 1; i < tp.world; ++i) {
+      double* dst = tp.peer_recv[(tp.rank + i) % tp.world] + parity_off + tp.rank * tp.stride;
+#pragma unroll
+      for (int k = 0; k < kPerThread; ++k)
+        if (t + k * kThreads < elements) dst[t + k * kThreads] = val[k];
+    }
+    // the CTA barrier orders every thread's pushes before the flag threads' release (cumulativity): one
+    // system-scope fence per flag thread, not one per thread
+    __syncthreads();
+    BB_TL(5);
+    if (t < tp.world && t != tp.rank) {
+      st_release_sys_u32(tp.peer_flags[t] + tp.rank * kSlices, epoch);
+      const uint32_t* mine = tp.peer_flags[tp.rank] + t * kSlices;
+      const long long t0 = clock64();
+      // epochs are compared as signed distances so that the counter may wrap
+      while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - epoch) < 0) {
+        if (clock64() - t0 > tp.spin_limit) {
+          atomicMax(tp.status, t + 1);
+          *sflag = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    BB_TL(6);
+    const bool lost = *sflag != 0;
+    const double* mine = tp.peer_recv[tp.rank] + parity_off;
+    double sum[kPerThread];
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) sum[k] = 0.0;
+    for (int r0 = 0; r0 < tp.world; r0 += 2) {               // two ranks' slots in flight together
+      double in[2][kPerThread];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+          const int r = r0 + j, idx = t + k * kThreads;
+          in[j][k] = (r < tp.world && r != tp.rank && idx < elements) ? __ldcv(mine + r * tp.stride + idx) : 0.0;
+        }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k)
+          if (r0 + j < tp.world) sum[k] += (r0 + j == tp.rank) ? val[k] : in[j][k];
+    }
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k)
+      val[k] = lost ? __longlong_as_double(0x7ff8000000000000LL) : sum[k];      // lost peer: poison, never a partial sum
+  }
+  // 3. outputs and the expected log-likelihood of the reduced statistics
+  double term = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) {
+    const int idx = t + k * kThreads;
+    double v = val[k];
+    if (idx < d * d) {
+      if (tp.accumulate) v += tp.s2[idx];
+      tp.s2[idx] = v;
+    } else if (idx < d * d + d) {
+      if (tp.s1 != nullptr) {
+        if (tp.accumulate) v += tp.s1[idx - d * d];
+        tp.s1[idx - d * d] = v;
+      }
+    } else if (idx == d * d + d) {
+      if (tp.count_out != nullptr) *tp.count_out = v;
+      pay[idx] = v;                                        // the reduced row count, read by thread 0 below
+    }
+    if (idx < elements) term += coef[idx] * v;
+  }
+  if (want_ll) {
+    // fixed reduction tree: the value depends only on the reduced statistics
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) term += __shfl_xor_sync(0xffffffffu, term, off);
+    if ((t & 31) == 0) red[t >> 5] = term;
+  }
   __syncthreads();
-  if (t == 0) *sflag = atomicAdd(tp.bar_arrive, 1u) == bar_base + 2u * static_cast<unsigned int>(grid) - 1u;
-  __syncthreads();
-  if (!*sflag || t != 0) return;
-  // last CTA of the grid: every CTA has read the stored base / epoch and finished
-  __threadfence();
-  *tp.bar_base = bar_base + 2u * static_cast<unsigned int>(grid);
-  if (tp.world > 1) *tp.epoch_dev = epoch;
-  if (!want_ll) return;
-  double total = 0.0;
-  const int used = (elements + per - 1) / per;
-  for (int j = 0; j < used; ++j) total += __ldcg(tp.scratch + j);
-  const double n = tp.world > 1 ? __ldcg(tp.scratch + kSlices) : tp.n_total;
-  const double log_2pi = 1.8378770664093454835606594728112;
-  tp.loglik[0] = total - 0.5 * n * d * log_2pi + 0.5 * n * tp.e_logdet - 0.5 * n * tp.e_mu_l_mu;
+  if (t == 0) {
+    if (want_ll) {
+      double total = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) total += red[w];
+      const double n = tp.world > 1 ? pay[d * d + d] : tp.n_total;
+      const double log_2pi = 1.8378770664093454835606594728112;
+      tp.loglik[0] = total - 0.5 * n * d * log_2pi + 0.5 * n * tp.e_logdet - 0.5 * n * tp.e_mu_l_mu;
+    }
+    *tp.ticket = 0u;                                       // the next launch is stream-ordered after this one
+    if (tp.world > 1) *tp.epoch_dev = epoch;
+  }
+  BB_TL(7);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
-                    double* __restrict__ partial,      // [grid][kPartialDoubles]
                     const SuffstatsTail tail) {
   extern __shared__ uint8_t smem_raw[];
   BB_TL(0);
@@ -456,8 +482,10 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
       }
     }
     // every MMA of this CTA has completed (last acc_full), so every pipeline stage has been consumed: the
-    // first two stages become the CTA's [128][64] float64 scratch (hi^T hi on rows 0-63, lo^T hi on 64-127)
-    double* out = reinterpret_cast<double*>(sm.stage[0]) + (q * 32 + lane) * kFeat + chalf * kCols;
+    // first three stages become the CTA's [128][64] float64 scratch (hi^T hi on rows 0-63, lo^T hi on 64-127);
+    // rows are padded to 65 doubles so that neither these row-per-lane stores nor the transposed reads below
+    // meet in one shared-memory bank
+    double* out = reinterpret_cast<double*>(sm.stage[0]) + (q * 32 + lane) * kScratchStride + chalf * kCols;
 #pragma unroll
     for (int c = 0; c < kCols; ++c) out[c] = acc[c];
   }
@@ -466,72 +494,54 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
   __syncthreads();
   BB_TL(2);
   if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
-  // this CTA's partial statistics in the packed output layout [S2 (64 x 64) | S1 (64)]:
-  // S2[r][c] = hi^T hi [r][c] + lo^T hi [r][c] + lo^T hi [c][r]
+  // this CTA's partial statistics, S2[r][c] = hi^T hi [r][c] + lo^T hi [r][c] + lo^T hi [c][r] (upper triangle)
+  // and S1, added into the accumulator block at L2.  The start is rotated per CTA so that the 148 CTAs, which
+  // finish together, do not all hit the same address at the same moment.
   {
     const double* P = reinterpret_cast<const double*>(sm.stage[0]);
-    double* mine = partial + static_cast<int64_t>(blockIdx.x) * kPartialDoubles;
-    for (int e = threadIdx.x; e < kPartialDoubles; e += kThreads) {
-      double v;
+    const int d = tail.d;
+    const int rot = static_cast<int>((blockIdx.x * 416u) % kAccumDoubles);
+    for (int e0 = threadIdx.x; e0 < kAccumDoubles; e0 += kThreads) {
+      int e = e0 + rot;
+      if (e >= kAccumDoubles) e -= kAccumDoubles;
       if (e < kFeat * kFeat) {
         const int r = e >> 6, c = e & 63;
-        v = P[r * kFeat + c] + P[(kFeat + r) * kFeat + c] + P[(kFeat + c) * kFeat + r];
-      } else {
-        v = sm.s1_part[0][e - kFeat * kFeat] + sm.s1_part[1][e - kFeat * kFeat];
+        if (r <= c && c < d)
+          atomicAdd(tail.accum + e, P[r * kScratchStride + c] + P[(kFeat + r) * kScratchStride + c] +
+                                        P[(kFeat + c) * kScratchStride + r]);
+      } else if (e - kFeat * kFeat < d) {
+        atomicAdd(tail.accum + e, sm.s1_part[0][e - kFeat * kFeat] + sm.s1_part[1][e - kFeat * kFeat]);
       }
-      mine[e] = v;
     }
   }
-  // every CTA's partials are complete and visible before any CTA reads them
+  // completion ticket: the last CTA to arrive sees every CTA's reductions
   __threadfence();
   __syncthreads();
-#ifdef BB_SUFFSTATS_COOP
-  cg::this_grid().sync();
-  const unsigned int bar_base = __ldcg(tail.bar_base);
-#else
-  // Grid barrier on the monotonic arrival counter (all CTAs are resident: grid <= SM count, one CTA per
-  // SM).  The counter is never reset: this launch's arrivals run from bar_base (stored by the previous
-  // launch's last CTA) to bar_base + 2 grid -- first the barrier, then the completion ticket.
-  __shared__ unsigned int bar_base_s;
-  __shared__ int bar_lost_s;
-  if (threadIdx.x == 0) {
-    const unsigned int base = __ldcg(tail.bar_base);
-    bar_base_s = base;
-    bar_lost_s = 0;
-    atomicAdd(tail.bar_arrive, 1u);
-    const unsigned int target = base + gridDim.x;
-    const long long t0 = clock64();
-    while (static_cast<int>(ld_acquire_gpu_u32(tail.bar_arrive) - target) < 0) {
-      if (clock64() - t0 > kGridBarrierSpinLimit) {         // a CTA of this grid is not resident: never hang
-        if (tail.status != nullptr) atomicMax(tail.status, 0x40000000);
-        bar_lost_s = 1;
-        break;
-      }
-    }
-  }
+  volatile int* sflag = reinterpret_cast<volatile int*>(&sm.tmem_base);
+  if (threadIdx.x == 0) *sflag = atomicAdd(tail.ticket, 1u) == gridDim.x - 1u;
   __syncthreads();
-  const unsigned int bar_base = bar_base_s;
-  if (bar_lost_s) return;
-#endif
   BB_TL(3);
-  // the pipeline is drained (every TMA load was consumed): its third stage is scratch now
-  fused_tail(tail, partial, bar_base, reinterpret_cast<double*>(sm.stage[2]),
-             reinterpret_cast<volatile int*>(&sm.tmem_base));
+  if (!*sflag) return;
+  __threadfence();
+  // scratch of the tail: the payload in stages 3-4 (33 KB), the consumer's coefficients in stages 0-1 (the
+  // CTA's statistics scratch is dead: its reductions were issued before the barrier above), per-warp terms in 5
+  last_cta_tail(tail, reinterpret_cast<double*>(sm.stage[3]), reinterpret_cast<double*>(sm.stage[0]),
+                reinterpret_cast<double*>(sm.stage[5]), sflag);
 #ifdef BB_SUFFSTATS_TIMELINE
-  BB_TL(5);
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    printf("timeline ns: init %llu  main+partials %llu  gridsync %llu  slice-reduce %llu  rest-of-tail(cta0) %llu  | since previous launch's end %lld\n",
-           g_tl[1] - g_tl[0], g_tl[2] - g_tl[1], g_tl[3] - g_tl[2], g_tl[4] - g_tl[3], g_tl[5] - g_tl[4],
-           static_cast<long long>(g_tl[0] - g_tl[6]));
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
+    printf("timeline ns (CTA 0): init %llu  main %llu  reductions+ticket %llu | last CTA %d: gather %llu  push+fence %llu  "
+           "flags %llu  sum+outputs %llu | launch total %llu  since previous launch's end %lld\n",
+           g_tl[1] - g_tl[0], g_tl[2] - g_tl[1], g_cta[1][0] ? g_tl[3] - g_cta[1][blockIdx.x] : 0ull, static_cast<int>(blockIdx.x),
+           g_tl[4] - g_tl[3], g_tl[5] - g_tl[4], g_tl[6] - g_tl[5], g_tl[7] - (tail.world > 1 ? g_tl[6] : g_tl[4]),
+           g_tl[7] - g_tl[0], static_cast<long long>(g_tl[0] - g_tl[8]));
     unsigned long long s0 = ~0ull, s1 = 0, m0 = ~0ull, m1 = 0;
     for (unsigned int b = 0; b < gridDim.x; ++b) {
       s0 = min(s0, g_cta[0][b]); s1 = max(s1, g_cta[0][b]);
       m0 = min(m0, g_cta[1][b]); m1 = max(m1, g_cta[1][b]);
     }
-    printf("   CTA entry skew %llu ns, main-loop-end skew %llu ns (CTA 0 entry at +%llu, main end at +%llu of the earliest)\n",
-           s1 - s0, m1 - m0, g_tl[0] - s0, g_tl[2] - m0);
-    g_tl[6] = g_tl[5];
+    printf("   CTA entry skew %llu ns, main-loop-end skew %llu ns; last main-loop end -> kernel end %llu ns\n",
+           s1 - s0, m1 - m0, g_tl[7] - m1);
+    g_tl[8] = g_tl[7];
   }
 #endif
 }
@@ -571,16 +581,15 @@ int grid_for(int64_t n) {
 }
 }  // namespace
 
-// partials + [kSlices + 2] float64 tail scratch (the last one holds the two barrier words of the
-// caller-workspace entry points)
-int64_t suffstats_tc_workspace(int64_t n) {
-  return grid_for(n) * kPartialDoubles * static_cast<int64_t>(sizeof(double)) +
-         (kSlices + 2) * static_cast<int64_t>(sizeof(double)) + 512;
+// the accumulator block + the ticket word (caller-workspace entry points; a bb_gaussian_pass handle owns
+// persistent ones)
+int64_t suffstats_tc_workspace(int64_t) {
+  return kAccumDoubles * static_cast<int64_t>(sizeof(double)) + 64 + 512;
 }
 
-// ONE cooperative launch: statistics, cross-CTA reduction, (world > 1) cross-GPU exchange, expected
-// log-likelihood.  `tail` carries outputs / consumers / peers; its scratch and ticket are carved from the
-// workspace here.  n == 0 is allowed (a rank with no rows still takes part in the exchange).
+// ONE launch: statistics, cross-CTA reduction, (world > 1) cross-GPU exchange, expected
+// log-likelihood.  `tail` carries outputs / consumers / peers; without its own accumulator block and ticket
+// (zero between launches) they are carved from the workspace here and zeroed by a memset node.  n == 0 is allowed (a rank with no rows still takes part in the exchange).
 int launch_suffstats_tc_fused(const float* x, int64_t n, int d, void* workspace, int64_t workspace_bytes,
                               SuffstatsTail tail, cudaStream_t stream) {
   if (n < 0 || d < 4 || d > kFeat || (d % 4) != 0 || (n > 0 && !suffstats_tc_supported(n, d, x))) {
@@ -625,15 +634,11 @@ int launch_suffstats_tc_fused(const float* x, int64_t n, int d, void* workspace,
   }
   int64_t tiles = (n + kTileRows - 1) / kTileRows;
   const int grid = grid_for(n);
-  double* partial = reinterpret_cast<double*>(
-      (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
-  tail.scratch = partial + static_cast<int64_t>(grid) * kPartialDoubles;
-  if (tail.bar_arrive == nullptr) {
-    // caller-provided (uninitialised) workspace: the barrier words live behind the scratch and are zeroed
-    // per launch; a bb_gaussian_pass handle owns persistent ones instead (no memset in its step)
-    tail.bar_arrive = reinterpret_cast<unsigned int*>(tail.scratch + kSlices + 1);
-    tail.bar_base = tail.bar_arrive + 1;
-    BB_CUDA_OK(cudaMemsetAsync(tail.bar_arrive, 0, 2 * sizeof(unsigned int), stream));
+  if (tail.accum == nullptr || tail.ticket == nullptr) {
+    double* block = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+    tail.accum = block;
+    tail.ticket = reinterpret_cast<unsigned int*>(block + kAccumDoubles);
+    BB_CUDA_OK(cudaMemsetAsync(block, 0, kAccumDoubles * sizeof(double) + sizeof(unsigned int), stream));
   }
   tail.d = d;
   if (tail.world < 1) tail.world = 1;
@@ -641,17 +646,7 @@ int launch_suffstats_tc_fused(const float* x, int64_t n, int d, void* workspace,
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout)) + 1024;
   static SmemOptIn smem_opt_in_0;
   BB_CUDA_OK(smem_opt_in_0.ensure(suffstats_tc_kernel, smem_bytes));
-#ifdef BB_SUFFSTATS_COOP
-  void* args[] = {&map, &tiles, &partial, &tail};
-  BB_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(suffstats_tc_kernel), dim3(grid), dim3(kThreads),
-                                         args, smem_bytes, stream));
-#else
-  // a plain launch: the grid barrier inside needs every CTA resident, which grid <= SM count with one CTA
-  // per SM gives as long as no other kernel occupies SMs indefinitely (one pass at a time per device; a CTA
-  // that cannot become resident turns into a status flag after ~2 s, not a hang).  A cooperative launch
-  // would guarantee residency but was measured to add ~10 us of launch latency per step.
-  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, partial, tail);
-#endif
+  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, tail);
   BB_CHECK_LAUNCH("suffstats_tc_kernel");
   return BB_OK;
 }

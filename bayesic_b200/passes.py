@@ -86,6 +86,8 @@ class GmmStep(object):
                          (X, [('out', 0), ('sum', 1)])], 2)
         lin = A.dot(X, bk.T)
         self.logits_fn = (lin + (-0.5) * quad + ck.dimshuffle('x', 0)).compile()
+        self.exp_fn = A.exp(A.var('LR', 2)).compile()
+        self._whiten_key, self._whiten_value = None, None
 
     @staticmethod
     def expectations(log_pi, m, beta, W, nu):
@@ -121,26 +123,32 @@ class GmmStep(object):
         nk, rx, rxx = stats.weighted_suffstats_from_logits(X, logits, lse)
         return {'logits': logits, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
 
+    def _whitened(self, Ak, bk, ck):
+        """``whiten`` once per parameter update, not per minibatch: cached on the identity and version
+        counters of the parameter tensors."""
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (Ak, bk, ck))
+        if self._whiten_key != key:
+            self._whiten_value, self._whiten_key = self.whiten(Ak, bk, ck), key
+        return self._whiten_value
+
     def __call__(self, X, Ak, bk, ck, fused=True, want_log_resp=True):
-        import torch
+        """Local step from (A_k, b_k, c_k).  Every per-minibatch operation is a device kernel of this
+        library: the shapes the tcgen05 kernels serve take ``local_step`` (two kernels; a third, the
+        in-place row normalisation, only when the log-responsibilities themselves are asked for); other
+        shapes take the compiled einsum plan, the log-softmax kernel, a compiled ``exp`` and the generic
+        weighted-statistics kernel."""
         d, k = X.shape[1], Ak.shape[0]
-        if (fused and not want_log_resp and stats.mixture_logits_supported(d, k) and d % 8 == 0 and k <= 256
-                and X.shape[0] >= 1024):
-            # whole local step in two kernels: logits + row log-sum-exp, then the statistics with
-            # r = exp(logit - lse) formed inside the operand conversion (R is never written)
-            logits, lse, sum_lse = stats.mixture_logits(X, *self.whiten(Ak, bk, ck), upper_triangular=True)
-            nk, rx, rxx = stats.weighted_suffstats_from_logits(X, logits, lse)
-            return {'logits': logits, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
-        if fused and stats.mixture_logits_supported(X.shape[1], Ak.shape[0]):
-            # same value as the einsum plan, as one tcgen05 projection with the quadratic form
-            # consumed on chip (the plan route materialises N x K x D and cannot run at cfg3 size)
-            logits, _, _ = stats.mixture_logits(X, *self.whiten(Ak, bk, ck), want_lse=False, want_sum=False,
-                                               upper_triangular=True)
-        else:
-            logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
+        if fused and stats.mixture_logits_supported(d, k) and d % 8 == 0 and k <= 256 and k % 4 == 0:
+            out = self.local_step(X, *self._whitened(Ak, bk, ck))
+            if want_log_resp:
+                logits = out.pop('logits')
+                log_resp, _, _ = stats.log_responsibilities(logits, want_lse=False, want_sum=False,
+                                                            out=logits)     # in place
+                out['log_resp'] = log_resp
+            return out
+        logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
         log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place
-        resp = torch.exp(log_resp)
-        nk, rx, rxx = stats.weighted_suffstats(X, resp)
+        nk, rx, rxx = stats.weighted_suffstats(X, self.exp_fn(LR=log_resp))
         return {'log_resp': log_resp, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
 
 

@@ -172,8 +172,9 @@ def test_gaussian_pass_lost_peer_gives_nan_and_a_status():
             lib.bb_gaussian_pass_destroy(h)
 
 
-def test_gaussian_pass_matches_the_workspace_entry_point_bit_for_bit():
-    """bb_suffstats_gaussian_loglik (caller workspace) and the handle-based pass are the same kernel."""
+def test_gaussian_pass_matches_the_workspace_entry_point():
+    """bb_suffstats_gaussian_loglik (caller workspace) and the handle-based pass are the same kernel (its CTAs'
+    float64 partial sums meet in arrival order, so two launches agree to ~1e-16 relative, not bit for bit)."""
     import torch
     import bayesic_b200.stats as S
     from bayesic_b200.parallel import GaussianPass
@@ -187,6 +188,122 @@ def test_gaussian_pass_matches_the_workspace_entry_point_bit_for_bit():
     p = GaussianPass(d, dev)
     cnt, b1, b2, bll = p.run(X, e_lambda, e_lambda_mu, 0.3, -0.2)
     p.check()
-    assert torch.equal(a1, b1) and torch.equal(a2, b2) and torch.equal(all_, bll)
+    close = lambda u, v: torch.testing.assert_close(u, v, rtol=1e-12, atol=1e-12 * float(v.abs().max()))
+    close(a1, b1), close(a2, b2), close(all_, bll)
     _, c1, c2 = S.gaussian_suffstats(X)
-    assert torch.equal(a2, c2)
+    close(a2, c2)
+    assert torch.equal(b2, b2.T)                      # symmetric by construction
+
+
+def _reduce_on_one_gpu(layout, per_rank_parts, rows):
+    """What ``parallel._reduce_into`` does on every rank -- pack the local parts and the row count into the
+    communicator's input, one ``bb_comm_allreduce_sum`` -- with all the "ranks" on this device."""
+    import torch
+    world = len(per_rank_parts)
+    lib, ins, outs, flags, comms = _make_comms(world, layout.numel)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    try:
+        for r in range(world):
+            views = layout.views(ins[r][:layout.numel])
+            for name, value in per_rank_parts[r].items():
+                views[name].copy_(value.reshape(views[name].shape))
+            views['count'].fill_(float(rows[r]))
+        torch.cuda.synchronize()
+        for r in range(world):
+            L.check(lib.bb_comm_allreduce_sum(comms[r], layout.numel, ctypes.c_void_p(streams[r].cuda_stream)))
+        torch.cuda.synchronize()
+        for r in range(world):
+            status = ctypes.c_int32(-1)
+            L.check(lib.bb_comm_status(comms[r], ctypes.byref(status), None))
+            assert status.value == 0
+            assert torch.equal(outs[r][:layout.numel], outs[0][:layout.numel])       # replicated bit for bit
+        return {k: v.cpu().numpy() for k, v in layout.views(outs[0][:layout.numel].clone()).items()}
+    finally:
+        for h in comms:
+            lib.bb_comm_destroy(h)
+
+
+def _scaled_close(got, want, scale, tol):
+    np.testing.assert_array_less(np.abs(got - want), tol * scale + 1e-300)
+
+
+def test_sharded_regression_statistics_equal_the_unsharded_oracle():
+    """cfg4 over 3 shards (ragged: 2304 / 1 / 1791 rows): local tcgen05 Gram passes, one peer all-reduce of
+    D^2 + D + 2 float64; against the float64 oracle on the concatenated rows."""
+    import torch
+    import bayesic_b200.stats as S
+    from bayesic_b200.parallel import PackedStats
+    d, rows = 256, [2304, 1, 1791]
+    rng = np.random.RandomState(11)
+    X = rng.randn(sum(rows), d).astype(np.float32)
+    y = (X @ (rng.randn(d) / np.sqrt(d)) + 0.1 * rng.randn(sum(rows))).astype(np.float32)
+    parts, lo = [], 0
+    for n in rows:
+        xtx, xty, yty = S.regression_suffstats(torch.from_numpy(X[lo:lo + n]).cuda(), torch.from_numpy(y[lo:lo + n]).cuda())
+        parts.append({'xtx': xtx, 'xty': xty, 'yty': yty})
+        lo += n
+    got = _reduce_on_one_gpu(PackedStats.regression(d), parts, rows)
+    wxtx, wxty, wyty = O.regression_suffstats(X, y)
+    dg = np.sqrt(np.diag(wxtx))
+    _scaled_close(got['xtx'], wxtx, np.outer(dg, dg), 2e-5)
+    _scaled_close(got['xty'], wxty, dg * np.sqrt(wyty), 2e-5)
+    np.testing.assert_allclose(got['yty'], wyty, rtol=1e-6)
+    assert float(got['count']) == float(sum(rows))
+
+
+def test_sharded_mixture_statistics_equal_the_unsharded_oracle():
+    """cfg3 over 2 shards: responsibilities stay sharded; {N_k, sum r x, sum r x x^T, sum lse} are summed."""
+    import torch
+    import bayesic_b200.stats as S
+    from bayesic_b200.parallel import PackedStats
+    d, k, rows = 64, 256, [3000, 2120]
+    rng = np.random.RandomState(12)
+    X = rng.randn(sum(rows), d).astype(np.float32)
+    logits = (rng.randn(sum(rows), k) * 2.0).astype(np.float32)
+    lr64 = logits.astype('f8') - np.log(np.exp(logits.astype('f8')).sum(1, keepdims=True))
+    R64 = np.exp(lr64)
+    parts, lo = [], 0
+    for n in rows:
+        lg = torch.from_numpy(logits[lo:lo + n]).cuda()
+        log_resp, lse, sum_lse = S.log_responsibilities(lg)
+        nk, rx, rxx = S.weighted_suffstats(torch.from_numpy(X[lo:lo + n]).cuda(), torch.exp(log_resp))
+        parts.append({'nk': nk, 'rx': rx, 'rxx': rxx, 'sum_lse': sum_lse})
+        lo += n
+    got = _reduce_on_one_gpu(PackedStats.mixture(k, d), parts, rows)
+    X64 = X.astype('f8')
+    wnk, wrx = R64.sum(0), R64.T @ X64
+    wrxx = np.einsum('nk,nd,ne->kde', R64, X64, X64)
+    x2 = R64.T @ (X64 ** 2)
+    np.testing.assert_allclose(got['nk'], wnk, rtol=2e-5)
+    _scaled_close(got['rx'], wrx, np.sqrt(wnk[:, None] * x2), 2e-5)
+    _scaled_close(got['rxx'], wrxx, np.sqrt(np.einsum('kd,ke->kde', x2, x2)), 2e-5)
+    want_lse = np.log(np.exp(logits.astype('f8')).sum(1)).sum()
+    np.testing.assert_allclose(float(got['sum_lse']), want_lse, rtol=1e-6)
+    assert float(got['count']) == float(sum(rows))
+
+
+def test_sharded_logistic_gradient_equals_the_unsharded_oracle():
+    """cfg5 over 2 shards: replicated draws W, {loglik[S], G[D, S]} summed over the ranks' rows."""
+    import torch
+    import bayesic_b200.stats as S
+    from bayesic_b200.parallel import PackedStats
+    d, s, rows = 512, 64, [1400, 2700]
+    rng = np.random.RandomState(13)
+    X = rng.randn(sum(rows), d).astype(np.float32)
+    y = (rng.rand(sum(rows)) < 0.5).astype(np.float32)
+    W = (rng.randn(s, d) / np.sqrt(d)).astype(np.float32)
+    Wd = torch.from_numpy(W).cuda()
+    parts, lo = [], 0
+    for n in rows:
+        loglik, G = S.logistic_reparam_stats(torch.from_numpy(X[lo:lo + n]).cuda(), torch.from_numpy(y[lo:lo + n]).cuda(), Wd)
+        parts.append({'loglik': loglik, 'G': G})
+        lo += n
+    got = _reduce_on_one_gpu(PackedStats.logistic(d, s), parts, rows)
+    Z = X.astype('f8') @ W.astype('f8').T
+    want_ll = (y[:, None] * Z - np.logaddexp(0.0, Z)).sum(0)
+    resid = y[:, None] - 1.0 / (1.0 + np.exp(-Z))
+    want_G = X.astype('f8').T @ resid
+    np.testing.assert_allclose(got['loglik'], want_ll, rtol=2e-5)
+    scale = np.linalg.norm(X.astype('f8'), axis=0)[:, None] * np.linalg.norm(resid, axis=0)[None, :]
+    _scaled_close(got['G'], want_G, scale, 2e-5)
+    assert float(got['count']) == float(sum(rows))

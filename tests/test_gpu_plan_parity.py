@@ -98,6 +98,11 @@ def test_call_time_errors():
         fn(X=INPUTS['x'], y=INPUTS['y'])                 # wrong rank
     with pytest.raises(ValueError):
         fn(X=INPUTS['X'], y=np.ones(7, dtype='float32'))  # contracted extents differ
+    counts = A.var('counts', 1, dtype='int64')
+    total = A.sum(counts, axis=0).compile()
+    assert float(total(counts=np.array([3, 4, 1 << 24], dtype='int64'))) == float((1 << 24) + 7)
+    with pytest.raises(ValueError):
+        total(counts=np.array([3, (1 << 24) + 1], dtype='int64'))   # not exact in float32: refused, not rounded
 
 
 def test_larger_random_contractions():
