@@ -566,7 +566,9 @@ struct bb_gaussian_pass {
   int d = 0, device = 0;
   void* ws = nullptr;
   int64_t ws_bytes = 0;
-  int* status = nullptr;           // device: [0] status word, [1] epochs completed, [2] completion ticket
+  int* status = nullptr;           // device: [0] status word, [1] epochs completed, [2] completion ticket,
+                                   // [4], [5] tile counters of even / odd launches
+  uint64_t launches = 0;
   int rank = 0, world = 1;
   double** peer_recv = nullptr;
   uint32_t** peer_flags = nullptr;
@@ -596,7 +598,7 @@ BB_API int bb_gaussian_pass_create(int32_t d, bb_gaussian_pass** pass) {
   p->ws_bytes = suffstats_tc_workspace(int64_t(1) << 30) + 256;
   if (cudaGetDevice(&p->device) != cudaSuccess || cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess ||
       cudaMemset(p->ws, 0, p->ws_bytes) != cudaSuccess ||
-      cudaMalloc(&p->status, 4 * sizeof(int)) != cudaSuccess || cudaMemset(p->status, 0, 4 * sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&p->status, 8 * sizeof(int)) != cudaSuccess || cudaMemset(p->status, 0, 8 * sizeof(int)) != cudaSuccess) {
     set_error("gaussian_pass_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     bb_gaussian_pass_destroy(p);
     return BB_ERR_CUDA;
@@ -641,6 +643,11 @@ BB_API int bb_gaussian_pass_run(bb_gaussian_pass* p, const float* X, int64_t n, 
   t.status = p->status;
   t.accum = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p->ws) + 255) & ~static_cast<uintptr_t>(255));
   t.ticket = reinterpret_cast<unsigned int*>(p->status + 2);
+  // consecutive launches may overlap (the next one streams while this one's last CTA finishes), so they
+  // alternate between two tile counters; each launch's last CTA re-zeroes its own
+  t.tile_counter = reinterpret_cast<unsigned int*>(p->status + 4 + (p->launches & 1));
+  t.pdl = 1;
+  ++p->launches;
   if (p->world > 1) {
     t.peer_recv = p->peer_recv; t.peer_flags = p->peer_flags; t.stride = p->stride;
     t.epoch_dev = reinterpret_cast<uint32_t*>(p->status + 1);

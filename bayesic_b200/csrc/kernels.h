@@ -45,6 +45,9 @@ struct SuffstatsTail {
   double* accum;               // [64 * 64 + 64] float64 accumulator block, zero between launches (null: carved from
                                // the workspace and zeroed per launch)
   unsigned int* ticket;        // completion ticket, zero between launches
+  unsigned int* tile_counter;  // dynamic tile scheduler: next unclaimed tile, zero at launch (null: static partition);
+                               // launches that may overlap (pdl) alternate between two counters
+  int pdl;                     // launch with programmatic stream serialization (handle-owned persistent state only)
   double local_count;          // this rank's row count (payload element d*d + d)
   int rank, world;
   double* const* peer_recv;    // device array [world]: receive buffers, [2][world][stride] float64 each

@@ -180,6 +180,8 @@ struct Fused2Params {
   int w_tmem_chunks;                // leading 64-feature chunks of the stacked W kept in TMEM (BB_FUSED2_W_TMEM, default 4)
   int prefetch;                     // L2 prefetch one converter step ahead of the register loads (BB_FUSED2_PREFETCH, default on)
   int collector;                    // A-operand collector reuse between MMAs that share A (BB_FUSED2_COLLECTOR, default on)
+  int ablate;                       // developer timing experiments (BB_FUSED2_ABLATE; results are WRONG when set): 1 no global
+                                    // loads, 2 no converter stores, 4 no W stream, 8 no Z MMAs, 16 no G MMAs, 32 no epilogue math
   const float* x;
   const float* y;
   const uint8_t* wprep;             // [d / 64 chunks][16 KB UMMA image of [W1; W2]]
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (2 * i < ld_rows_left) v = ldg_f4(ld_ptr + static_cast<int64_t>(2 * i) * kD + half * 64);
+          if (2 * i < ld_rows_left && !(p.ablate & 1)) v = ldg_f4(ld_ptr + static_cast<int64_t>(2 * i) * kD + half * 64);
           rx[i * 2 + half][0] = __float_as_uint(v.x);
           rx[i * 2 + half][1] = __float_as_uint(v.y);
           rx[i * 2 + half][2] = __float_as_uint(v.z);
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
         ld_rows_left -= kTileRows;
       }
       // L2 prefetch of the step after this one (ld_ptr now points at it): the warp's 8 rows x 4 lines
-      if (p.prefetch && ld_g < total && (lane >> 2) < ld_rows_left + sub)
+      if (p.prefetch && !(p.ablate & 1) && ld_g < total && (lane >> 2) < ld_rows_left + sub)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(ld_ptr - (sub * kD + c4 * 4) + (lane >> 2) * kD + (lane & 3) * 32));
     };
     auto split_in_place = [&]() {
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
         if ((seg & 1) == group) {
           split_in_place();
           ptx::mbar_wait_parked(&sm.x_free[seg], (static_cast<uint32_t>(t) & 1) ^ 1);
-          store(seg);
+          if (!(p.ablate & 2)) store(seg);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&sm.x_full[seg]);
@@ -384,10 +386,13 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
         for (int u = 0; u < 2; ++u) {
           const bool valid = j + u < n_valid;
           const float z = zv[j + u];
-          const float ez = ex2_approx(-1.4426950408889634f * fabsf(z));      // exp(-|z|) in (0, 1]
-          const float ope = 1.f + ez;
-          const float softplus = fmaf(0.6931471805599453f, lg2_approx(ope), fmaxf(z, 0.f));
-          const float rcp = rcp_approx(ope);
+          float ez = 0.5f, ope = 1.5f, softplus = z, rcp = 0.6f;
+          if (!(p.ablate & 32)) {
+            ez = ex2_approx(-1.4426950408889634f * fabsf(z));      // exp(-|z|) in (0, 1]
+            ope = 1.f + ez;
+            softplus = fmaf(0.6931471805599453f, lg2_approx(ope), fmaxf(z, 0.f));
+            rcp = rcp_approx(ope);
+          }
           const float sig = z >= 0.f ? rcp : ez * rcp;
           ll_t += valid ? fmaf(yv[j + u], z, -softplus) : 0.f;
           res[u] = valid ? yv[j + u] - sig : 0.f;        // rows past n contribute nothing to G
@@ -458,21 +463,21 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t b12 = ptx::make_smem_desc(x1 + c * (2 * kChunkBytes) + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
-                mma_bf16_ts(tmem + kTmemZ, tmem + kTmemW + c * 32 + ks * 8, b12, idesc_a, (c == 0 && ks == 0) ? 0u : 1u);
+                if (!(p.ablate & 8)) mma_bf16_ts(tmem + kTmemZ, tmem + kTmemW + c * 32 + ks * 8, b12, idesc_a, (c == 0 && ks == 0) ? 0u : 1u);
               }
               continue;
             }
-            const int ws = static_cast<int>(it % kWStages);
-            ptx::mbar_wait_parked(&sm.w_full[ws], static_cast<uint32_t>(it / kWStages) & 1);
+            const int ws = (p.ablate & 4) ? 0 : static_cast<int>(it % kWStages);
+            if (!(p.ablate & 4)) ptx::mbar_wait_parked(&sm.w_full[ws], static_cast<uint32_t>(it / kWStages) & 1);
             ptx::tc_fence_after_sync();
             const uint32_t wbase = ptx::smem_u32(sm.w[ws]);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t a = ptx::make_smem_desc(wbase + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
               const uint64_t b12 = ptx::make_smem_desc(x1 + c * (2 * kChunkBytes) + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
-              mma_bf16_ss(tmem + kTmemZ, a, b12, idesc_a, (c == 0 && ks == 0) ? 0u : 1u);
+              if (!(p.ablate & 8)) mma_bf16_ss(tmem + kTmemZ, a, b12, idesc_a, (c == 0 && ks == 0) ? 0u : 1u);
             }
-            ptx::mma_commit(&sm.w_empty[ws]);
+            if (!(p.ablate & 4)) ptx::mma_commit(&sm.w_empty[ws]);
             ++it;
           }
         }
@@ -491,6 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
             const uint64_t a2 = ptx::make_smem_desc(x2 + 2 * seg * (2 * kChunkBytes) + ks * 2048, 2 * kChunkBytes, 1024, ptx::kLayoutSwizzle128B);
             const uint64_t rb1 = ptx::make_smem_desc(r1 + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
             const uint64_t rb2 = ptx::make_smem_desc(r2 + ks * 32, 16, 1024, ptx::kLayoutSwizzle128B);
+            if (p.ablate & 16) continue;
             if (p.collector) {
               mma_bf16_ss_fill(d_tmem, a1, rb1, idesc_b, (first_in_chain && ks == 0) ? 0u : 1u);
               mma_bf16_ss_lastuse(d_tmem, a1, rb2, idesc_b, 1u);
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
     }
   } else {
     // ---------------- W producer: bulk copies of the L2-resident stacked chunks ----------------
-    if (lane == 0) {
+    if (lane == 0 && !(p.ablate & 4)) {
       uint64_t keep;
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
       int64_t it = 0;
@@ -633,6 +639,8 @@ int launch_logistic_fused2(const float* x, const float* y, const float* w, int64
   p.w_tmem_chunks = w_tmem;
   static const int prefetch = getenv("BB_FUSED2_PREFETCH") ? atoi(getenv("BB_FUSED2_PREFETCH")) : 1;
   p.prefetch = prefetch;
+  static const int ablate = getenv("BB_FUSED2_ABLATE") ? atoi(getenv("BB_FUSED2_ABLATE")) : 0;
+  p.ablate = ablate;
   p.x = x; p.y = y; p.wprep = wprep; p.partial_g = partial_g; p.partial_ll = partial_ll; p.n = n;
   switch (d / 128) {
     case 1: BB_TRY(launch_fused2_instance<1>(p, grid, stream)); break;

@@ -47,6 +47,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
@@ -55,17 +57,10 @@ namespace bb {
 
 namespace {
 
-// epilogue warps wait ~5 000 cycles per 512-row chunk; a backing-off wait (mbar_wait_sleep) was
-// measured here and made no difference (0.772 ms either way), so they spin
-#ifdef BB_SUFFSTATS_EPI_SLEEP
-#define BB_SUFFSTATS_EPI_WAIT(bar, parity) ptx::mbar_wait_sleep(bar, parity, 64)
-#else
-#define BB_SUFFSTATS_EPI_WAIT(bar, parity) ptx::mbar_wait(bar, parity)
-#endif
-
 constexpr int kFeat = 64;          // padded feature extent (= MMA N, = half of MMA M)
 constexpr int kTileRows = 128;     // data rows per pipeline stage
 constexpr int kStages = 6;
+constexpr int kClaimTiles = 4;     // tiles per claim of the dynamic scheduler (512 rows = 128 KB, ~2 us of one SM's share)
 // TMEM accumulators are drained to float64 every kFlushTiles tiles.  The tensor core truncates
 // its fp32 accumulate, so the chunk length sets the (systematic) error: measured on B200 at
 // N = 16 Mi, D = 64:  4 tiles (512 rows) 2.5e-6 relative, 0.79 ms/pass;  1 tile 7e-7, 0.93 ms.
@@ -74,6 +69,10 @@ constexpr int kStages = 6;
 #define BB_SUFFSTATS_FLUSH_TILES 4
 #endif
 constexpr int kFlushTiles = BB_SUFFSTATS_FLUSH_TILES;
+// a claim of the dynamic scheduler is exactly one fp32 accumulation chunk, aligned: whichever CTA processes it,
+// the chunk's fp32 sums are the same, so the statistics do not depend on the tile assignment beyond the order
+// of the float64 additions
+static_assert(kClaimTiles == kFlushTiles, "claims must coincide with the fp32 accumulation chunks");
 constexpr int kBoxCols = 32;       // one TMA box = 128 rows x 32 floats (one 128-byte swizzle span per row)
 constexpr int kHalfBytes = kTileRows * kBoxCols * 4;   // 16 KB
 constexpr int kStageBytes = 2 * kHalfBytes;            // 32 KB
@@ -95,7 +94,10 @@ struct __align__(1024) SmemLayout {
   uint64_t a_free[2];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t done;                 // MMA issuer: the tile stream has ended, total_tiles is valid
   double s1_part[2][kFeat];      // Sigma x of the two row halves (split warps)
+  volatile int stage_valid[kStages];   // 1: the stage holds a tile; 0: end of this CTA's tile stream
+  volatile int total_tiles;
   uint32_t tmem_base;
 };
 
@@ -111,8 +113,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 // (lane = feature, conflict-free: the 32 lanes of a load cover one 128-byte row), split, and
 // store 8 data rows at a time as 8 TMEM columns.
 template <bool kIsLo>
-__device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, int q, int khalf,
-                                                int lane, int my_tiles) {
+__device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, int q, int khalf, int lane) {
   const int half = q & 1;             // which 32-feature column block
   // byte offset of (row j of an 8-row group, feature = lane) inside a stage: rows are 128 B,
   // 32-byte chunks XOR-swizzled with (row & 3)  (TMA SWIZZLE_128B_ATOM_32B)
@@ -124,10 +125,11 @@ __device__ __forceinline__ void split_warp_loop(SmemLayout& sm, uint32_t tmem, i
   const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemA +
                              khalf * (kKBlocks / 2) * 8;
   double s1 = 0.0;
-  for (int i = 0; i < my_tiles; ++i) {
+  for (int i = 0;; ++i) {
     const int s = i % kStages;
     const int b = i & 1;
     ptx::mbar_wait(&sm.full[s], (i / kStages) & 1);
+    if (!sm.stage_valid[s]) break;                      // end of the tile stream
     ptx::mbar_wait(&sm.a_free[b], ((i >> 1) & 1) ^ 1);
     ptx::tc_fence_after_sync();
     const uint32_t stage_addr = ptx::smem_u32(sm.stage[s]);
@@ -356,7 +358,8 @@ __device__ __forceinline__ void last_cta_tail(const SuffstatsTail& tp, double* p
       const double log_2pi = 1.8378770664093454835606594728112;
       tp.loglik[0] = total - 0.5 * n * d * log_2pi + 0.5 * n * tp.e_logdet - 0.5 * n * tp.e_mu_l_mu;
     }
-    *tp.ticket = 0u;                                       // the next launch is stream-ordered after this one
+    *tp.ticket = 0u;                                       // the next launch touches these after its griddepcontrol.wait
+    if (tp.tile_counter != nullptr) *tp.tile_counter = 0u;  // every CTA of this launch has finished claiming
     if (tp.world > 1) *tp.epoch_dev = epoch;
   }
   BB_TL(7);
@@ -372,9 +375,6 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t tile_begin = n_tiles * blockIdx.x / gridDim.x;
-  const int64_t tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
-  const int my_tiles = static_cast<int>(tile_end - tile_begin);
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -388,6 +388,7 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
         ptx::mbar_init(&sm.acc_full[b], 1);
         ptx::mbar_init(&sm.acc_empty[b], kEpiWarps);
       }
+      ptx::mbar_init(&sm.done, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -403,28 +404,54 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
 
   if (warp == kTmaWarp) {
     // ---------------- TMA producer ----------------
+    // Tiles are handed out dynamically: claims of kClaimTiles consecutive tiles from a device-wide counter
+    // (the next claim is requested before the current one is issued, so its latency is hidden).  A CTA that
+    // starts late -- the one whose SM ran the previous launch's tail, see the PDL note at the launch -- simply
+    // takes fewer claims, and the CTAs end within one claim of each other.  tile_counter == nullptr: the
+    // static partition (contiguous range per CTA).
     if (ptx::elect_one()) {
-      for (int i = 0; i < my_tiles; ++i) {
+      int i = 0;
+      auto issue = [&](int64_t tile) {
         const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
-        ptx::mbar_wait(&sm.empty[s], ph ^ 1);
+        ptx::mbar_wait(&sm.empty[s], ((i / kStages) & 1) ^ 1);
+        sm.stage_valid[s] = 1;
         ptx::mbar_arrive_expect_tx(&sm.full[s], kStageBytes);
-        const int32_t row0 = static_cast<int32_t>((tile_begin + i) * kTileRows);
+        const int32_t row0 = static_cast<int32_t>(tile * kTileRows);
         ptx::tma_load_2d(sm.stage[s], &x_map, &sm.full[s], 0, row0);
         ptx::tma_load_2d(sm.stage[s] + kHalfBytes, &x_map, &sm.full[s], kBoxCols, row0);
+        ++i;
+      };
+      if (tail.tile_counter != nullptr) {
+        int64_t next = atomicAdd(tail.tile_counter, static_cast<unsigned int>(kClaimTiles));
+        while (next < n_tiles) {
+          const int64_t first = next;
+          next = atomicAdd(tail.tile_counter, static_cast<unsigned int>(kClaimTiles));
+          const int64_t last = first + kClaimTiles < n_tiles ? first + kClaimTiles : n_tiles;
+          for (int64_t tile = first; tile < last; ++tile) issue(tile);
+        }
+      } else {
+        const int64_t tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+        for (int64_t tile = n_tiles * blockIdx.x / gridDim.x; tile < tile_end; ++tile) issue(tile);
       }
+      // end marker: a stage without a tile
+      const int s = i % kStages;
+      ptx::mbar_wait(&sm.empty[s], ((i / kStages) & 1) ^ 1);
+      sm.stage_valid[s] = 0;
+      ptx::mbar_arrive(&sm.full[s]);
     }
   } else if (warp == kMmaWarp) {
     // ---------------- MMA issuer ----------------
     if (ptx::elect_one()) {
-      for (int i = 0; i < my_tiles; ++i) {
+      int i = 0;
+      for (;; ++i) {
         const int s = i % kStages;
         const int b = i & 1;
         const int chunk = i / kFlushTiles;
         const int ab = chunk & 1;
         const bool first_in_chunk = (i % kFlushTiles) == 0;
-        if (first_in_chunk) ptx::mbar_wait(&sm.acc_empty[ab], ((chunk >> 1) & 1) ^ 1);
         ptx::mbar_wait(&sm.full[s], (i / kStages) & 1);
+        if (!sm.stage_valid[s]) break;                    // end of the tile stream: i tiles in total
+        if (first_in_chunk) ptx::mbar_wait(&sm.acc_empty[ab], ((chunk >> 1) & 1) ^ 1);
         ptx::mbar_wait(&sm.a_ready[b], (i >> 1) & 1);
         ptx::tc_fence_after_sync();
         const uint32_t stage_addr = ptx::smem_u32(sm.stage[s]);
@@ -442,17 +469,19 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
         }
         ptx::mma_commit(&sm.empty[s]);
         ptx::mma_commit(&sm.a_free[b]);
-        if ((i % kFlushTiles) == kFlushTiles - 1 || i == my_tiles - 1)
-          ptx::mma_commit(&sm.acc_full[ab]);
+        if ((i % kFlushTiles) == kFlushTiles - 1) ptx::mma_commit(&sm.acc_full[ab]);
       }
+      if ((i % kFlushTiles) != 0) ptx::mma_commit(&sm.acc_full[(i / kFlushTiles) & 1]);     // the partial last chunk
+      sm.total_tiles = i;
+      ptx::mbar_arrive(&sm.done);                         // release: the epilogue warps read total_tiles after it
     }
   } else if (warp < kSplitWarps) {
     // ---------------- split warps: A = [hi ; lo] into TMEM, and Sigma x ----------------
     // Warp w owns TMEM lanes [32 (w&3), +32): quadrants 0,1 hold hi of features 0-31 / 32-63,
     // quadrants 2,3 hold lo.  The two warps sharing a quadrant take rows 0-63 / 64-127 of a tile.
     const int q = warp & 3;
-    if (q < 2) split_warp_loop<false>(sm, tmem, q, warp >> 2, lane, my_tiles);
-    else split_warp_loop<true>(sm, tmem, q, warp >> 2, lane, my_tiles);
+    if (q < 2) split_warp_loop<false>(sm, tmem, q, warp >> 2, lane);
+    else split_warp_loop<true>(sm, tmem, q, warp >> 2, lane);
   } else {
     // ---------------- epilogue warps: TMEM fp32 chunks -> float64 registers ----------------
     const int q = warp & 3;
@@ -461,10 +490,17 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
     double acc[kCols];
 #pragma unroll
     for (int c = 0; c < kCols; ++c) acc[c] = 0.0;
-    const int n_chunks = (my_tiles + kFlushTiles - 1) / kFlushTiles;
-    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    // the number of chunks is known only when the tile stream ends (`done`): wait for the next chunk OR the end
+    int n_chunks = 0x7fffffff;
+    for (int chunk = 0;; ++chunk) {
       const int ab = chunk & 1;
-      BB_SUFFSTATS_EPI_WAIT(&sm.acc_full[ab], (chunk >> 1) & 1);
+      bool ready = false;
+      while (!(ready = ptx::mbar_try_wait(&sm.acc_full[ab], (chunk >> 1) & 1))) {
+        if (n_chunks == 0x7fffffff && ptx::mbar_try_wait(&sm.done, 0))
+          n_chunks = (sm.total_tiles + kFlushTiles - 1) / kFlushTiles;
+        if (chunk >= n_chunks) break;
+      }
+      if (!ready) break;
       ptx::tc_fence_after_sync();
       const uint32_t d_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + kTmemAcc + ab * kFeat +
                               chalf * kCols;
@@ -494,6 +530,12 @@ suffstats_tc_kernel(const __grid_constant__ CUtensorMap x_map, int64_t n_tiles,
   __syncthreads();
   BB_TL(2);
   if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, kTmemCols);
+  // Programmatic dependent launch: everything above reads only X and this launch's own tile counter, so it may
+  // overlap the previous launch's tail.  The accumulator block, the ticket and the outputs are shared with the
+  // previous launch: wait for it to complete (and its memory to be visible) here, then let the NEXT launch start
+  // as CTAs of this one exit.  (Without the launch attribute both instructions are no-ops.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // this CTA's partial statistics, S2[r][c] = hi^T hi [r][c] + lo^T hi [r][c] + lo^T hi [c][r] (upper triangle)
   // and S1, added into the accumulator block at L2.  The start is rotated per CTA so that the 148 CTAs, which
   // finish together, do not all hit the same address at the same moment.
@@ -572,6 +614,15 @@ bool suffstats_tc_supported(int64_t n, int d, const void* x) {
 }
 
 namespace {
+// developer switches (read once): BB_SUFFSTATS_DYNAMIC=0 static tile partition, BB_SUFFSTATS_PDL=0 plain launches
+bool dynamic_tiles() {
+  static const bool on = !(getenv("BB_SUFFSTATS_DYNAMIC") && atoi(getenv("BB_SUFFSTATS_DYNAMIC")) == 0);
+  return on;
+}
+bool pdl_enabled() {
+  static const bool on = !(getenv("BB_SUFFSTATS_PDL") && atoi(getenv("BB_SUFFSTATS_PDL")) == 0);
+  return on;
+}
 int grid_for(int64_t n) {
   const int64_t tiles = (n + kTileRows - 1) / kTileRows;
   int64_t grid = device_sm_count();
@@ -584,7 +635,7 @@ int grid_for(int64_t n) {
 // the accumulator block + the ticket word (caller-workspace entry points; a bb_gaussian_pass handle owns
 // persistent ones)
 int64_t suffstats_tc_workspace(int64_t) {
-  return kAccumDoubles * static_cast<int64_t>(sizeof(double)) + 64 + 512;
+  return kAccumDoubles * static_cast<int64_t>(sizeof(double)) + 64 + 512;     // block, ticket, tile counter
 }
 
 // ONE launch: statistics, cross-CTA reduction, (world > 1) cross-GPU exchange, expected
@@ -638,15 +689,34 @@ int launch_suffstats_tc_fused(const float* x, int64_t n, int d, void* workspace,
     double* block = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
     tail.accum = block;
     tail.ticket = reinterpret_cast<unsigned int*>(block + kAccumDoubles);
-    BB_CUDA_OK(cudaMemsetAsync(block, 0, kAccumDoubles * sizeof(double) + sizeof(unsigned int), stream));
+    tail.tile_counter = dynamic_tiles() ? tail.ticket + 1 : nullptr;
+    tail.pdl = 0;
+    BB_CUDA_OK(cudaMemsetAsync(block, 0, kAccumDoubles * sizeof(double) + 2 * sizeof(unsigned int), stream));
   }
+  if (!dynamic_tiles()) tail.tile_counter = nullptr;
   tail.d = d;
   if (tail.world < 1) tail.world = 1;
 
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout)) + 1024;
   static SmemOptIn smem_opt_in_0;
   BB_CUDA_OK(smem_opt_in_0.ensure(suffstats_tc_kernel, smem_bytes));
-  suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, tail);
+  if (tail.pdl && pdl_enabled()) {
+    // back-to-back passes of one handle: the next launch's streaming overlaps this launch's single-CTA tail
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BB_CUDA_OK(cudaLaunchKernelEx(&cfg, suffstats_tc_kernel, map, tiles, tail));
+  } else {
+    suffstats_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map, tiles, tail);
+  }
   BB_CHECK_LAUNCH("suffstats_tc_kernel");
   return BB_OK;
 }

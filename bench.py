@@ -6,8 +6,8 @@ Workload: BASELINE config[1] -- multivariate Gaussian-Wishart mean-field pass ov
 "sharded over N at 1-8 B200": the 16 Mi rows are the WHOLE job, cut into contiguous shards with
 ``parallel.shard_bounds`` (strong scaling; each rank's shard is resident in its HBM).  One step =
 ONE kernel launch per rank (``bb_gaussian_pass_run``): {count, sum x, sum x x^T} of the shard on tcgen05,
-the cross-CTA reduction, the exchange of the 33 KB of partial statistics over NVLink peer memory and the
-expected log-likelihood (ELBO term) of the reduced statistics.  Weak scaling (16 Mi rows PER GPU) is
+the cross-CTA reduction (L2 float64 reductions), the exchange of the 33 KB of partial statistics over NVLink
+peer memory and the expected log-likelihood (ELBO term) of the reduced statistics (both in the last CTA).  Weak scaling (16 Mi rows PER GPU) is
 measured in the same run and reported under the extra key ``weak``.
 
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
@@ -386,8 +386,9 @@ def run_ours(args):
             sys.stderr.write("bench: one-launch pass disagreed with NCCL (%r vs %r); using NCCL\n" % (got, want))
             gpass = None
     if distributed:
-        collective = ("fused into the statistics kernel: per-slice push of %d float64 into the peers' receive buffers "
-                      "over NVLink + flags (1 launch per rank per step; checked against the NCCL all-reduce at start-up)"
+        collective = ("fused into the statistics kernel: its last CTA pushes the rank's %d float64 into the peers' "
+                      "receive buffers over NVLink (plain peer stores + one flag per peer) and sums the world's slots in "
+                      "rank order (1 launch per rank per step; checked against the NCCL all-reduce at start-up)"
                       % layout.numel) if gpass is not None else "one NCCL all-reduce of %d float64 per step" % layout.numel
     step = step_pass if gpass is not None else step_nccl
     launches_per_step = 1 if gpass is not None else (3 if distributed else 2)
@@ -511,7 +512,11 @@ def run_ours(args):
                            "arithmetic": "error-compensated TF32 (hi/lo split, one MMA) on tcgen05; fp32 TMEM "
                                          "accumulate drained to f64 every 512 rows",
                            "collective": collective, "cuda_graph": use_graph,
-                           "launches_per_step": launches_per_step},
+                           "launches_per_step": launches_per_step,
+                           "scheduling": "tiles claimed dynamically (512-row claims from a device counter); "
+                                         "back-to-back passes are launched with programmatic stream serialization, so "
+                                         "the single-CTA tail (reduction gather, exchange, ELBO term) of step i overlaps "
+                                         "the streaming of step i+1" if gpass is not None else "static"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(n_strong),
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured'
