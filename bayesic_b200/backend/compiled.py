@@ -62,6 +62,7 @@ class CompiledPlan(object):
         self._workspace = _Workspace()
         self._bound = {}           # slot -> device tensor of an ndarray literal
         self._shape_cache = {}
+        self._host_cache = {}      # input signature -> _HostCall (persistent buffers + captured CUDA graph) | False
         self.last_launches = 0
 
     # ---- native handle ---------------------------------------------------
@@ -125,6 +126,51 @@ class CompiledPlan(object):
         keep.append(t)
         return t.data_ptr(), tuple(t.shape), None
 
+    # ---- host-in / host-out calls: persistent buffers + one CUDA-graph launch -------------------
+    def _host_signature(self, inputs):
+        """Hashable (shapes, scalar values) of a call whose inputs are all host values, or None."""
+        import torch
+        sig = []
+        for name in self.lowered.input_names:
+            if name == '':
+                continue
+            value = inputs[name]
+            dtype, ndim = self.input_types[name]
+            if isinstance(value, torch.Tensor):
+                if value.is_cuda or value.dtype != torch.float32 or not value.is_contiguous() or value.dim() != ndim:
+                    return None
+                sig.append((name, tuple(value.shape)) if ndim else (name, float(value)))
+                continue
+            arr = np.asarray(value, dtype=np.dtype(dtype))
+            if arr.ndim != ndim:
+                return None                      # the general path raises the TypeError
+            if arr.dtype.kind in 'iu' and arr.size and int(np.abs(arr).max()) > (1 << 24):
+                return None                      # ... and the ValueError
+            sig.append((name, arr.shape) if ndim else (name, float(arr)))
+        return tuple(sig)
+
+    def _host_call(self, sig, inputs, device):
+        """The reference's own calling convention -- numpy in, numpy out (algebra.py:50-58) -- for a repeated input
+        signature: inputs go through persistent pinned staging into persistent device buffers, the plan's
+        kernels and the device -> host copies of the results are ONE captured CUDA graph, and the call ends
+        with a single stream synchronisation.  (Plain path: two pageable copies, one launch per plan node, one
+        blocking read per output.)"""
+        import torch
+        rec = self._host_cache.get(sig)
+        if rec is False:
+            return None
+        stream = torch.cuda.current_stream(device)
+        if rec is None:
+            if len(self._host_cache) >= 16:
+                return None
+            try:
+                rec = _HostCall(self, sig, inputs, device)
+            except Exception:                    # noqa: BLE001 -- anything unusual: the general path handles (or reports) it
+                self._host_cache[sig] = False
+                return None
+            self._host_cache[sig] = rec
+        return rec.run(inputs, stream)
+
     def __call__(self, **inputs):
         import torch
         lib = L.load()
@@ -133,6 +179,13 @@ class CompiledPlan(object):
         missing = [n for n in self.input_types if n not in inputs]
         if missing:
             raise KeyError(missing[0])
+        if not on_device and not torch.cuda.is_current_stream_capturing():
+            sig = self._host_signature(inputs)
+            if sig is not None:
+                with torch.cuda.device(device):
+                    results = self._host_call(sig, inputs, device)
+                if results is not None:
+                    return results
         keep = []
         n_slots = len(self.lowered.input_names)
         args = (L.TensorArg * max(n_slots, 1))()
@@ -194,6 +247,127 @@ class CompiledPlan(object):
                 else:
                     host = outs[j].cpu().numpy()
                     results.append(np.rint(host).astype(np.int64) if as_int else host)
+        return results
+
+
+class _HostCall(object):
+    """Persistent state of ``CompiledPlan._host_call`` for one input signature."""
+
+    def __init__(self, plan, sig, inputs, device):
+        import torch
+        lib = L.load()
+        self.plan = plan
+        lowered = plan.lowered
+        n_slots = len(lowered.input_names)
+        self.args = (L.TensorArg * max(n_slots, 1))()
+        self.stage, self.dev_in = {}, {}
+        for slot, name in enumerate(lowered.input_names):
+            arg = self.args[slot]
+            if name == '':
+                if slot not in plan._bound or plan._bound[slot].device != device:
+                    plan._bound[slot] = torch.from_numpy(lowered.bound_constants[slot]).to(device)
+                t = plan._bound[slot]
+                shp, host = tuple(t.shape), None
+            else:
+                entry = dict(sig)[name]
+                if plan.input_types[name][1] == 0:
+                    shp, host, t = (), float(entry), None
+                else:
+                    shp, host = tuple(entry), None
+                    self.stage[slot] = torch.empty(shp, dtype=torch.float32).pin_memory()
+                    t = self.dev_in[slot] = torch.empty(shp, dtype=torch.float32, device=device)
+            arg.ndim = len(shp)
+            for i, e in enumerate(shp):
+                arg.shape[i] = e
+            if host is not None:
+                arg.is_host_scalar, arg.host_value, arg.data = 1, host, None
+            else:
+                arg.is_host_scalar, arg.host_value, arg.data = 0, 0.0, t.data_ptr()
+        n_out = len(lowered.outputs)
+        infos = (L.ResultInfo * n_out)()
+        ws_bytes = ctypes.c_int64(0)
+        L.check(lib.bb_plan_infer(plan._native(), self.args, n_slots, infos, ctypes.byref(ws_bytes)), 'bb_plan_infer')
+        self.infos = [(i.ndim, bool(i.is_host_scalar), tuple(i.shape[:i.ndim]), i.host_value) for i in infos]
+        self.outs, self.host_outs = [], []
+        self.out_ptrs = (ctypes.c_void_p * n_out)()
+        for j, (ndim, is_host, shp, _) in enumerate(self.infos):
+            if is_host:
+                self.outs.append(None)
+                self.host_outs.append(None)
+                self.out_ptrs[j] = None
+            else:
+                t = torch.empty(shp, dtype=torch.float32, device=device)
+                self.outs.append(t)
+                self.host_outs.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+                self.out_ptrs[j] = t.data_ptr()
+        self.ws = torch.empty(max(int(ws_bytes.value), 256), dtype=torch.uint8, device=device)
+        self.n_slots = n_slots
+
+        def body(stream, with_h2d):
+            if with_h2d:
+                for slot, dev_t in self.dev_in.items():
+                    dev_t.copy_(self.stage[slot], non_blocking=True)
+            L.check(lib.bb_plan_execute(plan._native(), self.args, n_slots, self.out_ptrs, self.ws.data_ptr(),
+                                        self.ws.numel(), ctypes.c_void_p(stream.cuda_stream)), 'bb_plan_execute')
+            for dev_t, host_t in zip(self.outs, self.host_outs):
+                if dev_t is not None:
+                    host_t.copy_(dev_t, non_blocking=True)
+
+        # warm-up outside capture (kernel attributes, lazy module loading), then capture
+        for slot, t in self.stage.items():
+            t.zero_()
+        self.stage_np = {slot: t.numpy() for slot, t in self.stage.items()}
+        self._body, self._side = body, torch.cuda.Stream(device)
+        self._side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(self._side):
+            body(self._side, True)
+        self._side.synchronize()
+        count = ctypes.c_int32(0)
+        lib.bb_plan_last_launch_count(plan._native(), ctypes.byref(count))
+        self.launches = count.value
+        self.has_device_work = self.launches > 0 or any(t is not None for t in self.outs)
+        # two captures of the same work: with the staging -> device copies inside (numpy inputs: the whole call
+        # is one graph launch), and without (a caller's page-locked tensor is copied from directly, before it)
+        self.graphs = {True: None, False: None}
+
+    def _graph(self, with_h2d):
+        import torch
+        if self.graphs[with_h2d] is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._side):
+                self._body(self._side, with_h2d)
+            self.graphs[with_h2d] = g
+        return self.graphs[with_h2d]
+
+    def run(self, inputs, stream):
+        import torch
+        lowered = self.plan.lowered
+        values = {slot: inputs[lowered.input_names[slot]] for slot in self.dev_in}
+        caller_pinned = any(isinstance(v, torch.Tensor) and v.is_pinned() for v in values.values())
+        for slot, value in values.items():
+            if caller_pinned and isinstance(value, torch.Tensor) and value.is_pinned():
+                self.dev_in[slot].copy_(value, non_blocking=True)     # page-locked by the caller: DMA straight from it
+                continue
+            stage = self.stage[slot]
+            if isinstance(value, torch.Tensor):
+                stage.copy_(value)
+            else:
+                np.copyto(self.stage_np[slot], value, casting='unsafe')
+            if caller_pinned:
+                self.dev_in[slot].copy_(stage, non_blocking=True)
+        if self.has_device_work:
+            self._graph(not caller_pinned).replay()
+            stream.synchronize()
+        self.plan.last_launches = self.launches
+        results = []
+        for j, (ndim, is_host, shp, host_value) in enumerate(self.infos):
+            as_int = lowered.integer_result[j]
+            if is_host:
+                value = np.int64(round(host_value)) if as_int else np.float32(host_value)
+                results.append(np.full(shp, value) if ndim else value)
+            else:
+                host = self.host_outs[j].numpy().copy()
+                results.append(np.rint(host).astype(np.int64) if as_int else host)
         return results
 
 

@@ -283,7 +283,7 @@ BB_API int64_t bb_suffstats_regression_workspace(int64_t n, int32_t d) {
   int64_t need = align_up((static_cast<int64_t>(d) * d + d + 1) * 4, 256) +
                  std::max(gemm_workspace_bytes(d, d, n, 1),
                           std::max(gemm_workspace_bytes(d, 1, n, 1), gemm_workspace_bytes(1, 1, n, 1))) + 1024;
-  if (d >= 256 && d % 256 == 0 && d <= 4096 && n > 0) need = std::max(need, gram_tc_workspace(n, d) + 256);
+  if (d > 64 && d % 4 == 0 && d <= 4096 && n > 0) need = std::max(need, gram_tc_workspace(n, d) + 256);
   return need;
 }
 

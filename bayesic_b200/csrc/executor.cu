@@ -518,7 +518,7 @@ int run_node(Exec& ex, int idx) {
           BB_TRY(ex.alloc_scratch(d * d * 8, &s2));
           BB_TRY(ex.alloc_scratch(ws_bytes, &ws));
         }
-        const bool gram_shape = d >= 256 && d % 256 == 0 && d <= 4096 && n > 0;   // tcgen05 CTA-pair kernel
+        const bool gram_shape = d > 64 && d % 4 == 0 && d <= 4096 && n > 0;   // tcgen05 CTA-pair kernel (zero-padded to 256 k)
         if (gram_shape) {
           ws_bytes = gram_tc_workspace(n, static_cast<int>(d));
           BB_TRY(ex.alloc_scratch(d * d * 8, &s2));

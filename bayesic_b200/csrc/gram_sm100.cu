@@ -1,4 +1,5 @@
-// Large-D Gram statistics on tcgen05 CTA pairs (D % 256 == 0):
+// Large-D Gram statistics on tcgen05 CTA pairs (D % 4 == 0, D > 64; the feature axis is padded with zeros to a
+// multiple of 256 inside the converter -- nothing is padded in memory):
 //     XtX[d,e] = sum_n x_nd x_ne        Xty[d] = sum_n x_nd y_n        yty = sum_n y_n^2
 // over X[n, d] float32 row-major and (optionally) y[n].
 //
@@ -227,6 +228,11 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
   int64_t row0 = ca.row_begin + static_cast<int64_t>(group) * kStageRows + wi * kRowsPerWarp;
   const float* pa = ca.x + row0 * d + ca.feat_a + lane * 4;
   const float* pb = ca.x + row0 * d + ca.feat_b + lane * 4;
+  // features at or beyond d (the zero padding up to a multiple of 256) are never loaded; d % 4 == 0, so a
+  // lane's four features are all inside or all outside
+  const bool a_in = ca.feat_a + lane * 4 < ca.d;
+  const bool b_in = ca.feat_b + lane * 4 < ca.d;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* py = ca.y + row0;
   const int64_t step = static_cast<int64_t>(kConvGroups) * kStageRows * d;
   const bool do_yty = kXty && ca.want_yty && lane == 0;
@@ -237,16 +243,16 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
     if (row0 + kRowsPerWarp <= ca.n) {          // whole group of rows in range: no per-row checks
 #pragma unroll
       for (int j = 0; j < kRowsPerWarp; ++j) {
-        ra[j] = ldg_f4(pa + j * d);
-        if (!kAlias) rb[j] = ldg_f4(pb + j * d);
+        ra[j] = a_in ? ldg_f4(pa + j * d) : zero4;
+        if (!kAlias) rb[j] = b_in ? ldg_f4(pb + j * d) : zero4;
         if (kXty) ry[j] = __ldg(py + j);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < kRowsPerWarp; ++j) {
         const bool ok = row0 + j < ca.n;
-        ra[j] = ok ? ldg_f4(pa + j * d) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!kAlias) rb[j] = ok ? ldg_f4(pb + j * d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ra[j] = ok && a_in ? ldg_f4(pa + j * d) : zero4;
+        if (!kAlias) rb[j] = ok && b_in ? ldg_f4(pb + j * d) : zero4;
         if (kXty) ry[j] = ok ? __ldg(py + j) : 0.f;
       }
     }
@@ -255,8 +261,8 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
     if (ca.prefetch_iters > 0) {
       const int64_t prow = row0 + static_cast<int64_t>(ca.prefetch_iters) * kConvGroups * kStageRows + (lane >> 3);
       if (prow < ca.row_end && (!kAlias || (lane & 4) == 0)) {
-        const float* base = (lane & 4) ? ca.x + prow * d + ca.feat_b : ca.x + prow * d + ca.feat_a;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (lane & 3) * 32));
+        const int feat = ((lane & 4) ? ca.feat_b : ca.feat_a) + (lane & 3) * 32;
+        if (feat < ca.d) asm volatile("prefetch.global.L2 [%0];" ::"l"(ca.x + prow * d + feat));
       }
     }
     row0 += kConvGroups * kStageRows;
@@ -337,7 +343,7 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
   // upper-triangle block index -> (i, j), row-major over i <= j
   int2 ij;
   {
-    const int nb = d / kBlock;
+    const int nb = (d + kBlock - 1) / kBlock;
     int i = 0, rem = blk;
     while (rem >= nb - i) {
       rem -= nb - i;
@@ -465,7 +471,7 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (y != nullptr && diag) {
-    if (threadIdx.x < kHalf)
+    if (threadIdx.x < kHalf && feat_a + static_cast<int>(threadIdx.x) < d)
       partial_xty[static_cast<int64_t>(split) * d + feat_a + threadIdx.x] = sm.xty[threadIdx.x];
     if (blk == 0 && rank == 0 && threadIdx.x == 0) partial_yty[split] = sm.yty;
   }
@@ -480,7 +486,7 @@ gram_finalize_kernel(const float* __restrict__ partial, const double* __restrict
                      const double* __restrict__ partial_yty, int d, int n_blocks, int n_splits,
                      double* __restrict__ xtx, double* __restrict__ xty, double* __restrict__ yty) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int nb = d / kBlock;
+  const int nb = (d + kBlock - 1) / kBlock;
   if (idx < static_cast<int64_t>(d) * d) {
     const int row = static_cast<int>(idx / d), col = static_cast<int>(idx % d);
     const int r = row < col ? row : col, c = row < col ? col : row;
@@ -512,7 +518,7 @@ struct GramGrid {
 
 GramGrid plan_gram(int64_t n, int d) {
   GramGrid g;
-  g.nb = d / kBlock;
+  g.nb = (d + kBlock - 1) / kBlock;
   g.n_blocks = g.nb * (g.nb + 1) / 2;
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
@@ -526,8 +532,7 @@ GramGrid plan_gram(int64_t n, int d) {
 }  // namespace
 
 bool gram_tc_supported(int64_t n, int d, const void* x) {
-  return n > 0 && d >= kBlock && d % kBlock == 0 && d <= 4096 &&
-         reinterpret_cast<uintptr_t>(x) % 16 == 0;
+  return n > 0 && d > 64 && d % 4 == 0 && d <= 4096 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
 }
 
 int64_t gram_tc_workspace(int64_t n, int d) {

@@ -68,7 +68,7 @@ int launch_suffstats_tc_loglik(const float* x, int64_t n, int d, double* s1, dou
 int launch_suffstats_tc(const float* x, int64_t n, int d, double* s1, double* s2, void* workspace,
                         int64_t workspace_bytes, cudaStream_t stream);
 
-// gram_sm100.cu: X^T X (+ X^T y, y^T y) for d % 256 == 0 on tcgen05 CTA pairs (BF16x3)
+// gram_sm100.cu: X^T X (+ X^T y, y^T y) for d % 4 == 0, 64 < d <= 4096 on tcgen05 CTA pairs (BF16x3)
 bool gram_tc_supported(int64_t n, int d, const void* x);
 int64_t gram_tc_workspace(int64_t n, int d);
 int launch_gram_tc(const float* x, const float* y, int64_t n, int d, double* xtx, double* xty,

@@ -120,7 +120,7 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
 // (its contraction with R is Nk; at D = 64 the 38 blocks fill 10 tiles of N = 256 that are
 // issued in full anyway, so Nk costs no extra MMA).
 struct Geometry {
-  int d, k, n_groups, n_pair, n_blocks, n_tiles;
+  int d, k, ldr, n_groups, n_pair, n_blocks, n_tiles;      // ldr: row stride of R (>= k: a launch may cover a slice of the components)
   int base, rem;      // tile t holds base + (t < rem) blocks, starting at block t * base + min(t, rem)
 };
 
@@ -245,10 +245,10 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     const float km0 = 4 * lane < g.k ? 1.f : 0.f, km1 = 4 * lane + 128 < g.k ? 1.f : 0.f;
     const bool k_partial = g.k < kMaxK;                  // some lanes hold components past k
     // walking pointers to this warp's first row of the next stage it converts
-    const float* rp = r + row0 * g.k;
+    const float* rp = r + row0 * g.ldr;
     const float* xp = x + row0 * g.d;
     const float* lp = kFromLogits ? lse + row0 : nullptr;
-    const int64_t r_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.k;
+    const int64_t r_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.ldr;
     const int64_t x_step = static_cast<int64_t>(kConvGroups) * kStageRows * g.d;
     float4 rr[2][2];
     float row_lse[2] = {0.f, 0.f};   // logits mode: r = exp(logit - lse[row])
@@ -267,7 +267,7 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const float* rrow = rp + jj[j] * g.k;
+        const float* rrow = rp + jj[j] * g.ldr;
         const float* xrow = xp + jj[j] * g.d;
         rr[j][0] = ldg_f4(rrow + kc0);
         rr[j][1] = ldg_f4(rrow + kc1);
@@ -454,6 +454,7 @@ PairsPlan plan_pairs(int64_t n, int d, int k) {
   PairsPlan p;
   p.g.d = d;
   p.g.k = k;
+  p.g.ldr = k;
   p.g.n_groups = d / 8;
   p.g.n_pair = p.g.n_groups * (p.g.n_groups + 1) / 2;
   p.g.n_blocks = p.g.n_pair + 2;      // pair blocks, the linear block, the ones block (Nk)
@@ -471,12 +472,13 @@ PairsPlan plan_pairs(int64_t n, int d, int k) {
 }  // namespace
 
 bool weighted_pairs_supported(int64_t n, int d, int k, const void* x, const void* r) {
-  return n > 0 && d >= 8 && d <= 64 && d % 8 == 0 && k >= 4 && k <= kMaxK && k % 4 == 0 &&
+  // more than 256 components: one launch per slice of 256 (the kernel holds M = 256 in TMEM)
+  return n > 0 && d >= 8 && d <= 64 && d % 8 == 0 && k >= 4 && k <= 16 * kMaxK && k % 4 == 0 &&
          reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(r) % 16 == 0;
 }
 
 int64_t weighted_pairs_workspace(int64_t n, int d, int k) {
-  const PairsPlan p = plan_pairs(n, d, k);
+  const PairsPlan p = plan_pairs(n, d, k < kMaxK ? k : kMaxK);
   return static_cast<int64_t>(p.grid) * 2 * kTileCols * 128 * static_cast<int64_t>(sizeof(float)) +
          static_cast<int64_t>(p.n_splits) * k * static_cast<int64_t>(sizeof(double)) + 1024;
 }
@@ -494,28 +496,32 @@ int launch_weighted_pairs(const float* x, const float* r, const float* lse, int6
               static_cast<long long>(weighted_pairs_workspace(n, d, k)));
     return BB_ERR_WORKSPACE;
   }
-  const PairsPlan p = plan_pairs(n, d, k);
-  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
-  float* partial = reinterpret_cast<float*>(ws);
-  ws += static_cast<int64_t>(p.grid) * 2 * kTileCols * 128 * sizeof(float);
-  double* partial_nk = reinterpret_cast<double*>(ws);
+  uint8_t* ws0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
   static SmemOptIn smem_opt_in_0;
   BB_CUDA_OK(smem_opt_in_0.ensure(weighted_pairs_kernel<false>, smem_bytes));
   static SmemOptIn smem_opt_in_1;
   BB_CUDA_OK(smem_opt_in_1.ensure(weighted_pairs_kernel<true>, smem_bytes));
   static const int prefetch_iters = getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) : 0;
-  if (lse != nullptr)
-    weighted_pairs_kernel<true><<<p.grid, kThreads, smem_bytes, stream>>>(x, r, lse, n, p.g, p.n_splits, prefetch_iters,
-                                                                          partial, partial_nk);
-  else
-    weighted_pairs_kernel<false><<<p.grid, kThreads, smem_bytes, stream>>>(x, r, lse, n, p.g, p.n_splits, prefetch_iters,
-                                                                           partial, partial_nk);
-  BB_CHECK_LAUNCH("weighted_pairs_kernel");
-  const int64_t total = static_cast<int64_t>(k) * d * d + static_cast<int64_t>(k) * d + k;
-  weighted_pairs_finalize_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
-      partial, partial_nk, p.g, p.n_splits, nk, sum_rx, sum_rxx);
-  BB_CHECK_LAUNCH("weighted_pairs_finalize_kernel");
+  for (int k0 = 0; k0 < k; k0 += kMaxK) {                 // slices of at most 256 components (stream-ordered)
+    const int kc = k - k0 < kMaxK ? k - k0 : kMaxK;
+    PairsPlan p = plan_pairs(n, d, kc);
+    p.g.ldr = k;
+    float* partial = reinterpret_cast<float*>(ws0);
+    double* partial_nk = reinterpret_cast<double*>(ws0 + static_cast<int64_t>(p.grid) * 2 * kTileCols * 128 * sizeof(float));
+    if (lse != nullptr)
+      weighted_pairs_kernel<true><<<p.grid, kThreads, smem_bytes, stream>>>(x, r + k0, lse, n, p.g, p.n_splits, prefetch_iters,
+                                                                            partial, partial_nk);
+    else
+      weighted_pairs_kernel<false><<<p.grid, kThreads, smem_bytes, stream>>>(x, r + k0, lse, n, p.g, p.n_splits, prefetch_iters,
+                                                                             partial, partial_nk);
+    BB_CHECK_LAUNCH("weighted_pairs_kernel");
+    const int64_t total = static_cast<int64_t>(kc) * d * d + static_cast<int64_t>(kc) * d + kc;
+    weighted_pairs_finalize_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
+        partial, partial_nk, p.g, p.n_splits, nk != nullptr ? nk + k0 : nullptr,
+        sum_rx != nullptr ? sum_rx + static_cast<int64_t>(k0) * d : nullptr, sum_rxx + static_cast<int64_t>(k0) * d * d);
+    BB_CHECK_LAUNCH("weighted_pairs_finalize_kernel");
+  }
   return BB_OK;
 }
 

@@ -316,7 +316,7 @@ def _reduce_into(layout, device, parts, n_local, buffer, group):
 
 def regression_suffstats_sharded(X_local, y_local, buffer=None, group=None):
     """cfg4: ``{xtx, xty, yty, count}`` of the whole minibatch from this rank's rows: local fused
-    pass (tcgen05 CTA pairs when D % 256 == 0), then one all-reduce of D^2 + D + 2 float64."""
+    pass (tcgen05 CTA pairs when D % 4 == 0, D > 64), then one all-reduce of D^2 + D + 2 float64."""
     from . import stats
     n_local, d = X_local.shape
     xtx, xty, yty = stats.regression_suffstats(X_local, y_local)

@@ -138,7 +138,7 @@ class GmmStep(object):
         shapes take the compiled einsum plan, the log-softmax kernel, a compiled ``exp`` and the generic
         weighted-statistics kernel."""
         d, k = X.shape[1], Ak.shape[0]
-        if fused and stats.mixture_logits_supported(d, k) and d % 8 == 0 and k <= 256 and k % 4 == 0:
+        if fused and stats.mixture_logits_supported(d, k) and d % 8 == 0 and k <= 4096 and k % 4 == 0:
             out = self.local_step(X, *self._whitened(Ak, bk, ck))
             if want_log_resp:
                 logits = out.pop('logits')
@@ -156,7 +156,7 @@ class LinRegSviStep(object):
     """cfg4: conjugate natural-gradient SVI for Bayesian linear regression (noise precision tau).
     The minibatch statistics {X^T X, X^T y, y^T y} -- the plans of ``dot(X.T, X)``,
     ``dot(X.T, y)``, ``dot(y, y)`` -- come from ONE fused pass over X
-    (``stats.regression_suffstats``; tcgen05 CTA pairs when D % 256 == 0), or with
+    (``stats.regression_suffstats``; tcgen05 CTA pairs when D % 4 == 0, D > 64), or with
     ``fused=False`` from one compiled multi-output plan; the natural-parameter blend and the
     expected log-likelihood are float64 parameter-space arithmetic."""
 

@@ -216,7 +216,7 @@ def weighted_suffstats(X, R):
 
 def regression_suffstats(X, y=None):
     """``(X^T X [d, d], X^T y [d], y^T y [1])`` float64 CUDA tensors in one pass over ``X[n, d]``
-    (``y`` omitted: just the Gram matrix).  ``d % 256 == 0`` runs the tcgen05 CTA-pair kernel."""
+    (``y`` omitted: just the Gram matrix).  ``d % 4 == 0``, ``64 < d <= 4096`` runs the tcgen05 CTA-pair kernel."""
     torch = _torch()
     lib = L.load()
     X = _as_device_f32(X, 2, 'X')
@@ -308,7 +308,7 @@ def logistic_reparam_stats(X, y, W):
 
 def mixture_logits_supported(d, k):
     """Shapes the tcgen05 mixture-logit kernel serves."""
-    return d in (16, 32, 48, 64) and k % 4 == 0 and k >= 4
+    return d in (16, 32, 48, 64) and k % 4 == 0 and 4 <= k <= 4096
 
 
 def mixture_logits(X, U, t, c, want_lse=True, want_sum=True, upper_triangular=False):

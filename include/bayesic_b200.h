@@ -207,7 +207,8 @@ BB_API int bb_suffstats_gaussian_loglik(const float* X, int64_t n, int32_t d, do
  *   _tensordot(y, y, [0],[0])                                  (algebra.py:527-551, 1347-1351)
  * in ONE pass over X:  xtx[d,e] = sum_n X[n,d] X[n,e];  xty[d] = sum_n X[n,d] y[n];
  * yty = sum_n y[n]^2   (float64 out, device).  y, xty, yty may all be NULL (Gram matrix only).
- * d % 256 == 0 runs the tcgen05 CTA-pair kernel (error-compensated BF16); other d use the
+ * d % 4 == 0, 64 < d <= 4096 runs the tcgen05 CTA-pair kernel (error-compensated BF16; the feature axis is
+ * zero-padded to a multiple of 256 on the fly); other d use the
  * generic contraction kernels. */
 BB_API int64_t bb_suffstats_regression_workspace(int64_t n, int32_t d);
 BB_API int bb_suffstats_regression(const float* X, const float* y, int64_t n, int32_t d,
@@ -275,7 +276,8 @@ BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int3
 /* Same statistics (same plans, algebra.py:527-765) with the responsibilities formed on the fly from the logits and their row
  * log-sum-exp (as bb_mixture_logits returns them): r[n,k] = exp(logits[n,k] - lse[n]) -- the
  * N x K responsibility matrix is never written.  tcgen05 path only: d % 8 == 0, d <= 64,
- * k % 4 == 0, k <= 256 (BB_ERR_UNSUPPORTED otherwise; normalise with bb_logsoftmax_rows and use
+ * k % 4 == 0, k <= 4096 -- more than 256 components run as slices of 256 -- (BB_ERR_UNSUPPORTED otherwise;
+ * normalise with bb_logsoftmax_rows and use
  * bb_suffstats_weighted instead). */
 BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits, const float* lse,
                                       int64_t n, int32_t d, int32_t k,

@@ -1,6 +1,8 @@
 """Summarise an `ncu --set full` report (.ncu-rep) into the handful of numbers the design notes
 quote: duration, DRAM bytes, L2 bytes, tensor-pipe activity, shared-memory wavefronts, registers,
-and the top stall sites.  Usage: python profiles/summarize_ncu.py report.ncu-rep [n_stall_rows]"""
+and the top stall sites.  Usage: python profiles/summarize_ncu.py report.ncu-rep [n_stall_rows]
+       [--traffic-json out.json --rows N]   (also write {rows, dram_bytes} of the captured launch: bench.py's
+                                             `roofline.traffic` reads profiles/suffstats_traffic.json)"""
 import csv
 import subprocess
 import sys
@@ -15,9 +17,22 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__warps_active.avg.pct_of_peak_sustained_active']
 
 
+UNIT_SCALE = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+
+
 def main():
     rep = sys.argv[1]
-    n_rows = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    argv = sys.argv[2:]
+    traffic_json = rows_arg = None
+    if '--traffic-json' in argv:
+        i = argv.index('--traffic-json')
+        traffic_json = argv[i + 1]
+        del argv[i:i + 2]
+    if '--rows' in argv:
+        i = argv.index('--rows')
+        rows_arg = int(argv[i + 1])
+        del argv[i:i + 2]
+    n_rows = int(argv[0]) if argv else 12
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -27,6 +42,16 @@ def main():
         if key in hdr:
             i = hdr.index(key)
             print('  %-64s %s %s' % (key, vals[i], units[i]))
+    if traffic_json:
+        import json
+        total_bytes = 0.0
+        for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(key)
+            total_bytes += float(vals[i].replace(',', '')) * UNIT_SCALE[units[i]]
+        with open(traffic_json, 'w') as fh:
+            json.dump({'rows': rows_arg, 'dram_bytes': int(total_bytes), 'report': rep,
+                       'kernel': vals[hdr.index('Kernel Name')][:60]}, fh)
+            fh.write('\n')
     src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     h, data = rows[1], rows[2:]

@@ -25,7 +25,9 @@ def main():
     print('value %.6e  oracle %.6e  rel err %.2e  launches %d' % (got, want, abs(got - want) / abs(want),
                                                               fn.plan.last_launches))
     Xd, Ld = torch.from_numpy(Xh).cuda(), torch.from_numpy(Lh).cuda()
-    for label, kw in (('host numpy in/out', dict(X=Xh, L=Lh)), ('device resident', dict(X=Xd, L=Ld))):
+    Xp = torch.from_numpy(Xh).pin_memory()
+    for label, kw in (('host numpy in/out', dict(X=Xh, L=Lh)), ('host, X page-locked', dict(X=Xp, L=Lh)),
+                      ('device resident', dict(X=Xd, L=Ld))):
         for _ in range(20):
             out = fn(**kw)
         torch.cuda.synchronize()

@@ -74,12 +74,13 @@ def test_cfg4_linreg_svi_step():
     t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
     got = P.LinRegSviStep()(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), t(eta1), t(eta2), tau,
                             n_total, rho, t(eta1_prior), t(eta2_prior))
-    _close(got['xtx'], want['xtx'], scale_atol=1e-5)
+    # D = 128 runs on the tcgen05 CTA-pair kernel too (feature axis zero-padded to 256): BF16x3 class of error
+    _close(got['xtx'], want['xtx'], scale_atol=3e-5)
     _close(got['xty'], want['xty'], scale_atol=1e-5)
     _close(got['yty'], want['yty'])
     _close(got['eta1'], want['eta1'], scale_atol=1e-5)
-    _close(got['eta2'], want['eta2'], scale_atol=1e-5)
-    assert abs(float(got['ell']) - want['ell']) <= 1e-4 * abs(want['ell'])
+    _close(got['eta2'], want['eta2'], scale_atol=3e-5)
+    assert abs(float(got['ell']) - want['ell']) <= 1e-4 * 0.5 * tau * want['yty']
 
 
 def test_cfg5_logistic_reparam_gradient():

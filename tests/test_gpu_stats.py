@@ -177,7 +177,7 @@ def test_log_responsibilities_extremes():
 
 @pytest.mark.parametrize('n,d,k', [(1000, 64, 8), (4099, 16, 5), (300, 6, 3), (50000, 64, 16), (1, 4, 1),
                                    (2048, 64, 4), (5000, 32, 8), (40000, 64, 256), (1025, 16, 12),
-                                   (300000, 64, 8)])
+                                   (300000, 64, 8), (6000, 64, 516), (3000, 32, 260), (2500, 16, 1024)])
 def test_weighted_suffstats(n, d, k):
     import torch
     rng = np.random.RandomState(n + d + k)
@@ -225,7 +225,8 @@ def _close_gram(got, want, tol=3e-5):
 
 
 @pytest.mark.parametrize('n,d', [(1, 256), (31, 256), (32, 256), (33, 256), (1000, 256), (4097, 512),
-                                 (20000, 1024), (70001, 256), (0, 256), (500, 96), (300, 130), (64, 768)])
+                                 (20000, 1024), (70001, 256), (0, 256), (500, 96), (300, 130), (64, 768),
+                                 (3000, 128), (2000, 320), (1500, 68), (900, 1000), (40, 4096)])
 def test_regression_suffstats(n, d):
     import torch
     rng = np.random.RandomState(n * 7 + d)
@@ -248,11 +249,13 @@ def test_regression_suffstats(n, d):
     assert torch.equal(xtx, xtx.T)
 
 
-def test_regression_suffstats_exact_on_integers():
+@pytest.mark.parametrize('d', [512, 200, 68, 1020])
+def test_regression_suffstats_exact_on_integers(d):
     """Small integers are exact in bf16, so every product and every fp32 partial sum is exact:
-    any layout / quadrant / pipeline mistake in the CTA-pair kernel shows up as a whole-number error."""
+    any layout / quadrant / pipeline mistake in the CTA-pair kernel -- or in the zero padding of the feature
+    axis to a multiple of 256 -- shows up as a whole-number error."""
     import torch
-    n, d = 777, 512
+    n = 777
     i, j = np.meshgrid(np.arange(n), np.arange(d), indexing='ij')
     X = (((i * 3 + j * 5) % 11) - 5).astype(np.float32)
     y = ((np.arange(n) % 5) - 2).astype(np.float32)
