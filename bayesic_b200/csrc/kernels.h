@@ -87,13 +87,8 @@ int64_t colproj_tc_workspace(int64_t n, int d, int q);
 int launch_colproj_tc(const float* x, const float* r, int64_t n, int d, int q, double* out, void* workspace,
                       int64_t workspace_bytes, cudaStream_t stream);
 
-// logistic_fused_sm100.cu: the whole reparameterised logistic pass in one kernel (X read once)
-bool logistic_fused_supported(int64_t n, int d, int s, const void* x);
-int64_t logistic_fused_workspace(int64_t n, int d, int s);
-int launch_logistic_fused(const float* x, const float* y, const float* w, int64_t n, int d, int s, double* loglik,
-                          double* g, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
-
-// logistic_fused2_sm100.cu: same pass with the X tile resident (converted once) and W streamed
+// logistic_fused2_sm100.cu: the whole reparameterised logistic pass in one kernel -- X read once, the X tile
+// resident (converted once), W streamed
 bool logistic_fused2_supported(int64_t n, int d, int s, const void* x);
 int64_t logistic_fused2_workspace(int64_t n, int d, int s);
 int launch_logistic_fused2(const float* x, const float* y, const float* w, int64_t n, int d, int s, double* loglik,

@@ -1,5 +1,5 @@
 """Developer check for the cfg5 single-kernel pass (run on the GPU box): parity against float64 numpy
-at a few shapes, then timing at BASELINE size.  BB_FUSED_V2=0 selects the first design (logistic_fused_sm100.cu)."""
+at a few shapes, then timing at BASELINE size.  (The first design, logistic_fused_sm100.cu, was removed in round 2.)"""
 import os
 import sys
 import time

@@ -216,8 +216,10 @@ def test_weighted_suffstats_sum_over_components_is_the_plain_statistic():
 def _close_gram(got, want, tol=3e-5):
     """Elementwise |err| <= rtol |want| + tol sqrt(S_aa S_bb): the Cauchy-Schwarz scale of entry
     (a, b) is the natural unit for an off-diagonal sum that cancels (float32 BLAS has the same
-    shape of error).  Measured on B200: <= 1.2e-5 (BF16x3 products, fp32 TMEM accumulate drained
-    every 2048 rows)."""
+    shape of error).  Anchors (profiles/r02_parity_report.txt, column `cs`, N = 32 Ki x 1024): this kernel
+    1.16e-5, a float32 numpy/BLAS evaluation of the same plan (the reference's own arithmetic) 4.1e-7 -- the
+    BF16x3 kernel is ~28x a float32 BLAS on this scale (two-part BF16 operands carry 16 mantissa bits,
+    DESIGN.md 4.3) and the coefficient is 2.5x its own measured figure, NOT 2x the float32 reference's."""
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
     assert got.shape == want.shape
@@ -339,7 +341,9 @@ def test_column_projection(n, d, q):
     G = S.column_projection(torch.from_numpy(X).cuda(), torch.from_numpy(R).cuda()).cpu().numpy()
     want = X.astype(np.float64).T @ R.astype(np.float64)
     scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(R.astype(np.float64), axis=0)[None, :]
-    assert np.all(np.abs(G - want) <= RTOL * np.abs(want) + 3e-5 * scale)
+    # Cauchy-Schwarz-scale coefficient: measured 5.9e-7 at 64 Ki rows (profiles/r02_parity_report.txt, cfg5 G, `cs`;
+    # a float32 BLAS: 4.6e-8); 1e-5 leaves room for the short row counts above
+    assert np.all(np.abs(G - want) <= RTOL * np.abs(want) + 1e-5 * scale)
 
 
 def test_projections_exact_on_integers():
@@ -531,7 +535,7 @@ def test_logistic_reparam_stats(n, d, s):
     want_G = X.astype(np.float64).T @ resid
     np.testing.assert_allclose(ll.cpu().numpy(), want_ll, rtol=1e-4, atol=1e-5)
     scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(resid, axis=0)[None, :]
-    assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 3e-5 * scale + 1e-12)
+    assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 1e-5 * scale + 1e-12)    # anchors: see test_column_projection
 
 
 def test_logistic_reparam_stats_saturated_logits():
@@ -552,14 +556,14 @@ def test_logistic_reparam_stats_saturated_logits():
     assert np.isfinite(ll.cpu().numpy()).all() and np.isfinite(G.cpu().numpy()).all()
     np.testing.assert_allclose(ll.cpu().numpy(), want_ll, rtol=1e-4)
     scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(resid, axis=0)[None, :]
-    assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 1e-4 * scale + 1e-12)
+    assert np.all(np.abs(G.cpu().numpy() - want_G) <= RTOL * np.abs(want_G) + 3e-5 * scale + 1e-12)
 
 
-@pytest.mark.parametrize('env', [{'BB_FUSED_V2': '0'}, {'BB_LOGISTIC_UNFUSED': '1'}])
+@pytest.mark.parametrize('env', [{'BB_LOGISTIC_UNFUSED': '1'}])
 def test_logistic_reparam_alternative_kernels(env):
-    """The kernels behind the same entry point that are not the default -- the W-resident single-kernel
-    design (BB_FUSED_V2=0) and the two-kernel row/column projection path (BB_LOGISTIC_UNFUSED=1) --
-    stay parity-green.  The switches are read once per process, hence the subprocess."""
+    """The path behind the same entry point that is not the default -- the two-kernel row / column projection
+    path (BB_LOGISTIC_UNFUSED=1) -- stays parity-green.  The switch is read once per process, hence the
+    subprocess."""
     import os
     import subprocess
     import sys
@@ -577,7 +581,7 @@ def test_logistic_reparam_alternative_kernels(env):
         "    R = y[:, None] - 1.0 / (1.0 + np.exp(-Z)); want_G = X.astype(np.float64).T @ R\n"
         "    scale = np.linalg.norm(X.astype(np.float64), axis=0)[:, None] * np.linalg.norm(R, axis=0)[None, :]\n"
         "    np.testing.assert_allclose(ll.cpu().numpy(), want_ll, rtol=1e-4, atol=1e-5)\n"
-        "    assert np.all(np.abs(G.cpu().numpy() - want_G) <= 1e-4 * np.abs(want_G) + 3e-5 * scale + 1e-12)\n"
+        "    assert np.all(np.abs(G.cpu().numpy() - want_G) <= 1e-4 * np.abs(want_G) + 1e-5 * scale + 1e-12)\n"
         "print('ok')\n")
     run = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, **env), capture_output=True,
                          text=True, timeout=600)
