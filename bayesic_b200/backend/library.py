@@ -80,6 +80,7 @@ SIGNATURES = {
     'bb_mixture_logits_workspace': (_i64, [_i64, _i32, _i32]),
     'bb_mixture_logits': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     'bb_logsoftmax_rows': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    'bb_softmax_rows': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     'bb_suffstats_weighted_workspace': (_i64, [_i64, _i32, _i32]),
     'bb_suffstats_weighted_from_logits': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
                                                          _vp]),

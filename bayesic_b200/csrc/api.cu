@@ -406,7 +406,13 @@ BB_API int bb_gaussian_expected_loglik(const double* sum_x, const double* sum_xx
 BB_API int bb_logsoftmax_rows(const float* logits, int64_t n, int32_t k, float* log_resp, float* lse,
                        double* sum_lse, void* stream) {
   if (n < 0 || (n > 0 && (!logits || !log_resp))) { set_error("logsoftmax_rows: bad arguments"); return BB_ERR_INVALID; }
-  return launch_logsoftmax_rows(logits, n, k, log_resp, lse, sum_lse, static_cast<cudaStream_t>(stream));
+  return launch_logsoftmax_rows(logits, n, k, log_resp, lse, sum_lse, false, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_softmax_rows(const float* logits, int64_t n, int32_t k, float* resp, float* lse, double* sum_lse,
+                    void* stream) {
+  if (n < 0 || (n > 0 && (!logits || !resp))) { set_error("softmax_rows: bad arguments"); return BB_ERR_INVALID; }
+  return launch_logsoftmax_rows(logits, n, k, resp, lse, sum_lse, true, static_cast<cudaStream_t>(stream));
 }
 
 BB_API int64_t bb_mixture_logits_workspace(int64_t n, int32_t d, int32_t k) {

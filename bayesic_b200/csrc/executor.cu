@@ -493,7 +493,7 @@ int run_node(Exec& ex, int idx) {
         if (k > 2147483647LL || k < 1) { set_error("node %d: bad last extent", idx); return BB_ERR_SHAPE; }
         if (!ex.dry())
           BB_TRY(launch_logsoftmax_rows(X.ptr, out.numel() / k, static_cast<int>(k), out.ptr, nullptr,
-                                        nullptr, ex.stream));
+                                        nullptr, false, ex.stream));
       }
       break;
     }

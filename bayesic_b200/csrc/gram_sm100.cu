@@ -136,6 +136,25 @@ __device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, 
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with an A-operand collector hint (fill on the first, lastuse on the second of two MMAs that share A)
+__device__ __forceinline__ void mma_bf16_pair_a_fill(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                     uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair_a_lastuse(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this offset in BOTH CTAs once all MMAs issued so far completed
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -457,6 +476,12 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
           const uint64_t b1 = alias_b ? a1 : ptx::make_smem_desc(base + 2 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
           const uint64_t b2 = alias_b ? a2 : ptx::make_smem_desc(base + 3 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
           if (ablate & 1) continue;
+          if (ablate & 64) {                  // developer switch BB_GRAM_ABLATE=64: A-collector hints (results stay valid)
+            mma_bf16_pair_a_fill(d_tmem, a1, b1, kIdesc, (first && ks == 0) ? 0u : 1u);
+            mma_bf16_pair_a_lastuse(d_tmem, a1, b2, kIdesc, 1u);
+            mma_bf16_pair(d_tmem, a2, b1, kIdesc, 1u);
+            continue;
+          }
           mma_bf16_pair(d_tmem, a1, b1, kIdesc, (first && ks == 0) ? 0u : 1u);
           if (ablate & 16) continue;
           mma_bf16_pair(d_tmem, a1, b2, kIdesc, 1u);

@@ -103,7 +103,7 @@ int launch_mixture_logits(const float* x, const float* u, const float* t, const 
 
 // mixture_kernels.cu
 int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_resp, float* lse,
-                           double* sum_lse, cudaStream_t stream);
+                           double* sum_lse, bool responsibilities, cudaStream_t stream);
 int64_t weighted_stats_workspace(int64_t n, int d, int k);
 int launch_weighted_stats(const float* x, const float* r, int64_t n, int d, int k, double* nk,
                           double* sum_rx, double* sum_rxx, void* workspace,

@@ -39,7 +39,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // K = 128 * ITERS floats per row, row held in registers (ITERS float4 per lane).
-template <int ITERS>
+// kResp: write the responsibilities exp(logit - lse) instead of their logarithm.
+template <int ITERS, bool kResp>
 __global__ void __launch_bounds__(256)
 logsoftmax_rows_vec_kernel(const float* __restrict__ logits, int64_t n, float* __restrict__ log_resp,
                            float* __restrict__ lse_out, double* __restrict__ sum_lse) {
@@ -87,6 +88,9 @@ logsoftmax_rows_vec_kernel(const float* __restrict__ logits, int64_t n, float* _
       o.y = (v[i].y - row_max) - log_sum;
       o.z = (v[i].z - row_max) - log_sum;
       o.w = (v[i].w - row_max) - log_sum;
+      if (kResp) {
+        o.x = __expf(o.x); o.y = __expf(o.y); o.z = __expf(o.z); o.w = __expf(o.w);
+      }
       __stcs(dst + i * 32 + lane, o);
     }
     const float lse = row_max + log_sum;
@@ -108,6 +112,7 @@ logsoftmax_rows_vec_kernel(const float* __restrict__ logits, int64_t n, float* _
 }
 
 // Any K: three sweeps over the row (it stays in L1/L2 after the first).
+template <bool kResp>
 __global__ void __launch_bounds__(256)
 logsoftmax_rows_any_kernel(const float* __restrict__ logits, int64_t n, int k,
                            float* __restrict__ log_resp, float* __restrict__ lse_out,
@@ -136,7 +141,10 @@ logsoftmax_rows_any_kernel(const float* __restrict__ logits, int64_t n, int k,
     s = warp_sum(s);
     const float log_sum = log1pf(s);
     float* dst = log_resp + row * k;
-    for (int j = lane; j < k; j += 32) dst[j] = (src[j] - row_max) - log_sum;
+    for (int j = lane; j < k; j += 32) {
+      const float o = (src[j] - row_max) - log_sum;
+      dst[j] = kResp ? __expf(o) : o;
+    }
     const float lse = row_max + log_sum;
     if (lane == 0) {
       if (lse_out != nullptr) lse_out[row] = lse;
@@ -158,7 +166,7 @@ logsoftmax_rows_any_kernel(const float* __restrict__ logits, int64_t n, int k,
 }  // namespace
 
 int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_resp, float* lse,
-                           double* sum_lse, cudaStream_t stream) {
+                           double* sum_lse, bool responsibilities, cudaStream_t stream) {
   if (k <= 0) {
     set_error("logsoftmax_rows: k must be positive");
     return BB_ERR_INVALID;
@@ -174,9 +182,12 @@ int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_res
   const int iters = (k % 128 == 0) ? k / 128 : 0;
   if (aligned && iters >= 1 && iters <= 8) {
     switch (iters) {
-#define BB_LSE_CASE(I)                                                                       \
-  case I:                                                                                    \
-    logsoftmax_rows_vec_kernel<I><<<grid, threads, 0, stream>>>(logits, n, log_resp, lse, sum_lse); \
+#define BB_LSE_CASE(I)                                                                                    \
+  case I:                                                                                                 \
+    if (responsibilities)                                                                                 \
+      logsoftmax_rows_vec_kernel<I, true><<<grid, threads, 0, stream>>>(logits, n, log_resp, lse, sum_lse);  \
+    else                                                                                                  \
+      logsoftmax_rows_vec_kernel<I, false><<<grid, threads, 0, stream>>>(logits, n, log_resp, lse, sum_lse); \
     break;
       BB_LSE_CASE(1) BB_LSE_CASE(2) BB_LSE_CASE(3) BB_LSE_CASE(4)
       BB_LSE_CASE(5) BB_LSE_CASE(6) BB_LSE_CASE(7) BB_LSE_CASE(8)
@@ -184,7 +195,10 @@ int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_res
     }
     BB_CHECK_LAUNCH("logsoftmax_rows_vec_kernel");
   } else {
-    logsoftmax_rows_any_kernel<<<grid, threads, 0, stream>>>(logits, n, k, log_resp, lse, sum_lse);
+    if (responsibilities)
+      logsoftmax_rows_any_kernel<true><<<grid, threads, 0, stream>>>(logits, n, k, log_resp, lse, sum_lse);
+    else
+      logsoftmax_rows_any_kernel<false><<<grid, threads, 0, stream>>>(logits, n, k, log_resp, lse, sum_lse);
     BB_CHECK_LAUNCH("logsoftmax_rows_any_kernel");
   }
   return BB_OK;

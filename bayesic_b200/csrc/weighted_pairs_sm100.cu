@@ -73,6 +73,26 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same MMA with an A-operand collector hint: the second of two consecutive MMAs that share A may take it from the
+// tensor core's collector buffer instead of fetching it from shared memory again (the port is the bottleneck here)
+__device__ __forceinline__ void mma_bf16_ss_a_fill(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_a_lastuse(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                      uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -394,8 +414,13 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
           const uint64_t r1 = ptx::make_smem_desc(base + mb * 4096, 2048, 1024, ptx::kLayoutSwizzle128B);
           const uint64_t r2 = ptx::make_smem_desc(base + kRPart + mb * 4096, 2048, 1024, ptx::kLayoutSwizzle128B);
           const uint32_t d_tmem = tmem + mb * kTileCols;
-          mma_bf16_ss(d_tmem, r1, p1, idesc, first ? 0u : 1u);
-          mma_bf16_ss(d_tmem, r1, p2, idesc, 1u);
+          if (prefetch_iters & 0x100) {        // developer switch BB_WP_COLLECTOR=1 (bit 8 of the packed knobs)
+            mma_bf16_ss_a_fill(d_tmem, r1, p1, idesc, first ? 0u : 1u);
+            mma_bf16_ss_a_lastuse(d_tmem, r1, p2, idesc, 1u);
+          } else {
+            mma_bf16_ss(d_tmem, r1, p1, idesc, first ? 0u : 1u);
+            mma_bf16_ss(d_tmem, r1, p2, idesc, 1u);
+          }
           mma_bf16_ss(d_tmem, r2, p1, idesc, 1u);
         }
         ptx::mma_commit(&sm.empty[s]);
@@ -502,7 +527,8 @@ int launch_weighted_pairs(const float* x, const float* r, const float* lse, int6
   BB_CUDA_OK(smem_opt_in_0.ensure(weighted_pairs_kernel<false>, smem_bytes));
   static SmemOptIn smem_opt_in_1;
   BB_CUDA_OK(smem_opt_in_1.ensure(weighted_pairs_kernel<true>, smem_bytes));
-  static const int prefetch_iters = getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) : 0;
+  static const int prefetch_iters = (getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) & 0xff : 0) |
+                                    ((getenv("BB_WP_COLLECTOR") ? atoi(getenv("BB_WP_COLLECTOR")) : 0) ? 0x100 : 0);
   for (int k0 = 0; k0 < k; k0 += kMaxK) {                 // slices of at most 256 components (stream-ordered)
     const int kc = k - k0 < kMaxK ? k - k0 : kMaxK;
     PairsPlan p = plan_pairs(n, d, kc);

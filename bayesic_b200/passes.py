@@ -114,11 +114,22 @@ class GmmStep(object):
         return U.float().contiguous(), t.float().contiguous(), c.float().contiguous()
 
     @staticmethod
-    def local_step(X, U, t, c):
+    def local_step(X, U, t, c, materialise=True):
         """The whole local step from WHITENED parameters (``whiten`` once per global update, or the
-        ``U, t, c`` that ``updates.gmm_global_update`` emits): two kernels, nothing else -- logits + row
-        log-sum-exp, then {N_k, sum r x, sum r x x^T} with r = exp(logit - lse) formed inside the
-        operand conversion (the responsibility matrix is never written)."""
+        ``U, t, c`` that ``updates.gmm_global_update`` emits), device kernels only:
+
+        ``materialise=True`` (default, the faster route): logits -> responsibilities in place (one pass: row
+        log-sum-exp and r = exp(logit - lse), ``bb_softmax_rows``) -> {N_k, sum r x, sum r x x^T}; three kernels,
+        the N x K buffer is written twice.  ``materialise=False``: logits + row log-sum-exp, then the statistics
+        with r formed inside the operand conversion (two kernels, R never written, 2 GB less traffic per 2 Mi
+        rows) -- but every column-tile CTA of the statistics kernel then re-evaluates the exponentials of its row
+        range (10 x at D = 64), which costs more than the extra pass saves (measured at 2 Mi rows, K = 256:
+        16.2 ms against 14.7 ms)."""
+        if materialise:
+            logits, _, _ = stats.mixture_logits(X, U, t, c, want_lse=False, want_sum=False, upper_triangular=True)
+            resp, lse, sum_lse = stats.responsibilities(logits, out=logits)          # in place
+            nk, rx, rxx = stats.weighted_suffstats(X, resp)
+            return {'resp': resp, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
         logits, lse, sum_lse = stats.mixture_logits(X, U, t, c, upper_triangular=True)
         nk, rx, rxx = stats.weighted_suffstats_from_logits(X, logits, lse)
         return {'logits': logits, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
@@ -133,19 +144,21 @@ class GmmStep(object):
 
     def __call__(self, X, Ak, bk, ck, fused=True, want_log_resp=True):
         """Local step from (A_k, b_k, c_k).  Every per-minibatch operation is a device kernel of this
-        library: the shapes the tcgen05 kernels serve take ``local_step`` (two kernels; a third, the
-        in-place row normalisation, only when the log-responsibilities themselves are asked for); other
+        library: the shapes the tcgen05 kernels serve take ``local_step`` (when the log-responsibilities
+        themselves are asked for: logits, in-place log-softmax, statistics with r = exp(log r) formed in the
+        operand conversion); other
         shapes take the compiled einsum plan, the log-softmax kernel, a compiled ``exp`` and the generic
         weighted-statistics kernel."""
+        import torch
         d, k = X.shape[1], Ak.shape[0]
         if fused and stats.mixture_logits_supported(d, k) and d % 8 == 0 and k <= 4096 and k % 4 == 0:
-            out = self.local_step(X, *self._whitened(Ak, bk, ck))
-            if want_log_resp:
-                logits = out.pop('logits')
-                log_resp, _, _ = stats.log_responsibilities(logits, want_lse=False, want_sum=False,
-                                                            out=logits)     # in place
-                out['log_resp'] = log_resp
-            return out
+            if not want_log_resp:
+                return self.local_step(X, *self._whitened(Ak, bk, ck))
+            logits, _, _ = stats.mixture_logits(X, *self._whitened(Ak, bk, ck), want_lse=False, want_sum=False,
+                                               upper_triangular=True)
+            log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place
+            nk, rx, rxx = stats.weighted_suffstats_from_logits(X, log_resp, torch.zeros_like(lse))
+            return {'log_resp': log_resp, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
         logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
         log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place
         nk, rx, rxx = stats.weighted_suffstats(X, self.exp_fn(LR=log_resp))

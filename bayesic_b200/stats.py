@@ -18,6 +18,7 @@ import numpy as np
 from .backend import library as L
 
 __all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'gaussian_suffstats_loglik', 'log_responsibilities',
+           'responsibilities',
            'weighted_suffstats', 'regression_suffstats', 'row_projection', 'column_projection',
            'logistic_reparam_stats', 'logistic_reparam_supported', 'mixture_logits',
            'mixture_logits_supported', 'weighted_suffstats_from_logits', 'launch_count']
@@ -189,6 +190,23 @@ def log_responsibilities(logits, want_lse=True, want_sum=True, out=None):
                                        total.data_ptr() if want_sum else None, _stream(dev)),
                 'bb_logsoftmax_rows')
     return log_resp, lse, total
+
+
+def responsibilities(logits, want_lse=True, want_sum=True, out=None):
+    """``r = exp(logits - logsumexp(logits, axis=1))`` in one pass (``out`` may be ``logits`` itself).  Returns
+    ``(resp[n, k] float32, lse[n] float32 | None, sum_lse float64[1] | None)``."""
+    torch = _torch()
+    lib = L.load()
+    logits = _as_device_f32(logits, 2, 'logits')
+    n, k = logits.shape
+    dev = logits.device
+    with torch.cuda.device(dev):
+        resp = out if out is not None else torch.empty_like(logits)
+        lse = torch.empty(n, dtype=torch.float32, device=dev) if want_lse else None
+        total = torch.empty(1, dtype=torch.float64, device=dev) if want_sum else None
+        L.check(lib.bb_softmax_rows(logits.data_ptr(), n, k, resp.data_ptr(), lse.data_ptr() if want_lse else None,
+                                    total.data_ptr() if want_sum else None, _stream(dev)), 'bb_softmax_rows')
+    return resp, lse, total
 
 
 def weighted_suffstats(X, R):

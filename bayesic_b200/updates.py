@@ -127,7 +127,7 @@ def adam_step(param, grad, m, v, step, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8
 
 class GmmVmp(object):
     """Full-batch VMP for a Gaussian mixture (cfg3 as a loop): local step on the tcgen05 kernels
-    (logits + row log-sum-exp, then statistics with r formed on the fly), one all-reduce of the
+    (logits, responsibilities in place, statistics), one all-reduce of the
     packed statistics when a process group is up, global step in one kernel.  State lives on the
     device; ``step`` enqueues kernels only and returns device tensors."""
 
@@ -154,8 +154,10 @@ class GmmVmp(object):
         if self.state is None:
             raise RuntimeError("GmmVmp.initialise(...) first")
         prev = self.state
-        logits, lse, sum_lse = stats.mixture_logits(X_local, prev['U'], prev['t'], prev['c'], upper_triangular=True)
-        nk, rx, rxx = stats.weighted_suffstats_from_logits(X_local, logits, lse)
+        logits, _, _ = stats.mixture_logits(X_local, prev['U'], prev['t'], prev['c'], want_lse=False, want_sum=False,
+                                            upper_triangular=True)
+        resp, lse, sum_lse = stats.responsibilities(logits, out=logits)       # in place; see passes.GmmStep.local_step
+        nk, rx, rxx = stats.weighted_suffstats(X_local, resp)
         views = self.layout.views(self.packed)
         views['nk'].copy_(nk)
         views['rx'].copy_(rx)

@@ -247,6 +247,11 @@ BB_API int bb_logistic_reparam_pass(const float* X, const float* y, const float*
  * lse[n] and sum_lse (float64, device) are optional (may be NULL). */
 BB_API int bb_logsoftmax_rows(const float* logits, int64_t n, int32_t k,
                        float* log_resp, float* lse, double* sum_lse, void* stream);
+/* The responsibilities themselves, r[n,k] = exp(logits[n,k] - logsumexp_k logits[n,:]) -- the value of
+ * exp(Lg + (-1 * log(sum(exp(Lg), 1))).dimshuffle(0, 'x')) in the reference's vocabulary (algebra.py:1435-1448)
+ * -- in the same single pass (resp may alias logits); lse / sum_lse as above. */
+BB_API int bb_softmax_rows(const float* logits, int64_t n, int32_t k,
+                    float* resp, float* lse, double* sum_lse, void* stream);
 
 /* Gaussian-mixture expected log-densities in whitened form (VMP local step, README.md:30-37):
  *   logits[n,k] = c[k] - 1/2 || U[k] x_n - t[k] ||^2      (= c' + x.b_k - 1/2 x^T A_k x with

@@ -104,7 +104,7 @@ def main():
     row('cfg3', 'sum r x', got['rx'], want['rx'], f32=rx32, cs=cs_rx)
     row('cfg3', 'sum r x x^T', got['rxx'], want['rxx'], f32=rxx32, cs=cs_rxx)
     got2 = step(dev(X), dev(Ak), dev(bk), dev(ck), want_log_resp=False)
-    row('cfg3', 'sum r x x^T (R never written)', got2['rxx'], want['rxx'], f32=rxx32, cs=cs_rxx)
+    row('cfg3', 'sum r x x^T (local_step, R in place)', got2['rxx'], want['rxx'], f32=rxx32, cs=cs_rxx)
     upd = U.gmm_global_update(t64(want['nk']), t64(want['rx']), t64(want['rxx']), 1.0, 1.0, d + 2.0,
                               t64(np.zeros(d)), t64(np.eye(d)))
     ref = O.gmm_global_update(want['nk'], want['rx'], want['rxx'], 1.0, 1.0, d + 2.0, np.zeros(d), np.eye(d))

@@ -179,9 +179,10 @@ def test_cfg3_gmm_vmp_step_on_the_tensor_core_kernels():
         assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
 
 
-def test_cfg3_gmm_vmp_step_without_materialising_responsibilities():
-    """want_log_resp=False: logits + lse from the tcgen05 logits kernel, responsibilities formed
-    inside the statistics kernel; same statistics as the oracle's full step."""
+def test_cfg3_local_step_both_routes():
+    """``local_step`` from whitened parameters: the default route (logits -> responsibilities in place ->
+    statistics; ``want_log_resp=False`` of ``GmmStep.__call__``) and ``materialise=False`` (logits + lse, r formed
+    inside the statistics kernel, R never written); same statistics as the oracle's full step either way."""
     import torch
     rng = np.random.RandomState(8)
     n, d, k = 5000, 64, 12
@@ -194,16 +195,21 @@ def test_cfg3_gmm_vmp_step_without_materialising_responsibilities():
     W = np.stack([np.linalg.inv(_spd(rng, d)) / nu[j] for j in range(k)])
     want = O.gmm_vmp_step(X, log_pi, m, beta, W, nu)
     step = P.GmmStep()
-    Ak, bk, ck = step.expectations(log_pi, m, beta, W, nu)
-    got = step(torch.from_numpy(X).cuda(), torch.from_numpy(Ak).cuda(), torch.from_numpy(bk).cuda(),
-               torch.from_numpy(ck).cuda(), want_log_resp=False)
-    assert 'log_resp' not in got
-    log_resp = (got['logits'] - got['lse'][:, None]).cpu().numpy()
+    Ak, bk, ck = (torch.from_numpy(a).cuda() for a in step.expectations(log_pi, m, beta, W, nu))
+    Xd = torch.from_numpy(X).cuda()
+    got = step(Xd, Ak, bk, ck, want_log_resp=False)
+    assert 'log_resp' not in got and 'logits' not in got
+    np.testing.assert_allclose(got['resp'].cpu().numpy(), np.exp(want['log_resp']), rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(got['resp'].sum(1).cpu().numpy(), 1.0, rtol=1e-5)
+    other = step.local_step(Xd, *step.whiten(Ak, bk, ck), materialise=False)
+    log_resp = (other['logits'] - other['lse'][:, None]).cpu().numpy()
     np.testing.assert_allclose(log_resp, want['log_resp'], rtol=1e-4, atol=3e-3)
-    _close(got['nk'], want['nk'], rtol=1e-4, scale_atol=2e-5)
-    _close(got['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
-    _close(got['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
-    assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
+    for out in (got, other):
+        _close(out['nk'], want['nk'], rtol=1e-4, scale_atol=2e-5)
+        _close(out['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
+        _close(out['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
+        assert abs(float(out['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
+        np.testing.assert_allclose(out['lse'].cpu().numpy(), got['lse'].cpu().numpy(), rtol=1e-5, atol=1e-4)
 
 
 @pytest.mark.parametrize('n,d,l', [(20000, 256, 16), (5000, 96, 5), (8192, 1024, 32)])

@@ -160,6 +160,22 @@ def test_log_responsibilities(n, k):
     assert abs(float(tot) - ref_lse.sum()) <= RTOL * max(1.0, abs(ref_lse.sum()))
 
 
+@pytest.mark.parametrize('n,k', [(4096, 256), (1000, 128), (33, 7), (5, 1000), (7, 33), (1, 1), (0, 256)])
+def test_responsibilities_single_pass_and_in_place(n, k):
+    """bb_softmax_rows: r = exp(Lg - lse) in the same single pass as the log-softmax, also in place."""
+    import torch
+    rng = np.random.RandomState(n + 11 * k)
+    Lg = (rng.randn(n, k) * 3).astype(np.float32)
+    ref_lr, ref_lse = O.log_responsibilities(Lg)
+    dev = torch.from_numpy(Lg).cuda()
+    r, lse, tot = S.responsibilities(dev)
+    np.testing.assert_allclose(r.cpu().numpy(), np.exp(ref_lr), rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(lse.cpu().numpy(), ref_lse, rtol=RTOL, atol=2e-6)
+    assert abs(float(tot) - ref_lse.sum()) <= RTOL * max(1.0, abs(ref_lse.sum()))
+    r2, _, _ = S.responsibilities(dev, want_lse=False, want_sum=False, out=dev)
+    assert r2.data_ptr() == dev.data_ptr() and torch.equal(r2, r)
+
+
 def test_log_responsibilities_extremes():
     import torch
     Lg = np.zeros((4, 256), dtype=np.float32)
