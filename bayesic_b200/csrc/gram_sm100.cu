@@ -44,11 +44,14 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "sm100_pair.cuh"
 #include "sm100_ptx.cuh"
 
 namespace bb {
 
 namespace {
+
+using namespace pair;
 
 constexpr int kBlock = 256;               // output block edge (features) per CTA pair
 constexpr int kHalf = 128;                // features per CTA per operand side
@@ -80,89 +83,6 @@ struct __align__(1024) SmemLayout {
 // kind::f16, BF16 x BF16 -> FP32, both operands MN-major, M = 256 (pair), N = 256
 constexpr uint32_t kIdesc = ptx::make_idesc(256, 256, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// Arrive on the barrier at the same shared-memory offset in CTA `rank`, without a release fence:
-// ordering is provided by the caller (every lane has executed
-// fence.proxy.async -- SASS: MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC -- so its shared-memory stores
-// have completed, then __syncwarp).  A release.cluster arrive compiles to MEMBAR.ALL.GPU, which
-// on the per-stage path costs more than the whole MMA budget.
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
-      ::"r"(ptx::smem_u32(bar)), "r"(rank)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(ptx::smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t n_cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   ptx::smem_u32(smem_slot)),
-               "r"(n_cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t n_cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(n_cols)
-               : "memory");
-}
-// D[tmem, both CTAs] (+)= A[smem desc, both CTAs] * B[smem desc, both CTAs], issued by one
-// thread of the leader CTA.
-__device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                              uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// same with an A-operand collector hint (fill on the first, lastuse on the second of two MMAs that share A)
-__device__ __forceinline__ void mma_bf16_pair_a_fill(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                                     uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_bf16_pair_a_lastuse(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                                        uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at this offset in BOTH CTAs once all MMAs issued so far completed
-__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-      "[%0], %1;" ::"r"(ptx::smem_u32(bar)),
-      "h"(static_cast<uint16_t>(3))
-      : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -209,6 +129,8 @@ __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], u
 
 struct ConvArgs {
   int prefetch_iters;      // L2 prefetch distance in converter iterations (0 = off)
+  bool early;              // issue the next stage's loads before the proxy fence of the current one: their latency
+                           // overlaps the fence instead of following it (the converters never wait on the stage barrier)
   const float* x;
   const float* y;
   int64_t n, row_begin, row_end;
@@ -321,10 +243,12 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
         yty_f = fmaf(ry[j], ry[j], yty_f);
       }
     }
+    const bool more = it + kConvGroups < ca.n_iters;
+    if (ca.early && more) load_rows();
     fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster_relaxed(&sm.full[s], 0);
-    if (it + kConvGroups < ca.n_iters) load_rows();
+    if (!ca.early && more) load_rows();
     if (kXty && ++since_flush == kXtyFlushIters) {     // fp32 over 32 rows, then float64 (DADD is slow)
       since_flush = 0;
 #pragma unroll
@@ -409,6 +333,7 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
     // ---------------- converter warps: global fp32 -> registers -> bf16 b1/b2 tiles ----------------
     ConvArgs ca;
     ca.prefetch_iters = ablate >> 8;
+    ca.early = (ablate & 128) == 0;      // default on (3.20 -> 3.08 ms at cfg4); BB_GRAM_ABLATE=128 restores loads-after-arrive
     ca.row_end = it_end * kStageRows < n ? it_end * kStageRows : n;
     ca.x = x; ca.y = y; ca.n = n; ca.d = d; ca.feat_a = feat_a; ca.feat_b = feat_b;
     ca.row_begin = row_begin; ca.n_iters = n_iters; ca.warp = warp; ca.lane = lane;
@@ -476,7 +401,8 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
           const uint64_t b1 = alias_b ? a1 : ptx::make_smem_desc(base + 2 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
           const uint64_t b2 = alias_b ? a2 : ptx::make_smem_desc(base + 3 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
           if (ablate & 1) continue;
-          if (ablate & 64) {                  // developer switch BB_GRAM_ABLATE=64: A-collector hints (results stay valid)
+          if (!(ablate & 64)) {               // A-collector hints: the second MMA takes A = a1 from the collector buffer, not from
+                                              // shared memory (measured 3.200 -> 3.15 ms at cfg4; BB_GRAM_ABLATE=64 switches it off)
             mma_bf16_pair_a_fill(d_tmem, a1, b1, kIdesc, (first && ks == 0) ? 0u : 1u);
             mma_bf16_pair_a_lastuse(d_tmem, a1, b2, kIdesc, 1u);
             mma_bf16_pair(d_tmem, a2, b1, kIdesc, 1u);

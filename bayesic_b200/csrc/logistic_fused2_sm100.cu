@@ -181,7 +181,8 @@ struct Fused2Params {
   int prefetch;                     // L2 prefetch one converter step ahead of the register loads (BB_FUSED2_PREFETCH, default on)
   int collector;                    // A-operand collector reuse between MMAs that share A (BB_FUSED2_COLLECTOR, default on)
   int ablate;                       // developer timing experiments (BB_FUSED2_ABLATE; results are WRONG when set): 1 no global
-                                    // loads, 2 no converter stores, 4 no W stream, 8 no Z MMAs, 16 no G MMAs, 32 no epilogue math
+                                    // loads, 2 no converter stores, 4 no W stream, 8 no Z MMAs, 16 no G MMAs, 32 no epilogue math;
+                                    // 64 (results valid): next segment's loads issued before the proxy fence
   const float* x;
   const float* y;
   const uint8_t* wprep;             // [d / 64 chunks][16 KB UMMA image of [W1; W2]]
@@ -344,10 +345,11 @@ __global__ void __launch_bounds__(kThreads, 1) logistic_fused2_kernel(const Fuse
           split_in_place();
           ptx::mbar_wait_parked(&sm.x_free[seg], (static_cast<uint32_t>(t) & 1) ^ 1);
           if (!(p.ablate & 2)) store(seg);
+          if ((p.ablate & 64) && ld_g < total) load();        // experiment: next loads before the proxy fence
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&sm.x_full[seg]);
-          if (ld_g < total) load();
+          if (!(p.ablate & 64) && ld_g < total) load();
         }
       }
       // ---- epilogue part ----

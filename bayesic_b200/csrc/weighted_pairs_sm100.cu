@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -99,6 +100,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_f4_l1(const float* p) {      // through L1 (allocating): for lines an L1 prefetch brought in
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
@@ -277,25 +285,52 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     bool rows_ok = true;             // both rows of the prefetched stage are inside [0, n)
     // everything a stage needs is loaded one iteration ahead (nothing is fetched between the
     // barrier wait and the stores: dependent loads there serialise on the L2 latency)
-    auto load_all = [&]() {
-      rows_ok = row0 + 2 <= n;
+    const bool use_l1 = (prefetch_iters & 0x200) != 0;     // BB_WP_L1=1: prefetch into L1 and load through it
+    // part 1: R (+ lse) of the next stage this warp converts; part 2: X of that stage, then advance the pointers
+    // timing experiments (BB_WP_ABLATE; results are WRONG when set): 1 no global loads, 2 no converter stores,
+    // 4 no MMAs, 8 no proxy fence
+    const int ablate = prefetch_iters >> 12;
+    auto load_part = [&](int part) {
+      if (ablate & 1) {
+        if (part == 2) row0 += kConvGroups * kStageRows;
+        return;
+      }
+      const bool ok = row0 + 2 <= n;
       // ragged last stage: a row past the end re-reads row n - 1 (its weights are zeroed later)
       int jj[2] = {0, 1};
-      if (!rows_ok) {
+      if (!ok) {
         jj[0] = row0 < n ? 0 : static_cast<int>((n - 1) - row0);
         jj[1] = row0 + 1 < n ? 1 : static_cast<int>((n - 1) - row0);
       }
+      if (part == 1) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float* rrow = rp + jj[j] * g.ldr;
+          rr[j][0] = use_l1 ? ldg_f4_l1(rrow + kc0) : ldg_f4(rrow + kc0);
+          rr[j][1] = use_l1 ? ldg_f4_l1(rrow + kc1) : ldg_f4(rrow + kc1);
+          if (kFromLogits) row_lse[j] = __ldg(lp + jj[j]);
+        }
+        return;
+      }
+      rows_ok = ok;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const float* rrow = rp + jj[j] * g.ldr;
         const float* xrow = xp + jj[j] * g.d;
-        rr[j][0] = ldg_f4(rrow + kc0);
-        rr[j][1] = ldg_f4(rrow + kc1);
-        if (kFromLogits) row_lse[j] = __ldg(lp + jj[j]);
 #pragma unroll
         for (int t2 = 0; t2 < 2; ++t2) {
           xa[j][t2] = __ldg(xrow + src_a[t2]);
           xb[j][t2] = __ldg(reinterpret_cast<const float4*>(xrow + src_b[t2]));
+        }
+      }
+      // L2 / L1 prefetch of the rows this warp converts `pf` iterations from now (BB_WP_PREFETCH): 2 rows x
+      // (k * 4 / 128 lines of R) -- lanes 0-15 take one 128-byte line each at K = 256.  Measured neutral.
+      const int pf = prefetch_iters & 0xff;
+      if (pf > 0) {
+        const int64_t prow = row0 + static_cast<int64_t>(pf) * kConvGroups * kStageRows + (lane >> 4);
+        const int col = (lane & 15) * 32;
+        if (prow < row_end && col < g.k) {
+          if (use_l1) asm volatile("prefetch.global.L1 [%0];" ::"l"(r + prow * g.ldr + col));
+          else asm volatile("prefetch.global.L2 [%0];" ::"l"(r + prow * g.ldr + col));
         }
       }
       row0 += kConvGroups * kStageRows;
@@ -303,10 +338,29 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
       xp += x_step;
       if (kFromLogits) lp += kConvGroups * kStageRows;
     };
+    auto load_all = [&]() {
+      load_part(1);
+      load_part(2);
+    };
+    // Default (BB_WP_EARLY=0 restores the old order): issue the next stage's loads as soon as the registers they
+    // land in are free (R right after the R tile is stored, X right after the Phi tile) instead of after the
+    // hand-over: when the converters are the bottleneck the stage barrier never makes them wait, so loads issued
+    // after the arrive are needed at once and their whole latency is exposed; issued early it overlaps the Phi
+    // conversion and the proxy fence (measured at 1 Mi rows, K = 256: 3.55 -> 3.30 ms)
+    const bool early = (prefetch_iters & 0x400) != 0;
+#ifdef BB_WP_TIMELINE
+    long long tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tl_prev = clock64();
+#define BB_WP_TL(i) { const long long now_ = clock64(); tl[i] += now_ - tl_prev; tl_prev = now_; }
+#else
+#define BB_WP_TL(i)
+#endif
     if (group < n_iters) load_all();
     for (int it = group; it < n_iters; it += kConvGroups) {
       const int s = it % kStages;
+      BB_WP_TL(0)
       ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
+      BB_WP_TL(1)
       const uint32_t stage_addr = stage0 + s * kStageBytes;
       if (kFromLogits) {                                  // responsibilities from logits, on the fly
 #pragma unroll
@@ -337,9 +391,14 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
           uint32_t b1[2], b2[2];
           split_bf16(rr[j][h], b1, b2);
           const uint32_t addr = stage_addr + (2 * h + (lane >> 4)) * 2048 + off[j];
+          if (ablate & 2) continue;
           sts_u2(addr, b1[0], b1[1]);
           sts_u2(addr + kRPart, b2[0], b2[1]);
         }
+      BB_WP_TL(2)
+      const bool more = it + kConvGroups < n_iters;
+      if (early && more) load_part(1);
+      BB_WP_TL(3)
       // ---- Phi tile: [block (64 columns) 2 KB][k group][8][128 B] ----
 #pragma unroll
       for (int j = 0; j < 2; ++j)
@@ -352,14 +411,29 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
           uint32_t b1[2], b2[2];
           split_bf16(p, b1, b2);
           const uint32_t addr = stage_addr + 2 * kRPart + (2 * t2 + (lane >> 4)) * 2048 + off[j];
+          if (ablate & 2) continue;
           sts_u2(addr, b1[0], b1[1]);
           sts_u2(addr + kPPart, b2[0], b2[1]);
         }
-      fence_proxy_async_smem();
+      BB_WP_TL(4)
+      if (early && more) load_part(2);
+      BB_WP_TL(5)
+      if (!(ablate & 8)) fence_proxy_async_smem();
       __syncwarp();
+      BB_WP_TL(6)
       if (lane == 0) ptx::mbar_arrive(&sm.full[s]);
-      if (it + kConvGroups < n_iters) load_all();
+      if (!early && more) load_all();
+      BB_WP_TL(7)
     }
+#ifdef BB_WP_TIMELINE
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15)) {
+      const int its = (n_iters - group + kConvGroups - 1) / kConvGroups;
+      printf("converter warp %d (CTA 0, %d of its stages), clock64 cycles per stage: loop top %lld  wait empty %lld  "
+             "R convert+store %lld  R loads issued %lld  Phi convert+store %lld  X loads issued %lld  fence+syncwarp %lld  "
+             "arrive %lld | total %lld\n", warp, its, tl[0] / its, tl[1] / its, tl[2] / its, tl[3] / its, tl[4] / its,
+             tl[5] / its, tl[6] / its, tl[7] / its, (tl[0] + tl[1] + tl[2] + tl[3] + tl[4] + tl[5] + tl[6] + tl[7]) / its);
+    }
+#endif
   } else if (warp < kMmaWarp) {
     // ---------------- epilogue warps: TMEM fp32 -> fp32 partial (coalesced RMW), single-buffered ----------------
     const int qd = warp & 3;
@@ -400,17 +474,30 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
     // ---------------- MMA issuer ----------------
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc(128, kTileCols, /*bf16*/ 1, 1, 1);
+#ifdef BB_WP_TIMELINE
+      long long m_wait_acc = 0, m_wait_full = 0, m_t0 = clock64(), m_prev = m_t0;
+#endif
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % kStages;
         const int interval = it / kFlushIters;
         const bool first = (it % kFlushIters) == 0;
+#ifdef BB_WP_TIMELINE
+        m_prev = clock64();
+#endif
         if (first && interval > 0) ptx::mbar_wait(&sm.acc_empty, (interval - 1) & 1);
+#ifdef BB_WP_TIMELINE
+        { const long long now_ = clock64(); m_wait_acc += now_ - m_prev; m_prev = now_; }
+#endif
         ptx::mbar_wait(&sm.full[s], (it / kStages) & 1);
+#ifdef BB_WP_TIMELINE
+        { const long long now_ = clock64(); m_wait_full += now_ - m_prev; m_prev = now_; }
+#endif
         ptx::tc_fence_after_sync();
         const uint32_t base = ptx::smem_u32(sm.stage[s]);
         const uint64_t p1 = ptx::make_smem_desc(base + 2 * kRPart, 2048, 1024, ptx::kLayoutSwizzle128B);
         const uint64_t p2 = ptx::make_smem_desc(base + 2 * kRPart + kPPart, 2048, 1024, ptx::kLayoutSwizzle128B);
         for (int mb = 0; mb < m_blocks; ++mb) {
+          if ((prefetch_iters >> 12) & 4) break;
           const uint64_t r1 = ptx::make_smem_desc(base + mb * 4096, 2048, 1024, ptx::kLayoutSwizzle128B);
           const uint64_t r2 = ptx::make_smem_desc(base + kRPart + mb * 4096, 2048, 1024, ptx::kLayoutSwizzle128B);
           const uint32_t d_tmem = tmem + mb * kTileCols;
@@ -426,6 +513,12 @@ weighted_pairs_kernel(const float* __restrict__ x, const float* __restrict__ r, 
         ptx::mma_commit(&sm.empty[s]);
         if ((it % kFlushIters) == kFlushIters - 1 || it == n_iters - 1) ptx::mma_commit(&sm.acc_full);
       }
+#ifdef BB_WP_TIMELINE
+      if (blockIdx.x == 0)
+        printf("MMA issuer (CTA 0, %d stages), clock64 cycles per stage: waiting for a full stage %lld  waiting for the "
+               "accumulator drain %lld | total %lld (768 = the six MMAs of a stage)\n", n_iters, m_wait_full / n_iters,
+               m_wait_acc / n_iters, (clock64() - m_t0) / n_iters);
+#endif
     }
   }
 
@@ -528,7 +621,10 @@ int launch_weighted_pairs(const float* x, const float* r, const float* lse, int6
   static SmemOptIn smem_opt_in_1;
   BB_CUDA_OK(smem_opt_in_1.ensure(weighted_pairs_kernel<true>, smem_bytes));
   static const int prefetch_iters = (getenv("BB_WP_PREFETCH") ? atoi(getenv("BB_WP_PREFETCH")) & 0xff : 0) |
-                                    ((getenv("BB_WP_COLLECTOR") ? atoi(getenv("BB_WP_COLLECTOR")) : 0) ? 0x100 : 0);
+                                    ((getenv("BB_WP_COLLECTOR") ? atoi(getenv("BB_WP_COLLECTOR")) : 0) ? 0x100 : 0) |
+                                    ((getenv("BB_WP_L1") ? atoi(getenv("BB_WP_L1")) : 0) ? 0x200 : 0) |
+                                    ((getenv("BB_WP_EARLY") ? atoi(getenv("BB_WP_EARLY")) : 1) ? 0x400 : 0) |
+                                    ((getenv("BB_WP_ABLATE") ? atoi(getenv("BB_WP_ABLATE")) & 15 : 0) << 12);
   for (int k0 = 0; k0 < k; k0 += kMaxK) {                 // slices of at most 256 components (stream-ordered)
     const int kc = k - k0 < kMaxK ? k - k0 : kMaxK;
     PairsPlan p = plan_pairs(n, d, kc);

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -q -x -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python tests/gpu_cfg_timing.py 2>&1 | tee gpurun_out/r2_cfg_timing.txt
