@@ -81,6 +81,9 @@ SIGNATURES = {
     'bb_mixture_logits': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     'bb_logsoftmax_rows': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     'bb_softmax_rows': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    'bb_softmax_rows_split_bytes': (ctypes.c_int64, [_i64, _i32]),
+    'bb_softmax_rows_split': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    'bb_suffstats_weighted_split': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     'bb_suffstats_weighted_workspace': (_i64, [_i64, _i32, _i32]),
     'bb_suffstats_weighted_from_logits': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
                                                          _vp]),

@@ -443,6 +443,31 @@ BB_API int bb_suffstats_weighted(const float* X, const float* R, int64_t n, int3
                                     static_cast<cudaStream_t>(stream));
 }
 
+BB_API int64_t bb_softmax_rows_split_bytes(int64_t n, int32_t k) {
+  if (n < 0 || k < 256 || k % 256 != 0) return 0;
+  return weighted_pairs_split_bytes(n, k);
+}
+
+BB_API int bb_softmax_rows_split(const float* logits, int64_t n, int32_t k, void* rsplit, float* lse, double* sum_lse,
+                          void* stream) {
+  if (n < 0 || (n > 0 && (!logits || !rsplit))) { set_error("softmax_rows_split: bad arguments"); return BB_ERR_INVALID; }
+  return launch_softmax_rows_split(logits, n, k, rsplit, lse, sum_lse, static_cast<cudaStream_t>(stream));
+}
+
+BB_API int bb_suffstats_weighted_split(const float* X, const void* rsplit, int64_t n, int32_t d, int32_t k, double* Nk,
+                                double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n < 0 || !sum_rxx || (n > 0 && (!X || !rsplit))) { set_error("suffstats_weighted_split: bad arguments"); return BB_ERR_INVALID; }
+  if (n == 0) {
+    BB_CUDA_OK(cudaMemsetAsync(sum_rxx, 0, sizeof(double) * k * d * d, st));
+    if (sum_rx) BB_CUDA_OK(cudaMemsetAsync(sum_rx, 0, sizeof(double) * k * d, st));
+    if (Nk) BB_CUDA_OK(cudaMemsetAsync(Nk, 0, sizeof(double) * k, st));
+    return BB_OK;
+  }
+  return launch_weighted_pairs_split(X, rsplit, n, d, k, Nk, sum_rx, sum_rxx, workspace, workspace_bytes, st);
+}
+
 BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits, const float* lse, int64_t n,
                                       int32_t d, int32_t k, double* Nk, double* sum_rx, double* sum_rxx,
                                       void* workspace, int64_t workspace_bytes, void* stream) {

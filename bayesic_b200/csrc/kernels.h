@@ -121,6 +121,15 @@ int64_t weighted_pairs_workspace(int64_t n, int d, int k);
 int launch_weighted_pairs(const float* x, const float* r, const float* lse, int64_t n, int d, int k, double* nk,
                           double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
                           cudaStream_t stream);
+// pre-split responsibilities (BF16 operand tiles, see weighted_pairs_sm100.cu): layout producer in mixture_kernels.cu
+bool weighted_pairs_split_supported(int64_t n, int d, int k, const void* x, const void* rsplit);
+int64_t weighted_pairs_split_stages(int64_t n);
+int64_t weighted_pairs_split_bytes(int64_t n, int k);
+int launch_weighted_pairs_split(const float* x, const void* rsplit, int64_t n, int d, int k, double* nk,
+                                double* sum_rx, double* sum_rxx, void* workspace, int64_t workspace_bytes,
+                                cudaStream_t stream);
+int launch_softmax_rows_split(const float* logits, int64_t n, int k, void* rsplit, float* lse, double* sum_lse,
+                              cudaStream_t stream);
 // tcgen05 kernel when the shape allows it (and BB_WEIGHTED_SIMT is unset), SIMT kernel otherwise
 int64_t weighted_stats_auto_workspace(int64_t n, int d, int k);
 int launch_weighted_stats_auto(const float* x, const float* r, int64_t n, int d, int k, double* nk,

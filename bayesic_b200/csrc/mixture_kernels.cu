@@ -13,6 +13,7 @@
 // K x D x N intermediate the reference plan materialises
 //   _tensordot(_mul(_dimshuffle(R,1,'x',0), _dimshuffle(X,'x',1,0)), X, [2],[0])
 // (algebra.py:741-765 + 1297-1306).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -95,6 +96,85 @@ logsoftmax_rows_vec_kernel(const float* __restrict__ logits, int64_t n, float* _
     }
     const float lse = row_max + log_sum;
     if (lane == 0) {
+      if (lse_out != nullptr) lse_out[row] = lse;
+      lse_acc += static_cast<double>(lse);
+    }
+  }
+  if (sum_lse != nullptr) {
+    __shared__ double block_acc[8];
+    if (lane == 0) block_acc[warp_in_block] = lse_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (blockDim.x >> 5); ++w) t += block_acc[w];
+      atomicAdd(sum_lse, t);
+    }
+  }
+}
+
+// Responsibilities r = exp(logit - lse) written ALREADY SPLIT into the BF16 (b1 | b2) operand tiles the
+// weighted-statistics kernel feeds to the tensor core (weighted_pairs_sm100.cu, kMode 2): per slice of 256
+// components and per 16-row stage one 16 KB image [b1 | b2], each [64-component block (4)][8-row group (2)]
+// [8 rows x 128 B, 16-byte chunks XOR-swizzled with the row].  Same single pass as the log-softmax: K = 256 ITERS2
+// floats per row in registers, lane l holds components 128 i + 4 l .. + 3.  Rows n .. 32 ceil(n / 32) - 1 are written as
+// zeros (they are operand rows of the last MMAs).
+template <int ITERS>      // K = 128 * ITERS, ITERS even
+__global__ void __launch_bounds__(256)
+softmax_rows_split_kernel(const float* __restrict__ logits, int64_t n, uint8_t* __restrict__ rsplit,
+                          float* __restrict__ lse_out, double* __restrict__ sum_lse) {
+  constexpr int K = 128 * ITERS;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t stages = 2 * ((n + 31) / 32);       // = weighted_pairs_split_stages(n): an even number of 16-row images
+  const int64_t n_pad = stages * 16;
+  double lse_acc = 0.0;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_in_block; row < n_pad;
+       row += warps_total) {
+    float4 v[ITERS];
+    float lse = 0.f;
+    if (row < n) {
+      const float4* src = reinterpret_cast<const float4*>(logits + row * K);
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) v[i] = __ldcs(src + i * 32 + lane);
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+      const float row_max = warp_max(m);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        v[i].x = __expf(v[i].x - row_max); v[i].y = __expf(v[i].y - row_max);
+        v[i].z = __expf(v[i].z - row_max); v[i].w = __expf(v[i].w - row_max);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      s = warp_sum(s);
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        v[i].x *= inv; v[i].y *= inv; v[i].z *= inv; v[i].w *= inv;
+      }
+      lse = row_max + logf(s);
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int64_t stage = row >> 4;
+    const int kk = static_cast<int>(row & 15);
+    const uint32_t in_tile = (lane >> 4) * 2048 + (kk >> 3) * 1024 + (kk & 7) * 128 +
+                             ((((lane & 15) >> 1) ^ (kk & 7)) << 4) + (lane & 1) * 8;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i].x, v[i].y);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[i].z, v[i].w);
+      const uint32_t h0 = *reinterpret_cast<uint32_t*>(&p0), h1 = *reinterpret_cast<uint32_t*>(&p1);
+      __nv_bfloat162 q0 = __floats2bfloat162_rn(v[i].x - __uint_as_float(h0 << 16), v[i].y - __uint_as_float(h0 & 0xFFFF0000u));
+      __nv_bfloat162 q1 = __floats2bfloat162_rn(v[i].z - __uint_as_float(h1 << 16), v[i].w - __uint_as_float(h1 & 0xFFFF0000u));
+      uint8_t* tile = rsplit + ((static_cast<int64_t>(i >> 1) * stages + stage) << 14) + (i & 1) * 4096 + in_tile;
+      *reinterpret_cast<uint2*>(tile) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(tile + 8192) = make_uint2(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1));
+    }
+    if (lane == 0 && row < n) {
       if (lse_out != nullptr) lse_out[row] = lse;
       lse_acc += static_cast<double>(lse);
     }
@@ -201,6 +281,30 @@ int launch_logsoftmax_rows(const float* logits, int64_t n, int k, float* log_res
       logsoftmax_rows_any_kernel<false><<<grid, threads, 0, stream>>>(logits, n, k, log_resp, lse, sum_lse);
     BB_CHECK_LAUNCH("logsoftmax_rows_any_kernel");
   }
+  return BB_OK;
+}
+
+int launch_softmax_rows_split(const float* logits, int64_t n, int k, void* rsplit, float* lse, double* sum_lse,
+                              cudaStream_t stream) {
+  if (k < 256 || k % 256 != 0 || k > 1024 || reinterpret_cast<uintptr_t>(logits) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(rsplit) % 16 != 0) {
+    set_error("softmax_rows_split: needs k in {256, 512, 768, 1024} and 16-byte aligned buffers (got k=%d)", k);
+    return BB_ERR_UNSUPPORTED;
+  }
+  if (sum_lse != nullptr) BB_CUDA_OK(cudaMemsetAsync(sum_lse, 0, sizeof(double), stream));
+  if (n == 0) return BB_OK;
+  const int threads = 256, warps = threads / 32;
+  const int64_t want = ((n + 31) / 32 * 32 + warps - 1) / warps;
+  const int64_t cap = static_cast<int64_t>(std::max(1, device_sm_count())) * 8;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min(want, cap)));
+  uint8_t* out = static_cast<uint8_t*>(rsplit);
+  switch (k / 128) {
+    case 2: softmax_rows_split_kernel<2><<<grid, threads, 0, stream>>>(logits, n, out, lse, sum_lse); break;
+    case 4: softmax_rows_split_kernel<4><<<grid, threads, 0, stream>>>(logits, n, out, lse, sum_lse); break;
+    case 6: softmax_rows_split_kernel<6><<<grid, threads, 0, stream>>>(logits, n, out, lse, sum_lse); break;
+    default: softmax_rows_split_kernel<8><<<grid, threads, 0, stream>>>(logits, n, out, lse, sum_lse); break;
+  }
+  BB_CHECK_LAUNCH("softmax_rows_split_kernel");
   return BB_OK;
 }
 
@@ -345,7 +449,7 @@ int launch_weighted_stats(const float* x, const float* r, int64_t n, int d, int 
 int64_t weighted_stats_auto_workspace(int64_t n, int d, int k) {
   int64_t need = 256;
   if (d >= 4 && d <= 64 && d % 4 == 0 && k % 4 == 0 && n > 0) need = std::max(need, weighted_tc_workspace(n, k));
-  if (d >= 8 && d <= 64 && d % 8 == 0 && k >= 4 && k <= 256 && k % 4 == 0 && n > 0)
+  if (d >= 8 && d <= 64 && d % 8 == 0 && k >= 4 && k <= 4096 && k % 4 == 0 && n > 0)
     need = std::max(need, weighted_pairs_workspace(n, d, k));
   return need;
 }

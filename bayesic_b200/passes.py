@@ -114,18 +114,26 @@ class GmmStep(object):
         return U.float().contiguous(), t.float().contiguous(), c.float().contiguous()
 
     @staticmethod
-    def local_step(X, U, t, c, materialise=True):
+    def local_step(X, U, t, c, materialise=None):
         """The whole local step from WHITENED parameters (``whiten`` once per global update, or the
-        ``U, t, c`` that ``updates.gmm_global_update`` emits), device kernels only:
+        ``U, t, c`` that ``updates.gmm_global_update`` emits), three device kernels either way:
 
-        ``materialise=True`` (default, the faster route): logits -> responsibilities in place (one pass: row
-        log-sum-exp and r = exp(logit - lse), ``bb_softmax_rows``) -> {N_k, sum r x, sum r x x^T}; three kernels,
-        the N x K buffer is written twice.  ``materialise=False``: logits + row log-sum-exp, then the statistics
-        with r formed inside the operand conversion (two kernels, R never written, 2 GB less traffic per 2 Mi
-        rows) -- but every column-tile CTA of the statistics kernel then re-evaluates the exponentials of its row
-        range (10 x at D = 64), which costs more than the extra pass saves (measured at 2 Mi rows, K = 256:
-        16.2 ms against 14.7 ms)."""
-        if materialise:
+        default where the shapes allow (K in {256, 512, 768, 1024}, D % 8 == 0): logits -> responsibilities
+        written directly as the statistics kernel's BF16 operand tiles (``bb_softmax_rows_split``: the row pass
+        that finds the log-sum-exp also normalises and splits, same bytes as float32 R) -> statistics
+        (``bb_suffstats_weighted_split``, which bulk-copies R's tiles and converts only X (x) X);
+        ``materialise=True``: logits -> float32 responsibilities in place (``bb_softmax_rows``) -> statistics
+        (every column-tile CTA converts R again: the converters bound that kernel);
+        ``materialise=False``: logits + row log-sum-exp, then the statistics with r = exp(logit - lse) formed
+        inside the operand conversion (two kernels, R never written -- and the exponentials re-evaluated by each of
+        the ten column-tile CTAs of a row range: the slowest of the three)."""
+        d, k = X.shape[1], U.shape[0]
+        if materialise is None and stats.split_responsibilities_supported(d, k):
+            logits, _, _ = stats.mixture_logits(X, U, t, c, want_lse=False, want_sum=False, upper_triangular=True)
+            rsplit, lse, sum_lse = stats.responsibilities_split(logits)
+            nk, rx, rxx = stats.weighted_suffstats_split(X, rsplit, k)
+            return {'logits': logits, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
+        if materialise is None or materialise:
             logits, _, _ = stats.mixture_logits(X, U, t, c, want_lse=False, want_sum=False, upper_triangular=True)
             resp, lse, sum_lse = stats.responsibilities(logits, out=logits)          # in place
             nk, rx, rxx = stats.weighted_suffstats(X, resp)
@@ -144,21 +152,20 @@ class GmmStep(object):
 
     def __call__(self, X, Ak, bk, ck, fused=True, want_log_resp=True):
         """Local step from (A_k, b_k, c_k).  Every per-minibatch operation is a device kernel of this
-        library: the shapes the tcgen05 kernels serve take ``local_step`` (when the log-responsibilities
-        themselves are asked for: logits, in-place log-softmax, statistics with r = exp(log r) formed in the
-        operand conversion); other
+        library: the shapes the tcgen05 kernels serve take ``local_step`` (plus the in-place row normalisation
+        of the logits when the log-responsibilities themselves are asked for); other
         shapes take the compiled einsum plan, the log-softmax kernel, a compiled ``exp`` and the generic
         weighted-statistics kernel."""
-        import torch
         d, k = X.shape[1], Ak.shape[0]
         if fused and stats.mixture_logits_supported(d, k) and d % 8 == 0 and k <= 4096 and k % 4 == 0:
+            U, t, c = self._whitened(Ak, bk, ck)
             if not want_log_resp:
-                return self.local_step(X, *self._whitened(Ak, bk, ck))
-            logits, _, _ = stats.mixture_logits(X, *self._whitened(Ak, bk, ck), want_lse=False, want_sum=False,
-                                               upper_triangular=True)
-            log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place
-            nk, rx, rxx = stats.weighted_suffstats_from_logits(X, log_resp, torch.zeros_like(lse))
-            return {'log_resp': log_resp, 'lse': lse, 'sum_lse': sum_lse, 'nk': nk, 'rx': rx, 'rxx': rxx}
+                return self.local_step(X, U, t, c)
+            # a route that keeps the logits: the pre-split one where the shapes allow, else r formed in the kernel
+            out = self.local_step(X, U, t, c, None if stats.split_responsibilities_supported(d, k) else False)
+            logits = out.pop('logits')
+            out['log_resp'], _, _ = stats.log_responsibilities(logits, want_lse=False, want_sum=False, out=logits)
+            return out
         logits = self.logits_fn(X=X, Ak=Ak, bk=bk, ck=ck)
         log_resp, lse, sum_lse = stats.log_responsibilities(logits, out=logits)     # in place
         nk, rx, rxx = stats.weighted_suffstats(X, self.exp_fn(LR=log_resp))

@@ -18,7 +18,7 @@ import numpy as np
 from .backend import library as L
 
 __all__ = ['gaussian_suffstats', 'gaussian_expected_loglik', 'gaussian_suffstats_loglik', 'log_responsibilities',
-           'responsibilities',
+           'responsibilities', 'responsibilities_split', 'weighted_suffstats_split', 'split_responsibilities_supported',
            'weighted_suffstats', 'regression_suffstats', 'row_projection', 'column_projection',
            'logistic_reparam_stats', 'logistic_reparam_supported', 'mixture_logits',
            'mixture_logits_supported', 'weighted_suffstats_from_logits', 'launch_count']
@@ -207,6 +207,52 @@ def responsibilities(logits, want_lse=True, want_sum=True, out=None):
         L.check(lib.bb_softmax_rows(logits.data_ptr(), n, k, resp.data_ptr(), lse.data_ptr() if want_lse else None,
                                     total.data_ptr() if want_sum else None, _stream(dev)), 'bb_softmax_rows')
     return resp, lse, total
+
+
+def split_responsibilities_supported(d, k):
+    """Shapes the pre-split route (``responsibilities_split`` + ``weighted_suffstats_split``) serves."""
+    return k in (256, 512, 768, 1024) and d % 8 == 0 and 8 <= d <= 64
+
+
+def responsibilities_split(logits, want_lse=True, want_sum=True):
+    """``r = exp(logits - logsumexp(logits, axis=1))`` written directly as the error-compensated BF16 operand tiles
+    of the weighted-statistics kernel (``bb_softmax_rows_split``; opaque uint8 tensor, same bytes as float32 R).
+    Returns ``(rsplit, lse[n] float32 | None, sum_lse float64[1] | None)``."""
+    torch = _torch()
+    lib = L.load()
+    logits = _as_device_f32(logits, 2, 'logits')
+    n, k = logits.shape
+    dev = logits.device
+    with torch.cuda.device(dev):
+        nbytes = int(lib.bb_softmax_rows_split_bytes(n, k))
+        if nbytes <= 0 and n > 0:
+            raise ValueError("responsibilities_split: needs k in {256, 512, 768, 1024} (got %d)" % k)
+        rsplit = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        lse = torch.empty(n, dtype=torch.float32, device=dev) if want_lse else None
+        total = torch.empty(1, dtype=torch.float64, device=dev) if want_sum else None
+        L.check(lib.bb_softmax_rows_split(logits.data_ptr(), n, k, rsplit.data_ptr(), lse.data_ptr() if want_lse else None,
+                                          total.data_ptr() if want_sum else None, _stream(dev)), 'bb_softmax_rows_split')
+    return rsplit, lse, total
+
+
+def weighted_suffstats_split(X, rsplit, k):
+    """``(N_k, sum_rx, sum_rxx)`` from ``X[n, d]`` and the pre-split responsibilities of ``responsibilities_split``."""
+    torch = _torch()
+    lib = L.load()
+    X = _as_device_f32(X, 2, 'X')
+    n, d = X.shape
+    dev = X.device
+    if rsplit.numel() < int(lib.bb_softmax_rows_split_bytes(n, k)):
+        raise ValueError("weighted_suffstats_split: rsplit does not hold %d rows of %d components" % (n, k))
+    with torch.cuda.device(dev):
+        nk = torch.empty(k, dtype=torch.float64, device=dev)
+        rx = torch.empty((k, d), dtype=torch.float64, device=dev)
+        rxx = torch.empty((k, d, d), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.bb_suffstats_weighted_workspace(n, d, k), dev)
+        L.check(lib.bb_suffstats_weighted_split(X.data_ptr(), rsplit.data_ptr(), n, d, k, nk.data_ptr(), rx.data_ptr(),
+                                                rxx.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+                'bb_suffstats_weighted_split')
+    return nk, rx, rxx
 
 
 def weighted_suffstats(X, R):

@@ -154,10 +154,9 @@ class GmmVmp(object):
         if self.state is None:
             raise RuntimeError("GmmVmp.initialise(...) first")
         prev = self.state
-        logits, _, _ = stats.mixture_logits(X_local, prev['U'], prev['t'], prev['c'], want_lse=False, want_sum=False,
-                                            upper_triangular=True)
-        resp, lse, sum_lse = stats.responsibilities(logits, out=logits)       # in place; see passes.GmmStep.local_step
-        nk, rx, rxx = stats.weighted_suffstats(X_local, resp)
+        from .passes import GmmStep
+        out = GmmStep.local_step(X_local, prev['U'], prev['t'], prev['c'])
+        nk, rx, rxx, sum_lse = out['nk'], out['rx'], out['rxx'], out['sum_lse']
         views = self.layout.views(self.packed)
         views['nk'].copy_(nk)
         views['rx'].copy_(rx)

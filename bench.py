@@ -220,9 +220,9 @@ def time_other_configs(dev):
         U, t, c = step.whiten(Ak, bk, ck)                     # once per global update, not per minibatch
         ms = timed(lambda: step.local_step(X, U, t, c), reps=5)
         issued_per_pt = P.gmm_issued_flops_per_row(d, k, upper_triangular=True)
-        out['cfg3'] = {"workload": "GMM VMP local step, three kernels (whitened logits on tcgen05; responsibilities in "
-                                   "place, one pass with the row log-sum-exp; weighted statistics on tcgen05): "
-                                   "X[2 Mi, 64] f32, K = 256",
+        out['cfg3'] = {"workload": "GMM VMP local step, three kernels (whitened logits on tcgen05 CTA pairs; "
+                                   "responsibilities written as BF16 operand tiles in one pass with the row "
+                                   "log-sum-exp; weighted statistics on tcgen05 CTA pairs): X[2 Mi, 64] f32, K = 256",
                        "ms_per_pass": ms, "points_per_s": n / (ms * 1e-3),
                        "roofline": tensor_roofline(issued_per_pt, 2195456.0, n, ms,
                                                    "useful = SURVEY 8(d) minimal 2 195 456 flop/pt; issued = BF16x3 MMAs: "

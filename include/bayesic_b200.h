@@ -289,6 +289,21 @@ BB_API int bb_suffstats_weighted_from_logits(const float* X, const float* logits
                                       double* Nk, double* sum_rx, double* sum_rxx,
                                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same statistics with the responsibilities handed over ALREADY in the tensor core's operand format: the
+ * statistics kernel is bound by its operand conversion, and every one of its ten column-tile CTAs per row range
+ * converts the same rows of R -- so the row pass that normalises the logits writes r = exp(logits - lse) split
+ * into error-compensated BF16 (b1 | b2) operand tiles instead of float32 (same bytes), and the statistics kernel
+ * bulk-copies them (cp.async.bulk) and only forms the X (x) X operand.  Same value as
+ * bb_logsoftmax_rows + exp + bb_suffstats_weighted (plans of algebra.py:527-765 over the elementwise chain of
+ * :1435-1448).  Needs k in {256, 512, 768, 1024} (slices of 256 components), d % 8 == 0, d <= 64.
+ * rsplit: device buffer of bb_softmax_rows_split_bytes(n, k) bytes = 4 k * 32 ceil(n / 32). */
+BB_API int64_t bb_softmax_rows_split_bytes(int64_t n, int32_t k);
+BB_API int bb_softmax_rows_split(const float* logits, int64_t n, int32_t k, void* rsplit, float* lse,
+                          double* sum_lse, void* stream);
+BB_API int bb_suffstats_weighted_split(const float* X, const void* rsplit, int64_t n, int32_t d, int32_t k,
+                                double* Nk, double* sum_rx, double* sum_rxx,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- parameter-space update steps either side of the data pass ----
  * The reference names these algorithms in prose only (README.md:30-37 VMP, :47-51
  * reparameterised gradients, :69-80 SVI).  All pointers are device pointers; nothing here

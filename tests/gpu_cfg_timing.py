@@ -63,14 +63,14 @@ def cfg3():
     ms = timeit(lambda: step(X, Ak, bk, ck, want_log_resp=False), reps=2)
     print('cfg3 GmmStep without materialising R (N = %d): %.2f ms/step  %.2f M rows/s' % (n, ms, n / ms / 1e3), flush=True)
     U, t, c = step.whiten(Ak, bk, ck)
-    for materialise in (True, False):
+    for materialise in (None, True, False):
         ms = timeit(lambda: step.local_step(X, U, t, c, materialise=materialise), reps=3)
         print('cfg3 local_step(materialise=%s) (N = %d): %.2f ms/step  %.2f M rows/s' % (materialise, n, ms, n / ms / 1e3), flush=True)
     ms = timeit(lambda: S.mixture_logits(X, U, t, c, upper_triangular=True), reps=3)
     print('  mixture logits kernel: %.2f ms  %.1f M rows/s  %.0f TFLOP/s issued bf16'
           % (ms, n / ms / 1e3, 3 * 2.0 * k * d * d * n / ms / 1e9), flush=True)
     R = torch.softmax(torch.randn(n, k, device='cuda'), 1)
-    ms = timeit(lambda: S.weighted_suffstats(X, R), reps=2)
+    ms = timeit(lambda: S.weighted_suffstats(X, R), reps=5)
     print('  weighted stats: %.2f ms' % ms, flush=True)
     ms = timeit(lambda: S.log_responsibilities(R), reps=5)
     print('  log-softmax: %.2f ms' % ms, flush=True)
@@ -78,6 +78,11 @@ def cfg3():
     print('  softmax (responsibilities): %.2f ms' % ms, flush=True)
     lg = torch.randn(n, k, device='cuda')
     lse = torch.logsumexp(lg, 1)
+    ms = timeit(lambda: S.responsibilities_split(lg), reps=5)
+    print('  softmax -> pre-split operand tiles: %.2f ms' % ms, flush=True)
+    rsplit, _, _ = S.responsibilities_split(lg)
+    ms = timeit(lambda: S.weighted_suffstats_split(X, rsplit, k), reps=5)
+    print('  weighted stats from pre-split tiles: %.2f ms' % ms, flush=True)
     ms = timeit(lambda: S.weighted_suffstats_from_logits(X, lg, lse), reps=2)
     print('  weighted stats from logits: %.2f ms' % ms, flush=True)
 

@@ -179,9 +179,35 @@ def test_cfg3_gmm_vmp_step_on_the_tensor_core_kernels():
         assert abs(float(got['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
 
 
+def test_cfg3_local_step_at_k256_uses_pre_split_responsibilities():
+    """K = 256 (BASELINE cfg3's extent): the default local step writes the responsibilities as operand tiles."""
+    import torch
+    rng = np.random.RandomState(18)
+    n, d, k = 7000, 64, 256
+    centers = rng.randn(k, d) * 1.5
+    X = (centers[rng.randint(k, size=n)] + rng.randn(n, d)).astype(np.float32)
+    log_pi = np.log(rng.dirichlet(np.ones(k)))
+    m = centers + rng.randn(k, d) * 0.05
+    beta, nu = rng.rand(k) * 5 + 1, d + 2 + rng.rand(k) * 5
+    W = np.stack([np.linalg.inv(_spd(rng, d)) / nu[j] for j in range(k)])
+    want = O.gmm_vmp_step(X, log_pi, m, beta, W, nu)
+    step = P.GmmStep()
+    Ak, bk, ck = (torch.from_numpy(a).cuda() for a in step.expectations(log_pi, m, beta, W, nu))
+    Xd = torch.from_numpy(X).cuda()
+    outs = [step(Xd, Ak, bk, ck, want_log_resp=False), step.local_step(Xd, *step.whiten(Ak, bk, ck), materialise=True)]
+    assert 'resp' not in outs[0] and 'logits' in outs[0]          # pre-split route: no float32 R
+    for out in outs:
+        _close(out['nk'], want['nk'], rtol=1e-4, scale_atol=2e-5)
+        _close(out['rx'], want['rx'], rtol=1e-4, scale_atol=1e-4)
+        _close(out['rxx'], want['rxx'], rtol=1e-4, scale_atol=1e-4)
+        assert abs(float(out['sum_lse']) - want['sum_lse']) <= 1e-4 * abs(want['sum_lse'])
+    log_resp = (outs[0]['logits'] - outs[0]['lse'][:, None]).cpu().numpy()
+    np.testing.assert_allclose(log_resp, want['log_resp'], rtol=1e-4, atol=3e-3)
+
+
 def test_cfg3_local_step_both_routes():
-    """``local_step`` from whitened parameters: the default route (logits -> responsibilities in place ->
-    statistics; ``want_log_resp=False`` of ``GmmStep.__call__``) and ``materialise=False`` (logits + lse, r formed
+    """``local_step`` from whitened parameters at a K the pre-split route does not serve: ``materialise=True``
+    (logits -> responsibilities in place -> statistics) and ``materialise=False`` (logits + lse, r formed
     inside the statistics kernel, R never written); same statistics as the oracle's full step either way."""
     import torch
     rng = np.random.RandomState(8)
@@ -197,7 +223,7 @@ def test_cfg3_local_step_both_routes():
     step = P.GmmStep()
     Ak, bk, ck = (torch.from_numpy(a).cuda() for a in step.expectations(log_pi, m, beta, W, nu))
     Xd = torch.from_numpy(X).cuda()
-    got = step(Xd, Ak, bk, ck, want_log_resp=False)
+    got = step.local_step(Xd, *step.whiten(Ak, bk, ck), materialise=True)
     assert 'log_resp' not in got and 'logits' not in got
     np.testing.assert_allclose(got['resp'].cpu().numpy(), np.exp(want['log_resp']), rtol=2e-3, atol=1e-6)
     np.testing.assert_allclose(got['resp'].sum(1).cpu().numpy(), 1.0, rtol=1e-5)

@@ -209,6 +209,49 @@ def test_weighted_suffstats(n, d, k):
                                atol=1e-6 * np.abs(got).max())               # symmetric
 
 
+@pytest.mark.parametrize('n,d,k', [(4096, 64, 256), (1, 64, 256), (1031, 32, 256), (5000, 16, 512), (2000, 64, 1024),
+                                   (40000, 64, 256)])
+def test_weighted_suffstats_from_pre_split_responsibilities(n, d, k):
+    """bb_softmax_rows_split writes r = softmax(logits) as the statistics kernel's BF16 operand tiles and
+    bb_suffstats_weighted_split consumes them: same statistics as the float64 oracle on exp(log-softmax)."""
+    import torch
+    rng = np.random.RandomState(n + d + k)
+    X = rng.randn(n, d).astype(np.float32)
+    Lg = (rng.randn(n, k) * 2.5).astype(np.float32)
+    rsplit, lse, tot = S.responsibilities_split(torch.from_numpy(Lg).cuda())
+    ref_lr, ref_lse = O.log_responsibilities(Lg)
+    np.testing.assert_allclose(lse.cpu().numpy(), ref_lse, rtol=RTOL, atol=2e-6)
+    assert abs(float(tot) - ref_lse.sum()) <= RTOL * max(1.0, abs(ref_lse.sum()))
+    nk, rx, rxx = S.weighted_suffstats_split(torch.from_numpy(X).cuda(), rsplit, k)
+    rnk, rrx, rrxx = O.weighted_suffstats(X, np.exp(ref_lr))
+    _close(nk.cpu().numpy(), rnk)
+    _close(rx.cpu().numpy(), rrx, scale_atol=1e-5)
+    _close(rxx.cpu().numpy(), rrxx, scale_atol=1e-5)
+    # and the float32-R route gives the same numbers to the level of the BF16 split
+    r32, _, _ = S.responsibilities(torch.from_numpy(Lg).cuda())
+    nk2, rx2, rxx2 = S.weighted_suffstats(torch.from_numpy(X).cuda(), r32)
+    np.testing.assert_allclose(rxx.cpu().numpy(), rxx2.cpu().numpy(), rtol=1e-4, atol=1e-5 * float(rxx2.abs().max()))
+
+
+def test_pre_split_responsibilities_exact_on_one_hot_rows():
+    """One-hot responsibilities (a logit 200 above the rest) and small-integer data make every product and sum
+    exact: a wrong byte in the operand-tile layout shows up as a whole-number error."""
+    import torch
+    n, d, k = 3000, 64, 512
+    rng = np.random.RandomState(4)
+    z = rng.randint(0, k, size=n)
+    Lg = np.full((n, k), -100.0, dtype=np.float32)
+    Lg[np.arange(n), z] = 100.0
+    X = rng.randint(-4, 5, size=(n, d)).astype(np.float32)
+    rsplit, _, _ = S.responsibilities_split(torch.from_numpy(Lg).cuda(), want_lse=False, want_sum=False)
+    nk, rx, rxx = S.weighted_suffstats_split(torch.from_numpy(X).cuda(), rsplit, k)
+    R = np.zeros((n, k)); R[np.arange(n), z] = 1.0
+    rnk, rrx, rrxx = O.weighted_suffstats(X, R)
+    assert np.array_equal(nk.cpu().numpy(), rnk)
+    assert np.array_equal(rx.cpu().numpy(), rrx)
+    assert np.array_equal(rxx.cpu().numpy(), rrxx)
+
+
 def test_weighted_suffstats_sum_over_components_is_the_plain_statistic():
     # responsibilities sum to one per row => sum_k Srxx[k] = S2, sum_k Srx[k] = S1, sum_k Nk = n
     import torch
