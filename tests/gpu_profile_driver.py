@@ -1,5 +1,5 @@
 """Developer driver for ncu: runs ONE of the hot kernels a few times at (scaled) BASELINE extents.
-    python tests/gpu_profile_driver.py gram|rowproj|colproj|logistic|weighted|logits|suffstats|logsoftmax"""
+    python tests/gpu_profile_driver.py gram|rowproj|colproj|logistic|weighted|weighted_split|softmax_split|logits|suffstats|logsoftmax"""
 import os
 import sys
 
@@ -35,6 +35,14 @@ def main(which):
             t = torch.randn(k, d, device='cuda')
             c = torch.randn(k, device='cuda')
             fn = lambda: S.mixture_logits(X, U, t, c, upper_triangular=True)
+    elif which == 'weighted_split':          # cfg3 at 1 Mi rows, responsibilities pre-split into operand tiles (CTA pairs)
+        n, d, k = 1 << 20, 64, 256
+        X = torch.randn(n, d, device='cuda')
+        rsplit, _, _ = S.responsibilities_split(torch.randn(n, k, device='cuda') * 2)
+        fn = lambda: S.weighted_suffstats_split(X, rsplit, k)
+    elif which == 'softmax_split':
+        Lg = torch.randn(1 << 21, 256, device='cuda') * 3
+        fn = lambda: S.responsibilities_split(Lg)
     elif which == 'suffstats':               # cfg2: N = 16 Mi, D = 64
         X = torch.randn(1 << 24, 64, device='cuda')
         fn = lambda: S.gaussian_suffstats(X)
