@@ -64,3 +64,31 @@ def test_batch_axis_order_is_part_of_the_key():
     a, b = evaluate_descriptor(low.nodes, low.outputs, arrays)
     np.testing.assert_allclose(a, np.einsum('abk,abk->ab', p, q), rtol=1e-12)
     np.testing.assert_allclose(b, np.einsum('abk,abk->ba', p, q), rtol=1e-12)
+
+
+def test_host_call_signature_is_shapes_and_scalars():
+    """``CompiledPlan._host_signature`` (the key of the persistent-buffer / CUDA-graph cache of numpy-in calls):
+    array inputs contribute their shapes, rank-0 inputs their values; a wrong rank or integers beyond 2**24 give
+    ``None`` so that the general path reports them."""
+    import numpy as np
+    import bayesic_b200.algebra as A
+    from bayesic_b200.backend.compiled import CompiledPlan
+    X, s = A.var('X', 2), A.var('s', 0)
+    plan = CompiledPlan([A.sum(X * s, axis=0)])
+    a = plan._host_signature({'X': np.zeros((5, 3), np.float32), 's': 2.0})
+    b = plan._host_signature({'X': np.ones((5, 3), np.float32), 's': 2.0})
+    assert a == b and dict(a)['X'] == (5, 3) and dict(a)['s'] == 2.0
+    assert plan._host_signature({'X': np.zeros((6, 3), np.float32), 's': 2.0}) != a
+    assert plan._host_signature({'X': np.zeros((5, 3), np.float32), 's': 3.0}) != a
+    assert plan._host_signature({'X': np.zeros(5, np.float32), 's': 2.0}) is None
+    counts = A.var('c', 1, dtype='int64')
+    iplan = CompiledPlan([A.sum(counts, axis=0)])
+    assert iplan._host_signature({'c': np.array([1, 2, 3])}) is not None
+    assert iplan._host_signature({'c': np.array([1, (1 << 24) + 1])}) is None
+
+
+def test_split_responsibility_shapes():
+    import bayesic_b200.stats as S
+    assert S.split_responsibilities_supported(64, 256) and S.split_responsibilities_supported(16, 1024)
+    assert not S.split_responsibilities_supported(64, 128) and not S.split_responsibilities_supported(12, 256)
+    assert not S.split_responsibilities_supported(64, 260)
