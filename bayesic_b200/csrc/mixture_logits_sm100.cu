@@ -1,5 +1,5 @@
 // Gaussian-mixture expected log-densities (the "logits" of the responsibility softmax) on tcgen05
-// (D in {16, 32, 48, 64}, K % 4 == 0):
+// (D % 8 == 0, D <= 64 -- the feature axis is zero-padded to a multiple of 16 on chip --, K % 4 == 0):
 //     logit[n, k] = c_k - 1/2 || U_k x_n - t_k ||^2          (+ lse[n] = logsumexp_k logit[n, :])
 // i.e.  c'_k + x.b_k - 1/2 x^T A_k x  with A_k = U_k^T U_k (Cholesky), t_k = U_k m_k -- the
 // expression  dot(X, bk.T) + (-0.5) * einsum(X_nd Ak_kde X_ne) + ck  that a user of the reference
@@ -218,7 +218,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mixture
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_cg = (p.k + 15) / 16;          // component groups of 16
-  const int k_steps = p.d / 16;              // = number of j ranges with data
+  const int k_steps = (p.d + 15) / 16;       // = number of j ranges with data (d % 16 == 8: the last one is half zeros)
   const int n_seq = n_cg * k_steps;          // MMA tiles per row tile, in order (cg, jr)
   const int64_t n_ptiles = (p.n + 2 * kTileRows - 1) / (2 * kTileRows);      // 256-row pair tiles
   const int64_t my_tiles = n_ptiles > pair ? (n_ptiles - pair + n_pairs - 1) / n_pairs : 0;
@@ -437,6 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mixture
     const int wi = warp - kConvWarp0;
     const int sub = lane >> 4, c4 = lane & 15;
     const bool col_ok = c4 * 4 < p.d;
+    const bool col_stored = c4 * 4 < 16 * k_steps;      // features d .. 16 k_steps - 1 are operand columns too: zeros
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int tb = static_cast<int>(t & 1);
       const int64_t tile = (pair + t * n_pairs) * 2 + rank;
@@ -451,7 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mixture
         }
         // a tile lasts ~100k cycles: back off between polls instead of spinning over the epilogue warps
         if (hf == 0) ptx::mbar_wait_sleep(&sm.a_empty[tb], (static_cast<uint32_t>(t >> 1) & 1) ^ 1, 512);
-        if (col_ok) {
+        if (col_stored) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = wi * 32 + hf * 16 + 2 * i + sub;
@@ -494,7 +495,7 @@ int logits_grid(int64_t n) {           // CTAs (two per pair)
 }  // namespace
 
 bool mixture_logits_supported(int64_t n, int d, int k, const void* x) {
-  return n > 0 && d >= 16 && d <= 64 && d % 16 == 0 && k >= 4 && k % 4 == 0 && k <= 4096 &&
+  return n > 0 && d >= 8 && d <= 64 && d % 8 == 0 && k >= 4 && k % 4 == 0 && k <= 4096 &&
          reinterpret_cast<uintptr_t>(x) % 16 == 0;
 }
 

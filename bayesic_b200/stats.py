@@ -372,7 +372,7 @@ def logistic_reparam_stats(X, y, W):
 
 def mixture_logits_supported(d, k):
     """Shapes the tcgen05 mixture-logit kernel serves."""
-    return d in (16, 32, 48, 64) and k % 4 == 0 and 4 <= k <= 4096
+    return d % 8 == 0 and 8 <= d <= 64 and k % 4 == 0 and 4 <= k <= 4096
 
 
 def mixture_logits(X, U, t, c, want_lse=True, want_sum=True, upper_triangular=False):

@@ -259,7 +259,8 @@ BB_API int bb_softmax_rows(const float* logits, int64_t n, int32_t k,
  *   sum_lse = sum_n lse[n] (float64).  U [k,d,d], t [k,d], c [k], logits [n,k], lse [n]: device
  *   float32.  This is the value of the user expression dot(X, bk.T) - 0.5 einsum(X, Ak, X) + ck
  *   (the reference's plan for it is a batched _tensordot whose evaluation is broken,
- *   algebra.py:1370-1373, :1380).  Needs d in {16,32,48,64}, k % 4 == 0 (BB_ERR_UNSUPPORTED otherwise).
+ *   algebra.py:1370-1373, :1380).  Needs d % 8 == 0, 8 <= d <= 64 (the feature axis is zero-padded to a
+ *   multiple of 16 on chip), k % 4 == 0 (BB_ERR_UNSUPPORTED otherwise).
  *   upper_triangular != 0 promises U[k,j,i] == 0 for i < j (Cholesky factors): 10 of the 16 MMA
  *   K-steps at d = 64 are then skipped; with general factors pass 0. */
 BB_API int64_t bb_mixture_logits_workspace(int64_t n, int32_t d, int32_t k);

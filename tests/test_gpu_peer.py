@@ -307,3 +307,33 @@ def test_sharded_logistic_gradient_equals_the_unsharded_oracle():
     scale = np.linalg.norm(X.astype('f8'), axis=0)[:, None] * np.linalg.norm(resid, axis=0)[None, :]
     _scaled_close(got['G'], want_G, scale, 2e-5)
     assert float(got['count']) == float(sum(rows))
+
+
+def test_gaussian_pass_back_to_back_launches_do_not_interfere():
+    """Consecutive passes of one handle overlap (programmatic dependent launch: the next launch streams while the
+    previous launch's last CTA gathers, re-zeroes the accumulator block and writes the outputs) and share the
+    accumulator block, the ticket and two alternating tile counters.  400 launches back to back over three
+    different inputs, no synchronisation in between: the outputs after the last launch must be those of its input
+    alone, and the shared state must be clean for the launch after it."""
+    import torch
+    import bayesic_b200.stats as S
+    from bayesic_b200.parallel import GaussianPass
+    d = 64
+    dev = torch.device('cuda')
+    g = torch.Generator(device=dev).manual_seed(11)
+    Xs = [torch.randn(n, d, device=dev, generator=g) * s + m for n, s, m in ((300000, 1.3, 0.4), (40001, 0.7, -1.0), (128 * 148 * 4, 2.0, 0.1))]
+    e_lambda = torch.eye(d, dtype=torch.float64, device=dev) * 1.5
+    e_lambda_mu = torch.linspace(-1, 1, d, dtype=torch.float64, device=dev)
+    want = []
+    for X in Xs:
+        _, w1, w2, wll = S.gaussian_suffstats_loglik(X, e_lambda, e_lambda_mu, 0.3, -0.2)
+        want.append((w1.clone(), w2.clone(), wll.clone()))
+    p = GaussianPass(d, dev)
+    close = lambda u, v: torch.testing.assert_close(u, v, rtol=1e-12, atol=1e-12 * float(v.abs().max()))
+    for last in (0, 1, 2):
+        for i in range(400):
+            p.run(Xs[(i + last + 1) % 3], e_lambda, e_lambda_mu, 0.3, -0.2)
+        cnt, s1, s2, ll = p.run(Xs[last], e_lambda, e_lambda_mu, 0.3, -0.2)
+        p.check()
+        close(s1, want[last][0]), close(s2, want[last][1]), close(ll, want[last][2])
+        assert float(cnt) == float(Xs[last].shape[0])

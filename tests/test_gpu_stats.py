@@ -431,7 +431,8 @@ def test_projection_unsupported_shapes_fail_loudly():
 
 @pytest.mark.parametrize('triangular', [False, True], ids=['general', 'triangular'])
 @pytest.mark.parametrize('n,d,k', [(1, 64, 4), (127, 64, 8), (128, 64, 4), (129, 16, 12), (1000, 32, 8),
-                                   (5000, 48, 20), (20000, 64, 256), (4097, 64, 64), (3000, 64, 36)])
+                                   (5000, 48, 20), (20000, 64, 256), (4097, 64, 64), (3000, 64, 36),
+                                   (2000, 8, 8), (3000, 24, 12), (1500, 40, 16), (2500, 56, 8)])
 def test_mixture_logits(n, d, k, triangular):
     """Whitened Gaussian-mixture logits + row log-sum-exp vs float64.  The logits are O(1e2) in
     magnitude and come out of a float32 epilogue, hence the absolute term."""
