@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libbayesic_b200.so')
-SOURCES = ['runtime.cu', 'generic_kernels.cu', 'suffstats_sm100.cu', 'weighted_sm100.cu', 'weighted_pairs_sm100.cu', 'gram_sm100.cu', 'rowproj_sm100.cu', 'colproj_sm100.cu', 'logistic_fused2_sm100.cu', 'logistic_fused3_sm100.cu', 'mixture_logits_sm100.cu', 'mixture_kernels.cu',
+SOURCES = ['runtime.cu', 'generic_kernels.cu', 'suffstats_sm100.cu', 'weighted_sm100.cu', 'weighted_pairs_sm100.cu', 'gram_sm100.cu', 'rowproj_sm100.cu', 'colproj_sm100.cu', 'logistic_fused2_sm100.cu', 'mixture_logits_sm100.cu', 'mixture_kernels.cu',
            'stats_kernels.cu', 'update_kernels.cu', 'linalg_kernels.cu', 'p2p_reduce.cu', 'executor.cu', 'api.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--use_fast_math=false']

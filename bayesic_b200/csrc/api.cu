@@ -352,7 +352,7 @@ BB_API int64_t bb_logistic_reparam_workspace(int64_t n, int32_t d, int32_t s) {
   int64_t need = align_up(n * static_cast<int64_t>(s) * 4, 256) +
                  std::max(rowproj_tc_workspace(n, d, s), colproj_tc_workspace(n, d, s)) + 512;
   if (s == 64 && d >= 128 && d % 128 == 0 && d <= 512 && n > 0)
-    need = std::max(need, std::max(logistic_fused2_workspace(n, d, s), logistic_fused3_workspace(n, d, s)) + 512);
+    need = std::max(need, logistic_fused2_workspace(n, d, s) + 512);
   return need;
 }
 
@@ -381,10 +381,6 @@ BB_API int bb_logistic_reparam_pass(const float* X, const float* y, const float*
   static const bool unfused = getenv("BB_LOGISTIC_UNFUSED") != nullptr;
   // (the resident-tile design, logistic_fused2_sm100.cu; the first, W-resident design served the same shapes
   // 1.2x slower and was removed in round 2)
-  // BB_FUSED_V3=1: the CTA-pair design with two tiles in flight (logistic_fused3_sm100.cu; d in {256, 512})
-  static const bool fused_v3 = getenv("BB_FUSED_V3") != nullptr && atoi(getenv("BB_FUSED_V3")) != 0;
-  if (!unfused && fused_v3 && logistic_fused3_supported(n, d, s, X))
-    return launch_logistic_fused3(X, y, W, n, d, s, loglik, G, workspace, workspace_bytes, st);
   if (!unfused && logistic_fused2_supported(n, d, s, X))
     return launch_logistic_fused2(X, y, W, n, d, s, loglik, G, workspace, workspace_bytes, st);
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));

@@ -87,12 +87,6 @@ int64_t colproj_tc_workspace(int64_t n, int d, int q);
 int launch_colproj_tc(const float* x, const float* r, int64_t n, int d, int q, double* out, void* workspace,
                       int64_t workspace_bytes, cudaStream_t stream);
 
-// logistic_fused3_sm100.cu: the same pass on CTA pairs that split the feature axis (two tiles in flight; d in {256, 512})
-bool logistic_fused3_supported(int64_t n, int d, int s, const void* x);
-int64_t logistic_fused3_workspace(int64_t n, int d, int s);
-int launch_logistic_fused3(const float* x, const float* y, const float* w, int64_t n, int d, int s, double* loglik,
-                           double* g, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
-
 // logistic_fused2_sm100.cu: the whole reparameterised logistic pass in one kernel -- X read once, the X tile
 // resident (converted once), W streamed
 bool logistic_fused2_supported(int64_t n, int d, int s, const void* x);
