@@ -15,7 +15,8 @@ import numpy as np
 
 __all__ = ['shard_bounds', 'PackedStats', 'allreduce_packed', 'PeerComm', 'peer_comm_for', 'GaussianPass',
            'gaussian_suffstats_sharded',
-           'regression_suffstats_sharded', 'mixture_suffstats_sharded', 'logistic_reparam_sharded']
+           'regression_suffstats_sharded', 'mixture_suffstats_sharded', 'mixture_local_step_sharded',
+           'logistic_reparam_sharded']
 
 
 def shard_bounds(n, world_size, rank):
@@ -335,6 +336,20 @@ def mixture_suffstats_sharded(X_local, R_local, sum_lse_local=None, buffer=None,
     if sum_lse_local is not None:
         parts['sum_lse'] = sum_lse_local
     return _reduce_into(PackedStats.mixture(k, d), X_local.device, parts, n_local, buffer, group)
+
+
+def mixture_local_step_sharded(X_local, U, t, c, buffer=None, group=None):
+    """cfg3, the whole VMP local step on this rank's rows from the replicated whitened parameters
+    (``passes.GmmStep.local_step``: logits, responsibilities as operand tiles, statistics on CTA pairs where the
+    shapes allow) and one all-reduce of ``{nk, rx, rxx, sum_lse, count}``; the per-row outputs stay sharded."""
+    from .passes import GmmStep
+    n_local, d = X_local.shape
+    k = U.shape[0]
+    out = GmmStep.local_step(X_local, U, t, c)
+    parts = {'nk': out['nk'], 'rx': out['rx'], 'rxx': out['rxx'], 'sum_lse': out['sum_lse']}
+    reduced = _reduce_into(PackedStats.mixture(k, d), X_local.device, parts, n_local, buffer, group)
+    reduced['lse'] = out['lse']
+    return reduced
 
 
 def logistic_reparam_sharded(X_local, y_local, W, buffer=None, group=None):

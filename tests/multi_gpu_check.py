@@ -101,6 +101,26 @@ def main():
     report('cfg3 sharded {N_k, sum r x, sum r x x^T, sum lse}', e < 2e-5 and e_nk < 2e-5 and float(got['count']) == n,
            'cs err %.2e, N_k rel %.2e' % (e, e_nk))
     report('cfg3 sharded: replicated bit for bit', replicated(got['rxx']))
+    # cfg3, the whole local step at K = 256 (pre-split responsibilities, CTA-pair statistics kernel)
+    import bayesic_b200.passes as P
+    n, d, k = 1500 * world + 7, 64, 256
+    centres = rng.randn(k, d) * 1.5
+    X = (centres[rng.randint(k, size=n)] + rng.randn(n, d)).astype(np.float32)
+    log_pi = np.log(rng.dirichlet(np.ones(k)))
+    m, beta, nu = centres + 0.05 * rng.randn(k, d), rng.rand(k) * 5 + 1, d + 2 + rng.rand(k) * 5
+    Wk = np.stack([np.linalg.inv((lambda a: a @ a.T / d + np.eye(d))(rng.randn(d, d))) / nu[j] for j in range(k)])
+    want = O.gmm_vmp_step(X, log_pi, m, beta, Wk, nu)
+    step = P.GmmStep()
+    Ak, bk, ck = (torch.from_numpy(a).to(dev) for a in step.expectations(log_pi, m, beta, Wk, nu))
+    Uw, tw, cw = step.whiten(Ak, bk, ck)
+    lo, hi = PAR.shard_bounds(n, world, rank)
+    got = PAR.mixture_local_step_sharded(torch.from_numpy(X[lo:hi]).to(dev), Uw, tw, cw)
+    x2 = np.exp(want['log_resp']).T @ (X.astype('f8') ** 2)
+    e = scaled_err(got['rxx'], want['rxx'], np.sqrt(np.einsum('kd,ke->kde', x2, x2)))
+    e_lse = abs(float(got['sum_lse']) - want['sum_lse']) / abs(want['sum_lse'])
+    report('cfg3 sharded local step (logits -> operand tiles -> statistics)', e < 2e-5 and e_lse < 1e-5 and
+           float(got['count']) == n, 'cs err %.2e, sum lse rel %.2e' % (e, e_lse))
+    report('cfg3 sharded local step: replicated bit for bit', replicated(got['rxx']))
     # cfg5
     n, d, s = 2000 * world + 9, 512, 64
     X = rng.randn(n, d).astype(np.float32)
@@ -182,7 +202,13 @@ def main():
         R = torch.softmax(torch.randn(hi - lo, k, device=dev, generator=gen), dim=1)
         both('cfg3_weighted_stats_2Mi_x_64_K256', lambda: PAR.mixture_suffstats_sharded(X, R), n)
         timings['cfg3_weighted_stats_2Mi_x_64_K256']['local_only_ms'] = timed(lambda: S.weighted_suffstats(X, R))
-        del X, R
+        del R
+        Uw = (torch.eye(d, device=dev) * 1.2).repeat(k, 1, 1).contiguous()
+        tw = torch.randn(k, d, device=dev, generator=torch.Generator(device=dev).manual_seed(6))
+        cw = torch.randn(k, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        both('cfg3_local_step_2Mi_x_64_K256', lambda: PAR.mixture_local_step_sharded(X, Uw, tw, cw), n)
+        timings['cfg3_local_step_2Mi_x_64_K256']['local_only_ms'] = timed(lambda: P.GmmStep.local_step(X, Uw, tw, cw))
+        del X
         # the bare collectives on the three payloads
         for name, numel in (('allreduce_cfg3_payload', PAR.PackedStats.mixture(256, 64).numel),
                             ('allreduce_cfg4_payload', PAR.PackedStats.regression(1024).numel),
