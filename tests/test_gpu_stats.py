@@ -529,6 +529,16 @@ def test_large_cfg3_properties():
                                atol=3e-5 * float(s2.abs().max()))
     np.testing.assert_allclose(rx.sum(0).cpu().numpy(), Xw.sum(0).cpu().numpy(), rtol=5e-5,
                                atol=3e-5 * float(s1.abs().max()))
+    # the default route of the local step at this size: responsibilities as operand tiles, CTA-pair kernel --
+    # same statistics as the float32-R kernel to the level of the BF16 split, component by component
+    rsplit, lse2, total2 = S.responsibilities_split(logits)
+    np.testing.assert_allclose(lse2.cpu().numpy(), lse.cpu().numpy(), rtol=1e-5, atol=1e-3)
+    assert abs(float(total2) - float(total)) <= 1e-6 * abs(float(total))
+    nk2, rx2, rxx2 = S.weighted_suffstats_split(X, rsplit, k)
+    np.testing.assert_allclose(nk2.cpu().numpy(), nk.cpu().numpy(), rtol=2e-5)
+    scale = float(rxx.abs().max())
+    np.testing.assert_allclose(rxx2.cpu().numpy(), rxx.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale)
+    np.testing.assert_allclose(rx2.cpu().numpy(), rx.cpu().numpy(), rtol=1e-4, atol=2e-5 * float(rx.abs().max()))
 
 
 def test_full_size_cfg3_properties():
