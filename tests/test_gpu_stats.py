@@ -703,7 +703,7 @@ def test_entry_points_reject_bad_arguments_and_small_workspaces():
     Z = torch.empty(2048, 64, device='cuda')
     st = lib.bb_rowproj(X.data_ptr(), W.data_ptr(), 2048, 250, 64, Z.data_ptr(), ws.data_ptr(), ws.numel(), stream)
     assert st == 3                                                         # BB_ERR_UNSUPPORTED
-    st = lib.bb_mixture_logits(X.data_ptr(), X.data_ptr(), X.data_ptr(), X.data_ptr(), 2048, 40, 8, 0, Z.data_ptr(),
+    st = lib.bb_mixture_logits(X.data_ptr(), X.data_ptr(), X.data_ptr(), X.data_ptr(), 2048, 36, 8, 0, Z.data_ptr(),
                                None, None, ws.data_ptr(), ws.numel(), stream)
     assert st == 3
     st = lib.bb_logistic_reparam_pass(X.data_ptr(), y.data_ptr(), W.data_ptr(), 2048, 250, 64, out.data_ptr(),
