@@ -362,8 +362,14 @@ BB_API int bb_comm_destroy(bb_comm* comm);
 
 /* bb_gaussian_pass: the whole cfg2 step -- statistics of base.py:328-332 for core.py:41-44, their
  * combine over the ranks, and the expected log-likelihood of base.py:25-100 -- as ONE kernel launch
- * per step on any number of GPUs (csrc/suffstats_sm100.cu: tcgen05 pass, grid barrier, per-slice
- * reduction, per-slice push into the peers' receive buffers + flags, ELBO term by the last CTA).
+ * per step on any number of GPUs (csrc/suffstats_sm100.cu: tcgen05 pass with dynamically claimed tiles,
+ * L2 float64 reductions of the CTAs' partial statistics, then the LAST CTA pushes the rank's payload into
+ * the peers' receive buffers + one flag per peer, sums the world's slots in rank order and evaluates the
+ * ELBO term).  Back-to-back runs of one handle are launched with programmatic stream serialization: the
+ * next run streams its rows while this run's last CTA finishes (it touches the shared state only after
+ * griddepcontrol.wait), so consecutive runs must not depend on each other's OUTPUTS through device memory
+ * other than by stream order of other kernels in between -- which is the ordinary stream contract: a
+ * consumer kernel enqueued between two runs sees the first run complete.  Assumes one rank per GPU.
  * The handle owns its workspace (the only device allocation; one handle = one stream at a time).
  *   d                    4 <= d <= 64, d % 4 == 0;
  *   attach_peers         optional (world > 1): peer_recv = bb_gaussian_pass_peer_bytes' recv_bytes per
