@@ -43,6 +43,14 @@ def main():
     Z = ref.dot(D, W.T)
     out['cfg5_loglik'] = run(ref.sum(b.dimshuffle(0, 'x') * Z - ref.log(1 + ref.exp(Z)), axis=0), D='X5', W='W5', b='b5')
     out['cfg5_grad'] = run(ref.dot(D.T, b.dimshuffle(0, 'x') - (1 + ref.exp(-1 * Z)) ** -1), D='X5', W='W5', b='b5')
+    # cfg3 at K = 256: responsibilities by the reference's own spelling of the softmax (algebra.py:1435-1448), then the
+    # three statistics plans over them; n = 2048, d = 16 (components 0-15 and 240-255 of sum r x x^T are kept)
+    inp['R3b'] = run(ref.exp(Lg - ref.log(ref.sum(ref.exp(Lg), axis=1)).dimshuffle(0, 'x')), Lg='Lg3b')
+    out['cfg3b_nk'] = run(ref.sum(R, axis=0), R='R3b')
+    out['cfg3b_rx'] = run(ref.dot(R.T, D), R='R3b', D='X3b')
+    rxx_b = run(ref.einsum([(R, [('sum', 0), ('out', 0)]), (D, [('sum', 0), ('out', 1)]),
+                            (D, [('sum', 0), ('out', 2)])], 3), R='R3b', D='X3b')
+    out['cfg3b_rxx_32'] = np.concatenate([rxx_b[:16], rxx_b[240:]], axis=0)
     path = os.path.join(ROOT, 'tests', 'golden', 'hot_kernels_reference.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %s' % (path, {k: v.shape for k, v in out.items()}))

@@ -21,4 +21,8 @@ def hot_inputs():
     inp['X5'] = randn(2048, 128)                                  # cfg5
     inp['W5'] = (randn(64, 128) / np.sqrt(128.0)).astype(np.float32)
     inp['b5'] = (rng.rand(2048) < 0.5).astype(np.float32)
+    # cfg3 at K = 256 (the extent the pre-split / CTA-pair statistics route serves); appended last so that the
+    # inputs above keep their values
+    inp['X3b'] = randn(2048, 16) + randn(256, 16)[rng.randint(256, size=2048)] * 2.0
+    inp['Lg3b'] = (randn(2048, 256) * 2.5).astype(np.float32)
     return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in inp.items()}

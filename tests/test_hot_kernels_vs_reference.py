@@ -47,6 +47,15 @@ def _check_all(results):
     _close('cfg4_yty', results['cfg4_yty'], float(t4.astype('f8') @ t4.astype('f8')))
     _close('cfg5_loglik', results['cfg5_loglik'], float(X5.shape[0]))
     _close('cfg5_grad', results['cfg5_grad'], np.outer(_norms(X5, 0), np.full(64, np.sqrt(X5.shape[0]))))
+    # cfg3 at K = 256: responsibilities by the reference's own softmax spelling, then its statistics plans
+    X3b = INPUTS['X3b'].astype('f8')
+    Lg = INPUTS['Lg3b'].astype('f8')
+    R3b = np.exp(Lg - np.log(np.exp(Lg).sum(1, keepdims=True)))
+    r3b, x2b = np.sqrt((R3b ** 2).sum(0)), R3b.T @ (X3b ** 2)
+    keep = np.r_[0:16, 240:256]
+    _close('cfg3b_nk', results['cfg3b_nk'], r3b * np.sqrt(R3b.shape[0]))
+    _close('cfg3b_rx', results['cfg3b_rx'], np.outer(r3b, _norms(X3b, 0)))
+    _close('cfg3b_rxx_32', results['cfg3b_rxx_32'], np.sqrt(np.einsum('kd,ke->kde', x2b, x2b))[keep])
 
 
 def test_oracle_matches_the_reference_outputs_at_kernel_sizes():
@@ -59,9 +68,12 @@ def test_oracle_matches_the_reference_outputs_at_kernel_sizes():
     Z = X5 @ W5.T
     loglik = (b5[:, None] * Z - np.logaddexp(0.0, Z)).sum(0)
     grad = X5.T @ (b5[:, None] - 1.0 / (1.0 + np.exp(-Z)))
+    log_rb, _ = O.log_responsibilities(INPUTS['Lg3b'].astype(np.float64))
+    nkb, rxb, rxxb = O.weighted_suffstats(INPUTS['X3b'].astype(np.float64), np.exp(log_rb))
     _check_all({'cfg2_sxx': s2, 'cfg2_sx': s1, 'cfg3_nk': nk, 'cfg3_rx': rx, 'cfg3_rxx': rxx,
                 'cfg3_logsoftmax_rows96': log_r[:96], 'cfg4_xtx_rows32': xtx[:32], 'cfg4_xty': xty, 'cfg4_yty': yty,
-                'cfg5_loglik': loglik, 'cfg5_grad': grad})
+                'cfg5_loglik': loglik, 'cfg5_grad': grad,
+                'cfg3b_nk': nkb, 'cfg3b_rx': rxb, 'cfg3b_rxx_32': np.concatenate([rxxb[:16], rxxb[240:]], axis=0)})
 
 
 @pytest.mark.gpu
@@ -75,7 +87,12 @@ def test_hot_kernels_match_the_reference_outputs():
     log_r, _, _ = S.log_responsibilities(dev['Lg3'])                          # vectorised log-softmax (cfg3b)
     xtx, xty, yty = S.regression_suffstats(dev['X4'], dev['t4'])              # CTA-pair Gram kernel (cfg4)
     loglik, grad = S.logistic_reparam_stats(dev['X5'], dev['b5'], dev['W5'])  # single-kernel logistic pass (cfg5)
+    # cfg3 at K = 256: softmax written as BF16 operand tiles, statistics on CTA pairs (the default local-step route)
+    rsplit, _, _ = S.responsibilities_split(dev['Lg3b'])
+    nkb, rxb, rxxb = S.weighted_suffstats_split(dev['X3b'], rsplit, 256)
     _check_all({'cfg2_sxx': host(s2), 'cfg2_sx': host(s1), 'cfg3_nk': host(nk), 'cfg3_rx': host(rx),
                 'cfg3_rxx': host(rxx), 'cfg3_logsoftmax_rows96': host(log_r)[:96],
                 'cfg4_xtx_rows32': host(xtx)[:32], 'cfg4_xty': host(xty), 'cfg4_yty': host(yty).reshape(()),
-                'cfg5_loglik': host(loglik), 'cfg5_grad': host(grad)})
+                'cfg5_loglik': host(loglik), 'cfg5_grad': host(grad),
+                'cfg3b_nk': host(nkb), 'cfg3b_rx': host(rxb),
+                'cfg3b_rxx_32': np.concatenate([host(rxxb)[:16], host(rxxb)[240:]], axis=0)})
