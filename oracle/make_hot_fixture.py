@@ -51,6 +51,8 @@ def main():
     rxx_b = run(ref.einsum([(R, [('sum', 0), ('out', 0)]), (D, [('sum', 0), ('out', 1)]),
                             (D, [('sum', 0), ('out', 2)])], 3), R='R3b', D='X3b')
     out['cfg3b_rxx_32'] = np.concatenate([rxx_b[:16], rxx_b[240:]], axis=0)
+    # cfg4 at D = 136 (not a multiple of 256: the CTA-pair Gram kernel pads the feature axis on chip)
+    out['cfg4b_xtx'] = run(ref.dot(D.T, D), D='X4b')
     path = os.path.join(ROOT, 'tests', 'golden', 'hot_kernels_reference.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %s' % (path, {k: v.shape for k, v in out.items()}))

@@ -25,4 +25,5 @@ def hot_inputs():
     # inputs above keep their values
     inp['X3b'] = randn(2048, 16) + randn(256, 16)[rng.randint(256, size=2048)] * 2.0
     inp['Lg3b'] = (randn(2048, 256) * 2.5).astype(np.float32)
+    inp['X4b'] = randn(1536, 136) * 0.8 + 0.1                     # cfg4 at a D the Gram kernel serves through zero padding
     return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in inp.items()}

@@ -56,6 +56,8 @@ def _check_all(results):
     _close('cfg3b_nk', results['cfg3b_nk'], r3b * np.sqrt(R3b.shape[0]))
     _close('cfg3b_rx', results['cfg3b_rx'], np.outer(r3b, _norms(X3b, 0)))
     _close('cfg3b_rxx_32', results['cfg3b_rxx_32'], np.sqrt(np.einsum('kd,ke->kde', x2b, x2b))[keep])
+    c4b = _norms(INPUTS['X4b'], 0)
+    _close('cfg4b_xtx', results['cfg4b_xtx'], np.outer(c4b, c4b))
 
 
 def test_oracle_matches_the_reference_outputs_at_kernel_sizes():
@@ -73,7 +75,8 @@ def test_oracle_matches_the_reference_outputs_at_kernel_sizes():
     _check_all({'cfg2_sxx': s2, 'cfg2_sx': s1, 'cfg3_nk': nk, 'cfg3_rx': rx, 'cfg3_rxx': rxx,
                 'cfg3_logsoftmax_rows96': log_r[:96], 'cfg4_xtx_rows32': xtx[:32], 'cfg4_xty': xty, 'cfg4_yty': yty,
                 'cfg5_loglik': loglik, 'cfg5_grad': grad,
-                'cfg3b_nk': nkb, 'cfg3b_rx': rxb, 'cfg3b_rxx_32': np.concatenate([rxxb[:16], rxxb[240:]], axis=0)})
+                'cfg3b_nk': nkb, 'cfg3b_rx': rxb, 'cfg3b_rxx_32': np.concatenate([rxxb[:16], rxxb[240:]], axis=0),
+                'cfg4b_xtx': O.regression_suffstats(INPUTS['X4b'].astype(np.float64), np.zeros(1536))[0]})
 
 
 @pytest.mark.gpu
@@ -95,4 +98,5 @@ def test_hot_kernels_match_the_reference_outputs():
                 'cfg4_xtx_rows32': host(xtx)[:32], 'cfg4_xty': host(xty), 'cfg4_yty': host(yty).reshape(()),
                 'cfg5_loglik': host(loglik), 'cfg5_grad': host(grad),
                 'cfg3b_nk': host(nkb), 'cfg3b_rx': host(rxb),
-                'cfg3b_rxx_32': np.concatenate([host(rxxb)[:16], host(rxxb)[240:]], axis=0)})
+                'cfg3b_rxx_32': np.concatenate([host(rxxb)[:16], host(rxxb)[240:]], axis=0),
+                'cfg4b_xtx': host(S.regression_suffstats(dev['X4b'])[0])})
