@@ -105,6 +105,33 @@ def cfg3_full():
           % (n, ms, n / ms / 1e3), flush=True)
 
 
+def cfg3_full_slabs():
+    """BASELINE cfg3 at its full extent (N = 64 Mi rows resident, K = 256, D = 64) through the default local step,
+    in slabs of 8 Mi rows (the logits and operand-tile buffers are 8 GiB each and are reused); the statistics of the
+    slabs add up on the device."""
+    n, d, k, slab = 1 << 26, 64, 256, 1 << 23
+    X = torch.randn(n, d, device='cuda')
+    step = P.GmmStep()
+    U = (torch.eye(d, device='cuda') * 1.2).repeat(k, 1, 1).contiguous()
+    t = torch.randn(k, d, device='cuda')
+    c = torch.randn(k, device='cuda')
+
+    def full_pass():
+        tot = None
+        for lo in range(0, n, slab):
+            out = step.local_step(X[lo:lo + slab], U, t, c)
+            part = (out['nk'], out['rx'], out['rxx'], out['sum_lse'])
+            del out
+            tot = part if tot is None else tuple(a + b for a, b in zip(tot, part))
+        return tot
+    full_pass()
+    torch.cuda.synchronize()
+    ms = timeit(full_pass, reps=2, warm=0)
+    nk = full_pass()[0]
+    print('cfg3 full size, default local step in 8 Mi-row slabs (N = %d): %.1f ms  %.2f M rows/s  (sum N_k / N = %.6f)'
+          % (n, ms, n / ms / 1e3, float(nk.sum()) / n), flush=True)
+
+
 def loops():
     """Whole iterations built from the update kernels (bayesic_b200/updates.py)."""
     import bayesic_b200.updates as U
@@ -132,6 +159,6 @@ def loops():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['cfg4', 'cfg5', 'cfg3', 'loops']
+    which = sys.argv[1:] or ['cfg4', 'cfg5', 'cfg3', 'loops']      # also: cfg3_full, cfg3_full_slabs
     for name in which:
         globals()[name]()
