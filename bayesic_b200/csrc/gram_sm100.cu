@@ -19,7 +19,9 @@
 //   * error-compensated BF16 ("BF16x3"): x = b1 + b2 + O(2^-17 x), b1 = bf16(x),
 //     b2 = bf16(x - b1), and  x_d x_e ~= b1_d b1_e + b1_d b2_e + b2_d b1_e  (dropped terms
 //     <= 2^-16 relative, unbiased because both splits round to nearest).  Three kind::f16 MMAs
-//     cost 1.5x one TF32 pass (3xTF32 would cost 3x);
+//     cost 1.5x one TF32 pass (3xTF32 would cost 3x).  A DIAGONAL block issues two: its operand tile
+//     holds 2 b2 (exact), S = b1^T b1 + b1^T (2 b2) = P + 2 Q, and the finalize takes (S + S^T) / 2 =
+//     P + Q + Q^T -- the same three products;
 //   * no fp32 staging: 16 converter warps load X with coalesced 128-bit loads straight into
 //     registers (each warp group two stages ahead), split, and store b1/b2 into shared memory in the
 //     UMMA MN-major SWIZZLE_128B canonical layout (the data axis is the MMA K axis, so X's
@@ -40,6 +42,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -110,16 +113,24 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "memory");
 }
 
-// x = b1 + b2 + O(2^-17 x): four consecutive features -> two packed bf16x2 words each
+// x = b1 + b2 + O(2^-17 x): four consecutive features -> two packed bf16x2 words each.  kTwice stores 2 b2
+// instead of b2 (exact: a power of two) -- the diagonal blocks' second product, see the MMA issuer.
+template <bool kTwice = false>
 __device__ __forceinline__ void split_bf16(const float4& x, uint32_t (&b1)[2], uint32_t (&b2)[2]) {
   __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y);
   __nv_bfloat162 p1 = __floats2bfloat162_rn(x.z, x.w);
   b1[0] = *reinterpret_cast<uint32_t*>(&p0);
   b1[1] = *reinterpret_cast<uint32_t*>(&p1);
-  const float rx = x.x - __uint_as_float(b1[0] << 16);
-  const float ry = x.y - __uint_as_float(b1[0] & 0xFFFF0000u);
-  const float rz = x.z - __uint_as_float(b1[1] << 16);
-  const float rw = x.w - __uint_as_float(b1[1] & 0xFFFF0000u);
+  float rx = x.x - __uint_as_float(b1[0] << 16);
+  float ry = x.y - __uint_as_float(b1[0] & 0xFFFF0000u);
+  float rz = x.z - __uint_as_float(b1[1] << 16);
+  float rw = x.w - __uint_as_float(b1[1] & 0xFFFF0000u);
+  if (kTwice) {
+    rx += rx;
+    ry += ry;
+    rz += rz;
+    rw += rw;
+  }
   __nv_bfloat162 q0 = __floats2bfloat162_rn(rx, ry);
   __nv_bfloat162 q1 = __floats2bfloat162_rn(rz, rw);
   b2[0] = *reinterpret_cast<uint32_t*>(&q0);
@@ -144,7 +155,7 @@ struct ConvArgs {
 // stage periods to land and no load is in flight across the fence of the arrive (a release with
 // loads outstanding stalls until they return -- measured: 3.6x slower).  Lane l holds A features
 // [4l, 4l+4) and B features [4l, 4l+4) of this CTA's 128-feature halves.
-// kAlias: diagonal block, the B tiles ARE the A tiles (nothing loaded or stored for B).
+// kAlias: diagonal block, the B tiles ARE the A tiles (nothing loaded or stored for B); the b2 tile holds 2 b2.
 // kXty:   also accumulate X^T y (and y^T y) for this CTA's A features.
 // The loop is issue-bound (the first version spent 349 instructions per 4 rows, 698 issue cycles
 // per stage against a 768-cycle MMA budget), hence the hoisted pointers, the bounds-check-free
@@ -178,9 +189,12 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
   const int64_t step = static_cast<int64_t>(kConvGroups) * kStageRows * d;
   const bool do_yty = kXty && ca.want_yty && lane == 0;
 
-  float4 ra[kRowsPerWarp], rb[kRowsPerWarp];
-  float ry[kRowsPerWarp];
-  auto load_rows = [&]() {
+  // register buffers of loaded rows: one set for the off-diagonal blocks (A and B rows), kDepth = 2 sets for the
+  // diagonal ones (A rows only, so the second set is free) -- their loads are issued two of the warp's stages ahead
+  constexpr int kDepth = kAlias ? 2 : 1;
+  float4 ra[kDepth][kRowsPerWarp], rb[kAlias ? 1 : kRowsPerWarp];
+  float ry[kDepth][kRowsPerWarp];
+  auto load_rows = [&](float4 (&ra)[kRowsPerWarp], float (&ry)[kRowsPerWarp]) {
     if (row0 + kRowsPerWarp <= ca.n) {          // whole group of rows in range: no per-row checks
 #pragma unroll
       for (int j = 0; j < kRowsPerWarp; ++j) {
@@ -218,8 +232,9 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
   float yty_f = 0.f;
   int since_flush = 0;
 
-  if (group < ca.n_iters) load_rows();
-  for (int it = group; it < ca.n_iters; it += kConvGroups) {
+  // one stage: convert the rows in (ra, ry), publish, and refill the same registers with the rows kDepth of this
+  // warp's stages further on
+  auto convert_stage = [&](int it, float4 (&ra)[kRowsPerWarp], float (&ry)[kRowsPerWarp]) {
     const int s = it % kStages;
     ptx::mbar_wait(&sm.empty[s], ((it / kStages) & 1) ^ 1);
     const uint32_t stage_addr = stage0 + s * kStageBytes;
@@ -227,7 +242,7 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
     for (int j = 0; j < kRowsPerWarp; ++j) {
       const uint32_t addr = stage_addr + soff[j];
       uint32_t b1[2], b2[2];
-      split_bf16(ra[j], b1, b2);
+      split_bf16<kAlias>(ra[j], b1, b2);
       sts_u2(addr, b1[0], b1[1]);
       sts_u2(addr + kTileBytes, b2[0], b2[1]);
       if (!kAlias) {
@@ -243,12 +258,12 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
         yty_f = fmaf(ry[j], ry[j], yty_f);
       }
     }
-    const bool more = it + kConvGroups < ca.n_iters;
-    if (ca.early && more) load_rows();
+    const bool more = it + kDepth * kConvGroups < ca.n_iters;
+    if (ca.early && more) load_rows(ra, ry);
     fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster_relaxed(&sm.full[s], 0);
-    if (!ca.early && more) load_rows();
+    if (!ca.early && more) load_rows(ra, ry);
     if (kXty && ++since_flush == kXtyFlushIters) {     // fp32 over 32 rows, then float64 (DADD is slow)
       since_flush = 0;
 #pragma unroll
@@ -259,6 +274,15 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
       yty_acc += static_cast<double>(yty_f);
       yty_f = 0.f;
     }
+  };
+
+#pragma unroll
+  for (int b = 0; b < kDepth; ++b)
+    if (group + b * kConvGroups < ca.n_iters) load_rows(ra[b], ry[b]);
+  for (int it = group; it < ca.n_iters; it += kDepth * kConvGroups) {
+#pragma unroll
+    for (int b = 0; b < kDepth; ++b)
+      if (it + b * kConvGroups < ca.n_iters) convert_stage(it + b * kConvGroups, ra[b], ry[b]);
   }
   if (kXty) {
 #pragma unroll
@@ -267,35 +291,44 @@ __device__ __forceinline__ void converter_loop(SmemLayout& sm, const ConvArgs& c
   }
 }
 
-// grid = 2 * n_blocks * n_splits CTAs; pair p = blockIdx.x / 2: block = p % n_blocks,
-// split = p / n_blocks (pairs of one split walk the same rows at the same time -> L2 reuse).
+// grid = 2 * (nb * splits_diag + n_off * splits_off) CTAs; pairs [0, nb * splits_diag) own the diagonal blocks
+// (block = p % nb, split = p / nb), the rest the off-diagonal ones in the same way: pairs of one split walk the
+// same rows at the same time -> L2 reuse.  A diagonal block costs two products per K step, an off-diagonal one
+// three, so the diagonal blocks get fewer, longer row ranges (GramGrid).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n, int d,
-                 int n_blocks, int n_splits, int ablate,
+                 int splits_diag, int splits_off, int ablate,
                  float* __restrict__ partial,          // [pair][2][256 cols][128 rows] fp32
-                 double* __restrict__ partial_xty,     // [split][d]
-                 double* __restrict__ partial_yty) {   // [split]
+                 double* __restrict__ partial_xty,     // [diagonal split][d]
+                 double* __restrict__ partial_yty) {   // [diagonal split]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
-  const int blk = pair % n_blocks;
-  const int split = pair / n_blocks;
-  // upper-triangle block index -> (i, j), row-major over i <= j
+  const int nb = (d + kBlock - 1) / kBlock;
+  const int n_off = nb * (nb - 1) / 2;
+  const bool diag = pair < nb * splits_diag;
   int2 ij;
-  {
-    const int nb = (d + kBlock - 1) / kBlock;
-    int i = 0, rem = blk;
-    while (rem >= nb - i) {
-      rem -= nb - i;
+  int split, n_splits;
+  if (diag) {
+    ij.x = ij.y = pair % nb;
+    split = pair / nb;
+    n_splits = splits_diag;
+  } else {
+    const int q = pair - nb * splits_diag;
+    split = q / n_off;
+    n_splits = splits_off;
+    // strict upper-triangle block index -> (i, j), row-major over i < j
+    int i = 0, rem = q % n_off;
+    while (rem >= nb - 1 - i) {
+      rem -= nb - 1 - i;
       ++i;
     }
     ij.x = i;
-    ij.y = i + rem;
+    ij.y = i + 1 + rem;
   }
-  const bool diag = ij.x == ij.y;
   const bool alias_b = diag;                       // diagonal block: the B tiles ARE the A tiles
   const int feat_a = ij.x * kBlock + static_cast<int>(rank) * kHalf;
   const int feat_b = ij.y * kBlock + static_cast<int>(rank) * kHalf;
@@ -306,6 +339,11 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
   const int n_iters = static_cast<int>(it_end - it_begin);
   const int64_t row_begin = it_begin * kStageRows;
 
+#ifdef BB_GRAM_TIMELINE
+  // developer timeline (variant build): every pair's leader prints its kind, stage count and duration
+  unsigned long long tl_begin = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_begin));
+#endif
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
@@ -332,12 +370,12 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
   if (warp < kConvWarps) {
     // ---------------- converter warps: global fp32 -> registers -> bf16 b1/b2 tiles ----------------
     ConvArgs ca;
-    ca.prefetch_iters = ablate >> 8;
+    ca.prefetch_iters = ablate >> 8;     // BB_GRAM_PREFETCH, default 0: L2 hints make it slower, from these warps or a dedicated one
     ca.early = (ablate & 128) == 0;      // default on (3.20 -> 3.08 ms at cfg4); BB_GRAM_ABLATE=128 restores loads-after-arrive
     ca.row_end = it_end * kStageRows < n ? it_end * kStageRows : n;
     ca.x = x; ca.y = y; ca.n = n; ca.d = d; ca.feat_a = feat_a; ca.feat_b = feat_b;
     ca.row_begin = row_begin; ca.n_iters = n_iters; ca.warp = warp; ca.lane = lane;
-    ca.want_yty = blk == 0 && rank == 0;
+    ca.want_yty = diag && ij.x == 0 && rank == 0;
     if (!diag) converter_loop<false, false>(sm, ca);
     else if (y == nullptr) converter_loop<true, false>(sm, ca);
     else converter_loop<true, true>(sm, ca);
@@ -401,6 +439,13 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
           const uint64_t b1 = alias_b ? a1 : ptx::make_smem_desc(base + 2 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
           const uint64_t b2 = alias_b ? a2 : ptx::make_smem_desc(base + 3 * kTileBytes, 4096, 1024, ptx::kLayoutSwizzle128B);
           if (ablate & 1) continue;
+          if (diag) {
+            // a1^T a1 + a1^T (2 a2) = P + 2 Q: the finalize takes (S + S^T) / 2 = P + Q + Q^T, i.e. the same three
+            // products as an off-diagonal block for two MMAs
+            mma_bf16_pair_a_fill(d_tmem, a1, a1, kIdesc, (first && ks == 0) ? 0u : 1u);
+            mma_bf16_pair_a_lastuse(d_tmem, a1, a2, kIdesc, 1u);
+            continue;
+          }
           if (!(ablate & 64)) {               // A-collector hints: the second MMA takes A = a1 from the collector buffer, not from
                                               // shared memory (measured 3.200 -> 3.15 ms at cfg4; BB_GRAM_ABLATE=64 switches it off)
             mma_bf16_pair_a_fill(d_tmem, a1, b1, kIdesc, (first && ks == 0) ? 0u : 1u);
@@ -424,59 +469,113 @@ gram_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int64
   if (y != nullptr && diag) {
     if (threadIdx.x < kHalf && feat_a + static_cast<int>(threadIdx.x) < d)
       partial_xty[static_cast<int64_t>(split) * d + feat_a + threadIdx.x] = sm.xty[threadIdx.x];
-    if (blk == 0 && rank == 0 && threadIdx.x == 0) partial_yty[split] = sm.yty;
+    if (ij.x == 0 && rank == 0 && threadIdx.x == 0) partial_yty[split] = sm.yty;
   }
   cluster_sync_all();          // the peer's shared memory / barriers stay alive until both are done
   if (warp == kMmaWarp) tmem_dealloc_pair(tmem, kTmemCols);
+#ifdef BB_GRAM_TIMELINE
+  if (threadIdx.x == 0 && rank == 0) {
+    unsigned long long tl_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_end));
+    printf("gram pair %3d %s (%d,%d) split %d/%d stages %d  begin %llu  us %.1f  ns/stage %.0f\n", pair,
+           diag ? "diag" : "off ", ij.x, ij.y, split, n_splits, n_iters, tl_begin % 100000000ull,
+           (tl_end - tl_begin) * 1e-3, n_iters > 0 ? static_cast<double>(tl_end - tl_begin) / n_iters : 0.0);
+  }
+#endif
 }
 
-// XtX[d,e] (float64, full symmetric matrix) = sum over splits of the upper-triangle block
-// partials; Xty / yty likewise.  One thread per output element.
+// XtX[d,e] (float64, full symmetric matrix) = sum over splits of the upper-triangle block partials (a diagonal
+// block holds S = P + 2 Q, its element is (S[r,c] + S[c,r]) / 2); Xty / yty likewise.  One thread per output element.
 __global__ void __launch_bounds__(256)
 gram_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ partial_xty,
-                     const double* __restrict__ partial_yty, int d, int n_blocks, int n_splits,
+                     const double* __restrict__ partial_yty, int d, int splits_diag, int splits_off,
                      double* __restrict__ xtx, double* __restrict__ xty, double* __restrict__ yty) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int nb = (d + kBlock - 1) / kBlock;
+  const int n_off = nb * (nb - 1) / 2;
   if (idx < static_cast<int64_t>(d) * d) {
     const int row = static_cast<int>(idx / d), col = static_cast<int>(idx % d);
     const int r = row < col ? row : col, c = row < col ? col : row;
     const int bi = r / kBlock, bj = c / kBlock;
-    const int blk = bi * nb - bi * (bi - 1) / 2 + (bj - bi);
     const int rr = r % kBlock, cc = c % kBlock;
+    auto at = [&](int64_t pair, int a, int b) {
+      return static_cast<double>(partial[((pair * 2 + a / kHalf) * kBlock + b) * kHalf + a % kHalf]);
+    };
     double acc = 0.0;
-    for (int s = 0; s < n_splits; ++s) {
-      const int64_t pair = static_cast<int64_t>(s) * n_blocks + blk;
-      acc += static_cast<double>(partial[((pair * 2 + rr / kHalf) * kBlock + cc) * kHalf + rr % kHalf]);
+    if (bi == bj) {
+      for (int s = 0; s < splits_diag; ++s) {
+        const int64_t pair = static_cast<int64_t>(s) * nb + bi;
+        acc += at(pair, rr, cc) + at(pair, cc, rr);
+      }
+      acc *= 0.5;
+    } else {
+      const int off = bi * (nb - 1) - bi * (bi - 1) / 2 + (bj - bi - 1);
+      for (int s = 0; s < splits_off; ++s)
+        acc += at(static_cast<int64_t>(nb) * splits_diag + static_cast<int64_t>(s) * n_off + off, rr, cc);
     }
     xtx[idx] = acc;
   }
   if (xty != nullptr && idx < d) {
     double acc = 0.0;
-    for (int s = 0; s < n_splits; ++s) acc += partial_xty[static_cast<int64_t>(s) * d + idx];
+    for (int s = 0; s < splits_diag; ++s) acc += partial_xty[static_cast<int64_t>(s) * d + idx];
     xty[idx] = acc;
   }
   if (yty != nullptr && idx == 0) {
     double acc = 0.0;
-    for (int s = 0; s < n_splits; ++s) acc += partial_yty[s];
+    for (int s = 0; s < splits_diag; ++s) acc += partial_yty[s];
     *yty = acc;
   }
 }
 
 struct GramGrid {
-  int nb, n_blocks, n_splits;
+  int nb, n_off, splits_diag, splits_off;
+  int64_t pairs() const { return static_cast<int64_t>(nb) * splits_diag + static_cast<int64_t>(n_off) * splits_off; }
 };
 
+// Row splits per block kind.  Default: the same number of splits for every block, so that all pairs of a split walk
+// the same rows at the same time (D = 1024: 7 x 10 = 70 pairs).  BB_GRAM_BALANCE=1 (timing experiments) weighs the
+// splits by MMA count instead -- a diagonal block issues 2 products per K step, an off-diagonal one 3; pick
+// (splits_diag, splits_off) with nb * sd + n_off * so <= SMs / 2 minimising max(2 / sd, 3 / so): D = 1024 gives
+// 4 x 6 + 6 x 8 = 72 pairs.  Measured SLOWER (3.46 against 2.87 ms): a pair's pace is ~630 ns per 32-row stage
+// whatever its MMA count (profiles/r02_gram_pair_timeline.txt), so the longer diagonal row ranges just take longer,
+// and the diagonal and off-diagonal read fronts no longer share X through L2.
 GramGrid plan_gram(int64_t n, int d) {
   GramGrid g;
   g.nb = (d + kBlock - 1) / kBlock;
-  g.n_blocks = g.nb * (g.nb + 1) / 2;
+  g.n_off = g.nb * (g.nb - 1) / 2;
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  const int64_t iters = (n + kStageRows - 1) / kStageRows;
-  int64_t splits = std::max<int64_t>(1, (sms / 2) / g.n_blocks);
-  splits = std::min<int64_t>(splits, std::max<int64_t>(1, iters));
-  g.n_splits = static_cast<int>(splits);
+  const int P = sms / 2;
+  const int64_t iters = std::max<int64_t>(1, (n + kStageRows - 1) / kStageRows);
+  const int cap = static_cast<int>(std::min<int64_t>(iters, P));
+  static const bool balance = getenv("BB_GRAM_BALANCE") && atoi(getenv("BB_GRAM_BALANCE")) != 0;
+  const int equal = std::max(1, std::min(cap, P / (g.nb + g.n_off)));
+  g.splits_diag = g.splits_off = equal;
+  if (!balance) return g;
+  if (g.n_off == 0) {
+    g.splits_diag = std::max(1, std::min(cap, P / g.nb));
+    return g;
+  }
+  int64_t best_num = 3, best_den = equal;            // cost of the equal plan: 3 / equal
+  for (int so = 1; so <= cap; ++so) {
+    const int left = P - g.n_off * so;
+    if (left < g.nb) break;
+    const int sd = std::min(cap, left / g.nb);
+    // cost = max(2 / sd, 3 / so) as a fraction
+    int64_t num = 2, den = sd;
+    if (3 * static_cast<int64_t>(sd) > 2 * static_cast<int64_t>(so)) {
+      num = 3;
+      den = so;
+    }
+    if (num * best_den < best_num * den) {
+      best_num = num;
+      best_den = den;
+      g.splits_off = so;
+      // no more diagonal splits than the cost needs: fewer read fronts over X
+      int sd_min = static_cast<int>((2 * den + num - 1) / num);
+      g.splits_diag = std::max(1, std::min(sd, sd_min));
+    }
+  }
   return g;
 }
 
@@ -488,9 +587,8 @@ bool gram_tc_supported(int64_t n, int d, const void* x) {
 
 int64_t gram_tc_workspace(int64_t n, int d) {
   const GramGrid g = plan_gram(n, d);
-  const int64_t pairs = static_cast<int64_t>(g.n_blocks) * g.n_splits;
-  return pairs * 2 * kHalf * kBlock * static_cast<int64_t>(sizeof(float)) +
-         static_cast<int64_t>(g.n_splits) * (d + 1) * static_cast<int64_t>(sizeof(double)) + 1024;
+  return g.pairs() * 2 * kHalf * kBlock * static_cast<int64_t>(sizeof(float)) +
+         static_cast<int64_t>(g.splits_diag) * (d + 1) * static_cast<int64_t>(sizeof(double)) + 1024;
 }
 
 // xtx [d, d] float64 (required); xty [d], yty [1] float64 (both or neither, with y).
@@ -510,26 +608,26 @@ int launch_gram_tc(const float* x, const float* y, int64_t n, int d, double* xtx
     return BB_ERR_WORKSPACE;
   }
   const GramGrid g = plan_gram(n, d);
-  const int64_t pairs = static_cast<int64_t>(g.n_blocks) * g.n_splits;
+  const int64_t pairs = g.pairs();
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
   float* partial = reinterpret_cast<float*>(ws);
   ws += pairs * 2 * kHalf * kBlock * sizeof(float);
   double* partial_xty = reinterpret_cast<double*>(ws);
-  ws += static_cast<int64_t>(g.n_splits) * d * sizeof(double);
+  ws += static_cast<int64_t>(g.splits_diag) * d * sizeof(double);
   double* partial_yty = reinterpret_cast<double*>(ws);
   const int smem_bytes = static_cast<int>(sizeof(SmemLayout));
   static SmemOptIn smem_opt_in_0;
   BB_CUDA_OK(smem_opt_in_0.ensure(gram_pair_kernel, smem_bytes));
   const int grid = static_cast<int>(2 * pairs);
   // developer ablation switches (timing experiments only; results are wrong when set)
-  static const int ablate = (getenv("BB_GRAM_ABLATE") ? atoi(getenv("BB_GRAM_ABLATE")) : 0) |
+  static const int ablate = ((getenv("BB_GRAM_ABLATE") ? atoi(getenv("BB_GRAM_ABLATE")) : 0) & 0xff) |
                             ((getenv("BB_GRAM_PREFETCH") ? atoi(getenv("BB_GRAM_PREFETCH")) : 0) << 8);
-  gram_pair_kernel<<<grid, kThreads, smem_bytes, stream>>>(x, y, n, d, g.n_blocks, g.n_splits, ablate, partial,
+  gram_pair_kernel<<<grid, kThreads, smem_bytes, stream>>>(x, y, n, d, g.splits_diag, g.splits_off, ablate, partial,
                                                            partial_xty, partial_yty);
   BB_CHECK_LAUNCH("gram_pair_kernel");
   const int64_t total = static_cast<int64_t>(d) * d;
   gram_finalize_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
-      partial, partial_xty, partial_yty, d, g.n_blocks, g.n_splits, xtx, xty, yty);
+      partial, partial_xty, partial_yty, d, g.splits_diag, g.splits_off, xtx, xty, yty);
   BB_CHECK_LAUNCH("gram_finalize_kernel");
   return BB_OK;
 }

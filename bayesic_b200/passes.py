@@ -36,12 +36,12 @@ def gram_issued_flops_per_row(d):
     """Tensor-core flops ``gram_pair_kernel`` really issues per data row (csrc/gram_sm100.cu): the
     upper-triangle 256 x 256 feature blocks, BF16x3 = three bf16 products per off-diagonal block and
     two per diagonal block (b1^T b2 + its transpose gives the third)."""
-    nb = d // 256
+    nb = -(-d // 256)
     off, diag = nb * (nb - 1) // 2, nb
     return 2.0 * 256 * 256 * (3 * off + GRAM_DIAGONAL_PRODUCTS * diag)
 
 
-GRAM_DIAGONAL_PRODUCTS = 3     # products issued on a diagonal block (kernels.h: kept in step with gram_sm100.cu)
+GRAM_DIAGONAL_PRODUCTS = 2     # products issued on a diagonal block: b1^T b1 + b1^T (2 b2), symmetrised in the finalize (gram_sm100.cu)
 
 
 def gmm_issued_flops_per_row(d, k, upper_triangular=True):
