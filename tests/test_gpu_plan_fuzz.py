@@ -1,0 +1,45 @@
+"""GPU parity of the plan executor on seeded random expressions (the recipes of tests/test_reference_crosscheck.py,
+plus the pointwise vocabulary): each is compiled with ``bayesic_b200.algebra`` -- the reference's entry point,
+``Expression.compile`` -> ``f(**inputs)`` (bayesic/algebra.py:50-58) -- run through the C-ABI on the device in
+float32, and compared with the float64 declared semantics and with the numpy evaluation of the very descriptor the
+executor was given.  Tolerance: rtol 1e-4 (north-star) with an absolute floor of 1e-5 of the largest entry, which
+is where float32 cancellation in a depth-3 product of 5 x 5 matrices sits."""
+import numpy as np
+import pytest
+
+from oracle.descriptor_eval import evaluate_descriptor
+from oracle.semantics import evaluate
+from tests.test_lowering_fuzz import _decorated, _expressions
+
+pytestmark = pytest.mark.gpu
+
+DATA = np.random.RandomState(11)
+INPUTS = {'X': DATA.randn(5, 5).astype(np.float32), 'Y': DATA.randn(5, 5).astype(np.float32),
+          'x': DATA.randn(5).astype(np.float32), 'y': DATA.randn(5).astype(np.float32)}
+
+
+def _check(e):
+    used = {k: INPUTS[k] for k in e.input_types}
+    fn = e.compile()
+    got = np.asarray(fn(**used), dtype=np.float64)
+    want = np.asarray(evaluate(e, used), dtype=np.float64)
+    assert got.shape == want.shape, repr(e)
+    atol = 1e-5 * max(1.0, float(np.abs(want).max()) if want.size else 1.0)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=atol, err_msg=repr(e))
+    low = fn.plan.lowered
+    arrays = [used[n] if n else low.bound_constants[i] for i, n in enumerate(low.input_names)]
+    (desc_val,) = evaluate_descriptor(low.nodes, low.outputs, arrays)
+    np.testing.assert_allclose(got, np.asarray(desc_val, dtype=np.float64), rtol=1e-4, atol=atol, err_msg=repr(e))
+    return fn
+
+
+def test_random_expressions_on_the_device():
+    launched = 0
+    for e in _expressions(606, 60, 3):
+        launched += _check(e).plan.last_launches >= 1
+    assert launched >= 30           # a recipe can be a bare variable (a copy, no kernel); most launch kernels
+
+
+def test_random_pointwise_expressions_on_the_device():
+    for e in _decorated(707, 40):
+        _check(e)
