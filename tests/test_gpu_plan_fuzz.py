@@ -43,3 +43,22 @@ def test_random_expressions_on_the_device():
 def test_random_pointwise_expressions_on_the_device():
     for e in _decorated(707, 40):
         _check(e)
+
+
+def test_random_multi_output_plans_on_the_device():
+    """groups of three expressions compiled as ONE plan (compile_many): shared sub-trees, several outputs, and a
+    second call on the same handle (the host fast path replays its CUDA graph) give the same values"""
+    from bayesic_b200.backend.compiled import compile_many
+    exprs = _expressions(808, 45, 3)
+    for i in range(0, len(exprs), 3):
+        group = exprs[i:i + 3]
+        names = sorted(set().union(*[set(e.input_types) for e in group]))
+        used = {k: INPUTS[k] for k in names}
+        fn = compile_many(group)
+        first = [np.asarray(v, dtype=np.float64) for v in fn(**used)]
+        second = [np.asarray(v, dtype=np.float64) for v in fn(**used)]
+        for e, g, g2 in zip(group, first, second):
+            want = np.asarray(evaluate(e, {k: INPUTS[k] for k in e.input_types}), dtype=np.float64)
+            atol = 1e-5 * max(1.0, float(np.abs(want).max()) if want.size else 1.0)
+            np.testing.assert_allclose(g, want, rtol=1e-4, atol=atol, err_msg=repr(e))
+            np.testing.assert_array_equal(g, g2)
