@@ -18,13 +18,14 @@ INPUTS = {'X': DATA.randn(5, 5).astype(np.float32), 'Y': DATA.randn(5, 5).astype
           'x': DATA.randn(5).astype(np.float32), 'y': DATA.randn(5).astype(np.float32)}
 
 
-def _check(e):
-    used = {k: INPUTS[k] for k in e.input_types}
+def _check(e, inputs=None, floor=1e-5):
+    inputs = INPUTS if inputs is None else inputs
+    used = {k: inputs[k] for k in e.input_types}
     fn = e.compile()
     got = np.asarray(fn(**used), dtype=np.float64)
     want = np.asarray(evaluate(e, used), dtype=np.float64)
     assert got.shape == want.shape, repr(e)
-    atol = 1e-5 * max(1.0, float(np.abs(want).max()) if want.size else 1.0)
+    atol = floor * max(1.0, float(np.abs(want).max()) if want.size else 1.0)
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=atol, err_msg=repr(e))
     low = fn.plan.lowered
     arrays = [used[n] if n else low.bound_constants[i] for i, n in enumerate(low.input_names)]
@@ -62,3 +63,13 @@ def test_random_multi_output_plans_on_the_device():
             atol = 1e-5 * max(1.0, float(np.abs(want).max()) if want.size else 1.0)
             np.testing.assert_allclose(g, want, rtol=1e-4, atol=atol, err_msg=repr(e))
             np.testing.assert_array_equal(g, g2)
+
+
+def test_random_expressions_on_the_device_at_a_ragged_extent():
+    """the same recipes on 33 x 33 operands: extents that are no multiple of any tile edge of the generic kernels
+    (absolute floor 1e-4 of the largest entry: three chained float32 products of 33 terms)"""
+    data = np.random.RandomState(12)
+    inputs = {'X': (data.randn(33, 33) / 6).astype(np.float32), 'Y': (data.randn(33, 33) / 6).astype(np.float32),
+              'x': data.randn(33).astype(np.float32), 'y': data.randn(33).astype(np.float32)}
+    for e in _expressions(909, 40, 3):
+        _check(e, inputs, floor=1e-4)
